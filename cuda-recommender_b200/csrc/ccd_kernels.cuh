@@ -1,0 +1,56 @@
+// ccd_kernels.cuh — launch interface of the CCD++ sweeps (ccd_kernels.cu).
+#pragma once
+#include "layout.cuh"
+
+namespace mf {
+
+// sweep mode bits
+enum : int {
+    kSub = 1,     // residual -= g_old[idx] * s_old[seg]
+    kAdd = 2,     // residual += g_add[idx] * s_add[seg]
+    kSolve = 4,   // accumulate (g, h) against g_new
+    kAddSep = 8,  // the add-back gathers a vector other than g_new (CSR side of the fused schedule)
+};
+
+struct PanelSweepArgs {
+    const uint16_t* idx16;
+    float* val;
+    const WorkItem* items;
+    const uint32_t* cta_item_ptr;
+    const uint32_t* panel_item_ptr;
+    int npanels;
+    uint32_t panel_rows;
+    int64_t gdim;
+    int64_t seg_offset;   // global id of local segment 0 (indexes s_add / s_old)
+    const float* g_new;   // gathered factor for the solve (and the add-back unless kAddSep)
+    const float* g_add;   // gathered factor for the add-back when kAddSep
+    const float* g_old;   // gathered factor of the rank being subtracted
+    const float* s_add;   // per-segment factor for the add-back (full-length vector)
+    const float* s_old;   // per-segment factor of the rank being subtracted
+    float2* partials;
+};
+
+struct DirectSweepArgs {
+    int64_t nseg;
+    const uint32_t* ptr;
+    const uint32_t* idx;
+    float* val;
+    int64_t seg_offset;
+    const float* g_new;
+    const float* g_add;
+    const float* g_old;
+    const float* s_add;
+    const float* s_old;
+    float lambda;
+    int nmf;
+    float* out;  // already offset to this shard's first segment
+};
+
+int panel_sweep_vectors(int mode);
+size_t panel_sweep_smem(int mode, int panel_rows);
+int panel_sweep(int mode, const PanelSweepArgs& a, int ncta, int threads, cudaStream_t st);
+int panel_finalize(int64_t nseg, const uint32_t* slot_ptr, const float2* partials, const uint32_t* seg_ptr, float lambda,
+                   int nmf, float* out, cudaStream_t st);
+int direct_sweep(int mode, const DirectSweepArgs& a, int sm_count, cudaStream_t st);
+
+}  // namespace mf

@@ -1,0 +1,128 @@
+// dist.cu — multi-GPU exchange: one process per GPU, NCCL over NVLink 5 / NVSwitch.
+//
+// The reference is single-GPU (cudaSetDevice(0), cuda_src/CCD_CUDA.cu:170, ALS_CUDA.cu:189); the
+// sharding is the north star's: GPU r keeps CSR row block r and CSC column block r (nnz-balanced),
+// every GPU keeps full-length factor vectors, and the block of u_t / v_t (CCD++) or W / H (ALS) a GPU
+// has just solved is all-gathered in place.  Blocks are unequal (nnz-balanced, not row-balanced), so
+// the gather is a grouped set of ncclBroadcast calls, one per owner, which NCCL fuses into one launch.
+//
+// NCCL is bound at run time (dlopen of libnccl.so.2) so the library loads, and single-GPU sessions
+// run, on a box without NCCL, and so that inside a torch process the already-loaded NCCL is shared.
+#include <dlfcn.h>
+#include <string.h>
+
+#include "session.cuh"
+
+namespace mf {
+namespace {
+
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+enum { ncclSuccess = 0 };
+enum { ncclFloat32 = 7 };  // ncclDataType_t (nccl.h): int8 0, uint8 1, int32 2, uint32 3, int64 4, uint64 5, half 6, float 7
+
+struct Api {
+    void* handle = nullptr;
+    int (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    int (*CommDestroy)(ncclComm_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    int (*Broadcast)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+
+Api g_api;
+
+int load_api() {
+    if (g_api.handle) return MF_OK;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    void* h = nullptr;
+    for (const char* n : names) {
+        h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (h) break;
+    }
+    if (!h) {
+        set_error("NCCL not found (dlopen libnccl.so.2): %s", dlerror());
+        return MF_ERR_NCCL;
+    }
+    Api a;
+    a.handle = h;
+#define MF_SYM(field, name)                                               \
+    *(void**)(&a.field) = dlsym(h, name);                                 \
+    if (!a.field) { set_error("NCCL symbol %s missing", name); return MF_ERR_NCCL; }
+    MF_SYM(GetUniqueId, "ncclGetUniqueId")
+    MF_SYM(CommInitRank, "ncclCommInitRank")
+    MF_SYM(CommDestroy, "ncclCommDestroy")
+    MF_SYM(GroupStart, "ncclGroupStart")
+    MF_SYM(GroupEnd, "ncclGroupEnd")
+    MF_SYM(Broadcast, "ncclBroadcast")
+    MF_SYM(GetErrorString, "ncclGetErrorString")
+#undef MF_SYM
+    g_api = a;
+    return MF_OK;
+}
+
+#define MF_NCCL(expr)                                                                             \
+    do {                                                                                          \
+        int _r = (expr);                                                                          \
+        if (_r != ncclSuccess) {                                                                  \
+            set_error("NCCL error %d at %s:%d: %s", _r, __FILE__, __LINE__, g_api.GetErrorString(_r)); \
+            return MF_ERR_NCCL;                                                                   \
+        }                                                                                         \
+    } while (0)
+
+}  // namespace
+
+struct Dist {
+    ncclComm_t comm = nullptr;
+    int rank = 0, nranks = 1;
+};
+
+int dist_unique_id(void* id128) {
+    MF_REQUIRE(id128 != nullptr, "NULL argument");
+    MF_TRY(load_api());
+    ncclUniqueId id;
+    MF_NCCL(g_api.GetUniqueId(&id));
+    memcpy(id128, &id, sizeof(id));
+    return MF_OK;
+}
+
+int dist_create(Dist** out, int rank, int nranks, const void* id128, int device) {
+    MF_TRY(load_api());
+    MF_CUDA(cudaSetDevice(device));
+    ncclUniqueId id;
+    memcpy(&id, id128, sizeof(id));
+    Dist* d = new Dist();
+    d->rank = rank;
+    d->nranks = nranks;
+    int r = g_api.CommInitRank(&d->comm, nranks, id, rank);
+    if (r != ncclSuccess) {
+        set_error("ncclCommInitRank failed (%d): %s", r, g_api.GetErrorString(r));
+        delete d;
+        return MF_ERR_NCCL;
+    }
+    *out = d;
+    return MF_OK;
+}
+
+int dist_destroy(Dist* d) {
+    if (!d) return MF_OK;
+    if (d->comm) g_api.CommDestroy(d->comm);
+    delete d;
+    return MF_OK;
+}
+
+int dist_allgather_blocks(Dist* d, float* vec, const std::vector<int64_t>& bound, int64_t unit, cudaStream_t st) {
+    if (!d || d->nranks <= 1) return MF_OK;
+    MF_NCCL(g_api.GroupStart());
+    for (int r = 0; r < d->nranks; ++r) {
+        const int64_t lo = bound[r] * unit, n = (bound[r + 1] - bound[r]) * unit;
+        if (n <= 0) continue;
+        MF_NCCL(g_api.Broadcast(vec + lo, vec + lo, (size_t)n, ncclFloat32, r, d->comm, st));
+    }
+    MF_NCCL(g_api.GroupEnd());
+    return MF_OK;
+}
+
+}  // namespace mf

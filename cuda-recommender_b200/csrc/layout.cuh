@@ -1,0 +1,70 @@
+// layout.cuh — how one compressed-sparse copy of the ratings lives in HBM.
+//
+// A "side" is one copy with its solve direction:
+//   CSC side: segments = item columns, gathers the user factor u (length rows), solves v
+//   CSR side: segments = user rows,    gathers the item factor v (length cols), solves u
+// (the reference keeps the same two copies, src/pmf_util.h:34-149, and reaches the CSR one through
+//  the pointer-swap transpose, pmf_util.h:66-81).
+//
+// DIRECT layout: the caller's arrays as they are (ptr / uint32 idx / val).
+//
+// PANEL layout (the B200 layout): the gather dimension is cut into panels of
+// `panel_rows` factor entries so that one panel of the factor vector sits in shared memory while
+// the ratings that reference it stream past.  Every segment is cut at the panel boundaries into
+// pieces (panel p, segment s); storage is panel-major, pieces in segment order inside a panel, each
+// piece padded to a multiple of 8 entries (16-byte idx vectors, 32-byte val vectors).  Indices are
+// stored panel-local in 16 bits; padding entries carry idx16 = panel_rows (a zeroed shared-memory
+// slot) and val = 0, so they add nothing to g, h or the residual.
+// Pieces are cut into work items of at most `chunk` entries; item j of segment s writes its partial
+// (g, h) to a fixed slot, slots of one segment are contiguous and ordered (panel, chunk), and a
+// finalize pass adds them in that order — the reduction tree of a segment depends only on its own
+// entries and the global panel grid, never on scheduling or on the multi-GPU shard it sits in.
+#pragma once
+#include "common.cuh"
+
+namespace mf {
+
+struct WorkItem {        // 16 bytes, loaded as one uint4
+    uint32_t start;      // first entry in the padded arrays (multiple of 8)
+    uint32_t len;        // entries including padding (multiple of 8, <= chunk)
+    uint32_t seg;        // local segment id
+    uint32_t slot;       // partial-sum slot
+};
+
+struct Side {
+    // shape
+    int64_t nseg = 0;        // local segments (this shard)
+    int64_t seg_offset = 0;  // global id of local segment 0 (multi-GPU)
+    int64_t gdim = 0;        // length of the gathered factor vector (global)
+    int64_t nnz = 0;         // local entries
+    // direct layout (always present for ptr; idx/val only while needed)
+    uint32_t* ptr = nullptr;  // [nseg+1] local, rebased to 0
+    uint32_t* idx = nullptr;  // [nnz]
+    float* val = nullptr;     // [nnz]   (DIRECT: the live residual)
+    // panel layout
+    int panel_rows = 0, chunk = 0, npanels = 0;
+    int64_t npad = 0, nitems = 0, nslots = 0;
+    uint32_t* piece_ptr = nullptr;    // [npanels*nseg + 1] start of piece (p,s) in the padded arrays
+    uint32_t* piece_first = nullptr;  // [npanels*nseg]     raw offset of the piece's first entry
+    uint32_t* item_ptr = nullptr;     // [npanels*nseg + 1] first work item of piece (p,s)
+    uint16_t* idx16 = nullptr;        // [npad]
+    float* pval = nullptr;            // [npad]  (PANEL: the live residual)
+    WorkItem* items = nullptr;        // [nitems]
+    uint32_t* slot_ptr = nullptr;     // [nseg+1]
+    float2* partials = nullptr;       // [nslots]
+    uint32_t* cta_item_ptr = nullptr; // [ncta+1] equal-cost contiguous item ranges
+    uint32_t* panel_item_ptr = nullptr; // [npanels+1]
+    int ncta = 0;
+    bool sorted = true;
+};
+
+int side_free(Side& s);
+// raw device arrays must be set (ptr, idx, val, nseg, gdim, nnz); builds everything else.
+int side_build_panels(Side& s, int panel_rows, int chunk, int ncta, cudaStream_t st);
+// dst_raw[nnz] <- current panel values in the caller's order; and the inverse
+int side_panel_to_raw(const Side& s, float* dst_raw, cudaStream_t st);
+int side_raw_to_panel(Side& s, const float* src_raw, cudaStream_t st);
+// returns 1 in *sorted when every segment's indices are strictly ascending
+int side_check_sorted(const Side& s, bool* sorted, cudaStream_t st);
+
+}  // namespace mf

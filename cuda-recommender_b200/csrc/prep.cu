@@ -1,0 +1,354 @@
+// prep.cu — integer tier: builds the PANEL layout (layout.cuh) from a caller-order compressed
+// copy, converts values between the two orders, and the small index ops (degree bins, nnz-balanced
+// partition).  Everything here is exact integer / copy work and is checked bit-for-bit against a
+// numpy restatement in tests/ (the reference itself has no builder: it loads ready-made CSR and CSC,
+// src/tools.cpp:58-59, src/pmf_util.h:108-136).
+#include "layout.cuh"
+
+namespace mf {
+namespace {
+
+constexpr int kPad = 8;        // piece padding granule (entries)
+constexpr uint32_t kCost0 = 8; // per-item fixed cost in units of 8 entries (descriptor, reduce, store)
+
+__device__ __forceinline__ uint32_t lower_bound_u32(const uint32_t* __restrict__ a, uint32_t lo, uint32_t hi,
+                                                    uint32_t key) {
+    while (lo < hi) {
+        uint32_t mid = lo + ((hi - lo) >> 1);
+        if (a[mid] < key) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// one thread per piece q = p*nseg + s
+__global__ void k_piece_count(int64_t nseg, int npanels, uint32_t panel_rows, uint32_t chunk,
+                              const uint32_t* __restrict__ ptr, const uint32_t* __restrict__ idx,
+                              uint32_t* __restrict__ piece_first, uint32_t* __restrict__ padded,
+                              uint32_t* __restrict__ nitem) {
+    int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t Q = nseg * npanels;
+    if (q >= Q) return;
+    int p = (int)(q / nseg);
+    int64_t s = q - (int64_t)p * nseg;
+    uint32_t lo = ptr[s], hi = ptr[s + 1];
+    uint64_t k0 = (uint64_t)p * panel_rows, k1 = k0 + panel_rows;
+    uint32_t first = lower_bound_u32(idx, lo, hi, (uint32_t)k0);
+    uint32_t last = k1 > 0xffffffffull ? hi : lower_bound_u32(idx, first, hi, (uint32_t)k1);
+    uint32_t cnt = last - first;
+    uint32_t pd = (cnt + kPad - 1) / kPad * kPad;
+    piece_first[q] = first;
+    padded[q] = pd;
+    nitem[q] = (pd + chunk - 1) / chunk;
+}
+
+// one thread per segment: how many work items (= partial slots) the segment owns
+__global__ void k_seg_items(int64_t nseg, int npanels, const uint32_t* __restrict__ item_ptr,
+                            uint32_t* __restrict__ seg_items) {
+    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nseg) return;
+    uint32_t n = 0;
+    for (int p = 0; p < npanels; ++p) {
+        int64_t q = (int64_t)p * nseg + s;
+        n += item_ptr[q + 1] - item_ptr[q];
+    }
+    seg_items[s] = n;
+}
+
+// one warp per piece: copy + pad the entries, emit the work items
+__global__ void k_fill(int64_t nseg, int npanels, uint32_t panel_rows, uint32_t chunk,
+                       const uint32_t* __restrict__ ptr, const uint32_t* __restrict__ idx,
+                       const float* __restrict__ val, const uint32_t* __restrict__ piece_first,
+                       const uint32_t* __restrict__ piece_ptr, const uint32_t* __restrict__ item_ptr,
+                       const uint32_t* __restrict__ slot_ptr, uint16_t* __restrict__ idx16,
+                       float* __restrict__ pval, WorkItem* __restrict__ items, uint32_t* __restrict__ item_cost) {
+    const int lane = threadIdx.x & 31;
+    int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    int64_t Q = nseg * npanels;
+    for (int64_t q = warp; q < Q; q += nwarps) {
+        uint32_t dst0 = piece_ptr[q];
+        uint32_t pd = piece_ptr[q + 1] - dst0;
+        if (pd == 0) continue;
+        int p = (int)(q / nseg);
+        int64_t s = q - (int64_t)p * nseg;
+        uint32_t src0 = piece_first[q];
+        uint32_t src1 = (p == npanels - 1) ? ptr[s + 1] : piece_first[q + nseg];
+        uint32_t cnt = src1 - src0;
+        uint32_t base = (uint32_t)p * panel_rows;
+        for (uint32_t e = lane; e < pd; e += 32) {
+            bool real = e < cnt;
+            idx16[dst0 + e] = real ? (uint16_t)(idx[src0 + e] - base) : (uint16_t)panel_rows;
+            pval[dst0 + e] = real ? val[src0 + e] : 0.0f;
+        }
+        // slots of segment s are ordered (panel, chunk): count the items of the earlier panels
+        uint32_t before = 0;
+        for (int pp = lane; pp < p; pp += 32) {
+            int64_t qq = (int64_t)pp * nseg + s;
+            before += item_ptr[qq + 1] - item_ptr[qq];
+        }
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) before += __shfl_xor_sync(0xffffffffu, before, o);
+        uint32_t it0 = item_ptr[q], nit = item_ptr[q + 1] - it0;
+        uint32_t slot0 = slot_ptr[s] + before;
+        for (uint32_t j = lane; j < nit; j += 32) {
+            WorkItem w;
+            w.start = dst0 + j * chunk;
+            uint32_t rem = pd - j * chunk;
+            w.len = rem < chunk ? rem : chunk;
+            w.seg = (uint32_t)s;
+            w.slot = slot0 + j;
+            items[it0 + j] = w;
+            item_cost[it0 + j] = w.len / kPad + kCost0;
+        }
+    }
+}
+
+__global__ void k_panel_item_ptr(int64_t nseg, int npanels, const uint32_t* __restrict__ item_ptr,
+                                 uint32_t* __restrict__ panel_item_ptr) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p <= npanels) panel_item_ptr[p] = item_ptr[(int64_t)p * nseg];
+}
+
+// equal-cost contiguous item ranges: cta_item_ptr[j] = first item whose cost prefix >= j*total/ncta
+__global__ void k_cta_ranges(int ncta, int64_t nitems, const uint32_t* __restrict__ cost_prefix,
+                             uint32_t* __restrict__ cta_item_ptr) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j > ncta) return;
+    if (j == ncta) { cta_item_ptr[j] = (uint32_t)nitems; return; }
+    uint64_t total = cost_prefix[nitems];
+    uint32_t target = (uint32_t)(total * (uint64_t)j / (uint64_t)ncta);
+    cta_item_ptr[j] = lower_bound_u32(cost_prefix, 0, (uint32_t)nitems, target);
+}
+
+// one warp per piece: value copy between the panel order and the caller's order
+template <bool TO_RAW>
+__global__ void k_copy_values(int64_t nseg, int npanels, const uint32_t* __restrict__ ptr,
+                              const uint32_t* __restrict__ piece_first, const uint32_t* __restrict__ piece_ptr,
+                              float* __restrict__ pval, float* __restrict__ raw) {
+    const int lane = threadIdx.x & 31;
+    int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    int64_t Q = nseg * npanels;
+    for (int64_t q = warp; q < Q; q += nwarps) {
+        uint32_t dst0 = piece_ptr[q];
+        if (piece_ptr[q + 1] == dst0) continue;
+        int p = (int)(q / nseg);
+        int64_t s = q - (int64_t)p * nseg;
+        uint32_t src0 = piece_first[q];
+        uint32_t src1 = (p == npanels - 1) ? ptr[s + 1] : piece_first[q + nseg];
+        uint32_t cnt = src1 - src0;
+        for (uint32_t e = lane; e < cnt; e += 32) {
+            if (TO_RAW) raw[src0 + e] = pval[dst0 + e];
+            else pval[dst0 + e] = raw[src0 + e];
+        }
+    }
+}
+
+__global__ void k_check_sorted(int64_t nseg, const uint32_t* __restrict__ ptr, const uint32_t* __restrict__ idx,
+                               uint32_t gdim, int* __restrict__ bad) {
+    const int lane = threadIdx.x & 31;
+    int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t s = warp; s < nseg; s += nwarps) {
+        uint32_t lo = ptr[s], hi = ptr[s + 1];
+        bool b = false;
+        for (uint32_t e = lo + lane; e < hi; e += 32) {
+            uint32_t v = idx[e];
+            if (v >= gdim) b = true;
+            if (e + 1 < hi && v >= idx[e + 1]) b = true;
+        }
+        if (b) *bad = 1;
+    }
+}
+
+__global__ void k_degree_bins(int64_t nseg, const uint32_t* __restrict__ ptr, unsigned long long* __restrict__ seg_in_bin,
+                              unsigned long long* __restrict__ nnz_in_bin) {
+    __shared__ unsigned long long sa[33], sb[33];
+    if (threadIdx.x < 33) { sa[threadIdx.x] = 0; sb[threadIdx.x] = 0; }
+    __syncthreads();
+    for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < nseg; s += (int64_t)gridDim.x * blockDim.x) {
+        uint32_t d = ptr[s + 1] - ptr[s];
+        int b = 32 - __clz(d);  // bit length: 0 for empty, 1 for deg 1, 2 for 2..3, ...
+        atomicAdd(&sa[b], 1ull);
+        atomicAdd(&sb[b], (unsigned long long)d);
+    }
+    __syncthreads();
+    if (threadIdx.x < 33) {
+        if (sa[threadIdx.x]) atomicAdd(&seg_in_bin[threadIdx.x], sa[threadIdx.x]);
+        if (sb[threadIdx.x]) atomicAdd(&nnz_in_bin[threadIdx.x], sb[threadIdx.x]);
+    }
+}
+
+__global__ void k_partition(int64_t nseg, const uint32_t* __restrict__ ptr, int P, long long* __restrict__ bound) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p > P) return;
+    if (p == 0) { bound[0] = 0; return; }
+    if (p == P) { bound[P] = nseg; return; }
+    uint64_t nnz = ptr[nseg];
+    uint64_t target = (nnz * (uint64_t)p + (uint64_t)P - 1) / (uint64_t)P;
+    int64_t lo = 0, hi = nseg;
+    while (lo < hi) {
+        int64_t mid = (lo + hi) / 2;
+        if ((uint64_t)ptr[mid] >= target) hi = mid; else lo = mid + 1;
+    }
+    bound[p] = lo;
+}
+
+inline unsigned grid_for(int64_t n, int block) { return (unsigned)((n + block - 1) / block > 0 ? (n + block - 1) / block : 1); }
+
+}  // namespace
+
+int side_free(Side& s) {
+    void* ptrs[] = {s.ptr, s.idx, s.val, s.piece_ptr, s.piece_first, s.item_ptr, s.idx16, s.pval, s.items,
+                    s.slot_ptr, s.partials, s.cta_item_ptr, s.panel_item_ptr};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    s = Side();
+    return MF_OK;
+}
+
+int side_check_sorted(const Side& s, bool* sorted, cudaStream_t st) {
+    int* d_bad = nullptr;
+    MF_TRY(dev_alloc(&d_bad, 1));
+    MF_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int), st));
+    if (s.nseg > 0 && s.nnz > 0) {
+        int64_t warps = s.nseg < 65536 * 8 ? s.nseg : 65536 * 8;
+        k_check_sorted<<<grid_for(warps * 32, 256), 256, 0, st>>>(s.nseg, s.ptr, s.idx, (uint32_t)s.gdim, d_bad);
+    }
+    int h = 0;
+    MF_CUDA(cudaMemcpyAsync(&h, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st));
+    MF_CUDA(cudaStreamSynchronize(st));
+    cudaFree(d_bad);
+    *sorted = (h == 0);
+    return MF_OK;
+}
+
+int side_build_panels(Side& s, int panel_rows, int chunk, int ncta, cudaStream_t st) {
+    MF_REQUIRE(panel_rows > 0 && panel_rows <= 65528 && panel_rows % 8 == 0, "panel_rows must be a multiple of 8 in (0, 65528]");
+    MF_REQUIRE(chunk >= 8 && chunk % 8 == 0, "chunk must be a positive multiple of 8");
+    MF_REQUIRE(ncta > 0, "ncta must be positive");
+    s.panel_rows = panel_rows;
+    s.chunk = chunk;
+    s.ncta = ncta;
+    s.npanels = (int)((s.gdim + panel_rows - 1) / panel_rows);
+    if (s.npanels < 1) s.npanels = 1;
+    const int64_t Q = s.nseg * s.npanels;
+    MF_REQUIRE(Q < (int64_t)1 << 31, "too many (panel, segment) pieces: raise panel_rows");
+
+    uint32_t *padded = nullptr, *nitem = nullptr, *seg_items = nullptr, *tmp = nullptr, *cost = nullptr, *cost_prefix = nullptr;
+    MF_TRY(dev_alloc(&padded, (size_t)Q));
+    MF_TRY(dev_alloc(&nitem, (size_t)Q));
+    MF_TRY(dev_alloc(&s.piece_first, (size_t)Q));
+    MF_TRY(dev_alloc(&s.piece_ptr, (size_t)Q + 1));
+    MF_TRY(dev_alloc(&s.item_ptr, (size_t)Q + 1));
+    MF_TRY(dev_alloc(&seg_items, (size_t)s.nseg));
+    MF_TRY(dev_alloc(&s.slot_ptr, (size_t)s.nseg + 1));
+    MF_TRY(dev_alloc(&s.panel_item_ptr, (size_t)s.npanels + 1));
+    MF_TRY(dev_alloc(&s.cta_item_ptr, (size_t)ncta + 1));
+    size_t tmp_n = scan_tmp_elems((size_t)(Q > s.nseg ? Q : s.nseg));
+    MF_TRY(dev_alloc(&tmp, tmp_n));
+
+    if (Q > 0)
+        k_piece_count<<<grid_for(Q, 256), 256, 0, st>>>(s.nseg, s.npanels, (uint32_t)panel_rows, (uint32_t)chunk, s.ptr,
+                                                        s.idx, s.piece_first, padded, nitem);
+    MF_CUDA(cudaGetLastError());
+    MF_TRY(exclusive_scan_u32(padded, s.piece_ptr, (size_t)Q, tmp, st));
+    MF_TRY(exclusive_scan_u32(nitem, s.item_ptr, (size_t)Q, tmp, st));
+    if (s.nseg > 0)
+        k_seg_items<<<grid_for(s.nseg, 256), 256, 0, st>>>(s.nseg, s.npanels, s.item_ptr, seg_items);
+    MF_CUDA(cudaGetLastError());
+    MF_TRY(exclusive_scan_u32(seg_items, s.slot_ptr, (size_t)s.nseg, tmp, st));
+
+    uint32_t h_npad = 0, h_nitems = 0, h_nslots = 0;
+    MF_CUDA(cudaMemcpyAsync(&h_npad, s.piece_ptr + Q, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    MF_CUDA(cudaMemcpyAsync(&h_nitems, s.item_ptr + Q, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    MF_CUDA(cudaMemcpyAsync(&h_nslots, s.slot_ptr + s.nseg, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    MF_CUDA(cudaStreamSynchronize(st));
+    s.npad = h_npad;
+    s.nitems = h_nitems;
+    s.nslots = h_nslots;
+    MF_REQUIRE(s.nitems == s.nslots, "internal: item/slot count mismatch (%lld vs %lld)", (long long)s.nitems, (long long)s.nslots);
+
+    MF_TRY(dev_alloc(&s.idx16, (size_t)s.npad + 8));
+    MF_TRY(dev_alloc(&s.pval, (size_t)s.npad + 8));
+    MF_TRY(dev_alloc(&s.items, (size_t)s.nitems));
+    MF_TRY(dev_alloc(&s.partials, (size_t)s.nslots));
+    MF_TRY(dev_alloc(&cost, (size_t)s.nitems));
+    MF_TRY(dev_alloc(&cost_prefix, (size_t)s.nitems + 1));
+    if (Q > 0) {
+        int64_t warps = Q < 148 * 64 * 8 ? Q : 148 * 64 * 8;
+        k_fill<<<grid_for(warps * 32, 256), 256, 0, st>>>(s.nseg, s.npanels, (uint32_t)panel_rows, (uint32_t)chunk, s.ptr,
+                                                         s.idx, s.val, s.piece_first, s.piece_ptr, s.item_ptr, s.slot_ptr,
+                                                         s.idx16, s.pval, s.items, cost);
+    }
+    MF_CUDA(cudaGetLastError());
+    MF_TRY(exclusive_scan_u32(cost, cost_prefix, (size_t)s.nitems, tmp, st));
+    k_cta_ranges<<<grid_for(ncta + 1, 128), 128, 0, st>>>(ncta, s.nitems, cost_prefix, s.cta_item_ptr);
+    k_panel_item_ptr<<<grid_for(s.npanels + 1, 128), 128, 0, st>>>(s.nseg, s.npanels, s.item_ptr, s.panel_item_ptr);
+    MF_CUDA(cudaGetLastError());
+    MF_CUDA(cudaStreamSynchronize(st));
+    cudaFree(padded); cudaFree(nitem); cudaFree(seg_items); cudaFree(tmp); cudaFree(cost); cudaFree(cost_prefix);
+    return MF_OK;
+}
+
+int side_panel_to_raw(const Side& s, float* dst_raw, cudaStream_t st) {
+    int64_t Q = s.nseg * s.npanels;
+    if (Q == 0 || s.nnz == 0) return MF_OK;
+    int64_t warps = Q < 148 * 64 * 8 ? Q : 148 * 64 * 8;
+    k_copy_values<true><<<grid_for(warps * 32, 256), 256, 0, st>>>(s.nseg, s.npanels, s.ptr, s.piece_first, s.piece_ptr,
+                                                                  s.pval, dst_raw);
+    MF_CUDA(cudaGetLastError());
+    return MF_OK;
+}
+
+int side_raw_to_panel(Side& s, const float* src_raw, cudaStream_t st) {
+    int64_t Q = s.nseg * s.npanels;
+    if (Q == 0 || s.nnz == 0) return MF_OK;
+    int64_t warps = Q < 148 * 64 * 8 ? Q : 148 * 64 * 8;
+    k_copy_values<false><<<grid_for(warps * 32, 256), 256, 0, st>>>(s.nseg, s.npanels, s.ptr, s.piece_first, s.piece_ptr,
+                                                                   s.pval, const_cast<float*>(src_raw));
+    MF_CUDA(cudaGetLastError());
+    return MF_OK;
+}
+
+// ---- C-ABI: small integer ops -------------------------------------------------------------
+static int stage_ptr(const uint32_t* ptr, int64_t n, uint32_t** d_ptr, int device) {
+    MF_CUDA(cudaSetDevice(device));
+    MF_TRY(dev_alloc(d_ptr, (size_t)n));
+    MF_CUDA(cudaMemcpy(*d_ptr, ptr, sizeof(uint32_t) * (size_t)n, cudaMemcpyDefault));
+    return MF_OK;
+}
+
+}  // namespace mf
+
+extern "C" int mf_degree_bins(int64_t nseg, const uint32_t* ptr, uint64_t* seg_in_bin, uint64_t* nnz_in_bin, int device) {
+    using namespace mf;
+    MF_REQUIRE(nseg >= 0 && ptr && seg_in_bin && nnz_in_bin, "mf_degree_bins: bad argument");
+    uint32_t* d_ptr = nullptr;
+    MF_TRY(stage_ptr(ptr, nseg + 1, &d_ptr, device));
+    unsigned long long* d_bins = nullptr;
+    MF_TRY(dev_alloc(&d_bins, 66));
+    MF_CUDA(cudaMemset(d_bins, 0, 66 * sizeof(unsigned long long)));
+    if (nseg > 0) k_degree_bins<<<148 * 2, 256>>>(nseg, d_ptr, d_bins, d_bins + 33);
+    MF_CUDA(cudaGetLastError());
+    MF_CUDA(cudaMemcpy(seg_in_bin, d_bins, 33 * sizeof(uint64_t), cudaMemcpyDefault));
+    MF_CUDA(cudaMemcpy(nnz_in_bin, d_bins + 33, 33 * sizeof(uint64_t), cudaMemcpyDefault));
+    cudaFree(d_bins);
+    cudaFree(d_ptr);
+    return MF_OK;
+}
+
+extern "C" int mf_partition(int64_t nseg, const uint32_t* ptr, int P, int64_t* bound, int device) {
+    using namespace mf;
+    MF_REQUIRE(nseg >= 0 && ptr && bound && P >= 1, "mf_partition: bad argument");
+    uint32_t* d_ptr = nullptr;
+    MF_TRY(stage_ptr(ptr, nseg + 1, &d_ptr, device));
+    long long* d_b = nullptr;
+    MF_TRY(dev_alloc(&d_b, (size_t)P + 1));
+    k_partition<<<(P + 1 + 127) / 128, 128>>>(nseg, d_ptr, P, d_b);
+    MF_CUDA(cudaGetLastError());
+    MF_CUDA(cudaMemcpy(bound, d_b, sizeof(int64_t) * ((size_t)P + 1), cudaMemcpyDefault));
+    cudaFree(d_b);
+    cudaFree(d_ptr);
+    return MF_OK;
+}

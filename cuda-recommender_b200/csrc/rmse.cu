@@ -1,0 +1,54 @@
+// rmse.cu — test-set RMSE, fully on device.
+// Reference: calrmse / dot (src/tools.cpp:184-198, 235-248) on the CPU path; GPU_rmse
+// (cuda_src/CUDA_AUX.cu:3-27) plus a D2H copy of one float per test rating and a serial host sum
+// (cuda_src/CCD_CUDA.cu:385-401) on the GPU path.  Here: one thread per test rating, prediction =
+// sum over ranks of the FP32 product W*H promoted into a double accumulator (the CPU path's
+// arithmetic), squared error in double, warp + CTA reduction, one double atomicAdd per CTA, and a
+// single scalar comes back to the host.
+#include "rmse.cuh"
+
+namespace mf {
+namespace {
+
+__global__ void __launch_bounds__(256) k_rmse(int64_t nt, const uint32_t* __restrict__ trow, const uint32_t* __restrict__ tcol,
+                                               const float* __restrict__ tval, const float* __restrict__ W,
+                                               const float* __restrict__ H, int k, int64_t w_rank_stride,
+                                               int64_t w_row_stride, int64_t h_rank_stride, int64_t h_row_stride,
+                                               double* __restrict__ acc) {
+    __shared__ double part[8];
+    double local = 0.0;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < nt; e += (int64_t)gridDim.x * blockDim.x) {
+        const float* w = W + (int64_t)trow[e] * w_row_stride;
+        const float* h = H + (int64_t)tcol[e] * h_row_stride;
+        double pred = 0.0;
+        for (int t = 0; t < k; ++t) pred += (double)__fmul_rn(w[t * w_rank_stride], h[t * h_rank_stride]);
+        double err = -(double)tval[e];
+        err += pred;
+        local += err * err;
+    }
+    local = warp_sum(local);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = local;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double v = threadIdx.x < (blockDim.x >> 5) ? part[threadIdx.x] : 0.0;
+        v = warp_sum(v);
+        if (threadIdx.x == 0 && v != 0.0) atomicAdd(acc, v);
+    }
+}
+
+}  // namespace
+
+int rmse_accumulate(int64_t nt, const uint32_t* trow, const uint32_t* tcol, const float* tval, const float* W,
+                    const float* H, int k, int64_t w_rank_stride, int64_t w_row_stride, int64_t h_rank_stride,
+                    int64_t h_row_stride, double* d_acc, int sm_count, cudaStream_t st) {
+    MF_CUDA(cudaMemsetAsync(d_acc, 0, sizeof(double), st));
+    if (nt <= 0) return MF_OK;
+    int64_t blocks = (nt + 255) / 256;
+    if (blocks > (int64_t)sm_count * 8) blocks = (int64_t)sm_count * 8;
+    k_rmse<<<(unsigned)blocks, 256, 0, st>>>(nt, trow, tcol, tval, W, H, k, w_rank_stride, w_row_stride, h_rank_stride,
+                                            h_row_stride, d_acc);
+    MF_CUDA(cudaGetLastError());
+    return MF_OK;
+}
+
+}  // namespace mf

@@ -1,0 +1,720 @@
+// session.cu — the C-ABI (include/mf_abi.h): device residency, the CCD++ and ALS drivers, the
+// one-shot trainers that replace kernel_wrapper_ccdpp_NV / kernel_wrapper_als_NV.
+//
+// Reference orchestration being replaced: ccdpp_NV (cuda_src/CCD_CUDA.cu:224-451) and als_NV
+// (cuda_src/ALS_CUDA.cu:200-406); schedule semantics follow the CPU path ccdr1_OMP (src/CCD.cpp:45-163)
+// and ALS_OMP (src/ALS.cpp:81-233), which is also what the oracle restates.
+#include "session.cuh"
+
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "rmse.cuh"
+
+namespace mf {
+
+// ------------------------------------------------------------------------------------------
+// FamilyTimer
+// ------------------------------------------------------------------------------------------
+cudaEvent_t FamilyTimer::take() {
+    if (used == pool.size()) {
+        cudaEvent_t e = nullptr;
+        cudaEventCreate(&e);
+        pool.push_back(e);
+    }
+    return pool[used++];
+}
+void FamilyTimer::start(int fam) {
+    if (!enabled) return;
+    open_fam = fam;
+    open_ev = take();
+    cudaEventRecord(open_ev, st);
+}
+void FamilyTimer::stop() {
+    if (!enabled || open_fam < 0) return;
+    cudaEvent_t b = take();
+    cudaEventRecord(b, st);
+    spans.push_back({open_ev, b, open_fam});
+    open_fam = -1;
+}
+void FamilyTimer::collect(double* seconds, int64_t* launches) {
+    for (const Span& s : spans) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, s.a, s.b) == cudaSuccess) {
+            seconds[s.fam] += ms * 1e-3;
+            launches[s.fam] += 1;
+        }
+    }
+    spans.clear();
+    used = 0;
+}
+void FamilyTimer::destroy() {
+    for (cudaEvent_t e : pool) cudaEventDestroy(e);
+    pool.clear();
+    spans.clear();
+    used = 0;
+}
+
+namespace {
+
+constexpr int kThreads = 1024;
+constexpr size_t kSmemMax = 227 * 1024 - 64;
+
+int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+
+// largest panel (multiple of 8) such that nvec vectors of (panel+8) floats fit in shared memory
+int panel_cap(int nvec) {
+    int64_t cap = (int64_t)(kSmemMax / (sizeof(float) * nvec)) - 8;
+    return (int)(cap / 8 * 8);
+}
+
+// panel size for a gather dimension: one panel if it fits, else the fewest equal panels
+int choose_panel_rows(int64_t gdim, int cap) {
+    if (gdim <= cap) return (int)std::max<int64_t>(8, round_up(gdim, 8));
+    int64_t np = (gdim + cap - 1) / cap;
+    return (int)round_up((gdim + np - 1) / np, 8);
+}
+
+// nnz-balanced contiguous partition (same rule as oracle orc_partition / mf_partition)
+void partition_host(const std::vector<uint32_t>& ptr, int P, std::vector<int64_t>& bound) {
+    const int64_t nseg = (int64_t)ptr.size() - 1;
+    const uint64_t nnz = ptr[nseg];
+    bound.assign(P + 1, 0);
+    for (int p = 1; p < P; ++p) {
+        uint64_t target = (nnz * (uint64_t)p + (uint64_t)P - 1) / (uint64_t)P;
+        bound[p] = std::lower_bound(ptr.begin(), ptr.end(), target,
+                                    [](uint32_t a, uint64_t t) { return (uint64_t)a < t; }) - ptr.begin();
+        if (bound[p] > nseg) bound[p] = nseg;
+    }
+    bound[P] = nseg;
+}
+
+// upload segments [s0, s1) of one compressed copy (host or device source pointers)
+int upload_side(Side& sd, const std::vector<uint32_t>& ptr_full, int64_t s0, int64_t s1, const uint32_t* idx,
+                const float* val, int64_t gdim, cudaStream_t st) {
+    sd.nseg = s1 - s0;
+    sd.seg_offset = s0;
+    sd.gdim = gdim;
+    const uint32_t e0 = ptr_full[s0], e1 = ptr_full[s1];
+    sd.nnz = (int64_t)e1 - (int64_t)e0;
+    std::vector<uint32_t> local((size_t)sd.nseg + 1);
+    for (int64_t s = 0; s <= sd.nseg; ++s) local[s] = ptr_full[s0 + s] - e0;
+    MF_TRY(dev_alloc(&sd.ptr, (size_t)sd.nseg + 1));
+    MF_TRY(dev_alloc(&sd.idx, (size_t)sd.nnz));
+    MF_TRY(dev_alloc(&sd.val, (size_t)sd.nnz));
+    MF_CUDA(cudaMemcpyAsync(sd.ptr, local.data(), sizeof(uint32_t) * local.size(), cudaMemcpyHostToDevice, st));
+    if (sd.nnz > 0) {
+        MF_CUDA(cudaMemcpyAsync(sd.idx, idx + e0, sizeof(uint32_t) * (size_t)sd.nnz, cudaMemcpyDefault, st));
+        MF_CUDA(cudaMemcpyAsync(sd.val, val + e0, sizeof(float) * (size_t)sd.nnz, cudaMemcpyDefault, st));
+    }
+    MF_CUDA(cudaStreamSynchronize(st));  // `local` goes out of scope
+    return MF_OK;
+}
+
+int fetch_ptr(const uint32_t* src, int64_t n, std::vector<uint32_t>& out) {
+    out.resize((size_t)n);
+    MF_CUDA(cudaMemcpy(out.data(), src, sizeof(uint32_t) * (size_t)n, cudaMemcpyDefault));
+    return MF_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// CCD++ sweeps on a session
+// ------------------------------------------------------------------------------------------
+struct SweepVectors {
+    const float* g_new = nullptr;
+    const float* g_add = nullptr;
+    const float* g_old = nullptr;
+    const float* s_add = nullptr;
+    const float* s_old = nullptr;
+};
+
+int family_of(int mode) {
+    if (!(mode & kSolve)) return F_UPDATE;
+    return (mode & (kSub | kAdd)) ? F_FUSED : F_SOLVE;
+}
+
+// one sweep of `mode` over side sd; when it solves, `out` (full-length vector) receives this shard's block
+int run_sweep(mf_session* s, Side& sd, int mode, const SweepVectors& v, float* out) {
+    if (sd.nnz == 0 && !(mode & kSolve)) return MF_OK;
+    const int nmf = s->prm.nmf_project;
+    if (s->panel) {
+        PanelSweepArgs a;
+        a.idx16 = sd.idx16; a.val = sd.pval; a.items = sd.items;
+        a.cta_item_ptr = sd.cta_item_ptr; a.panel_item_ptr = sd.panel_item_ptr;
+        a.npanels = sd.npanels; a.panel_rows = (uint32_t)sd.panel_rows; a.gdim = sd.gdim;
+        a.seg_offset = sd.seg_offset;
+        a.g_new = v.g_new; a.g_add = v.g_add; a.g_old = v.g_old; a.s_add = v.s_add; a.s_old = v.s_old;
+        a.partials = sd.partials;
+        if (sd.nitems > 0) {
+            s->timer.start(family_of(mode));
+            MF_TRY(panel_sweep(mode, a, sd.ncta, kThreads, s->st));
+            s->timer.stop();
+        }
+        if (mode & kSolve) {
+            s->timer.start(F_FINALIZE);
+            MF_TRY(panel_finalize(sd.nseg, sd.slot_ptr, sd.partials, sd.ptr, s->prm.lambda, nmf, out + sd.seg_offset, s->st));
+            s->timer.stop();
+        }
+    } else {
+        DirectSweepArgs a;
+        a.nseg = sd.nseg; a.ptr = sd.ptr; a.idx = sd.idx; a.val = sd.val; a.seg_offset = sd.seg_offset;
+        a.g_new = v.g_new; a.g_add = v.g_add; a.g_old = v.g_old; a.s_add = v.s_add; a.s_old = v.s_old;
+        a.lambda = s->prm.lambda; a.nmf = nmf; a.out = out ? out + sd.seg_offset : nullptr;
+        s->timer.start(family_of(mode));
+        MF_TRY(direct_sweep(mode, a, s->sm_count, s->st));
+        s->timer.stop();
+    }
+    return MF_OK;
+}
+
+int gather_blocks(mf_session* s, float* vec, const std::vector<int64_t>& bound, int64_t unit) {
+    if (s->nranks <= 1) return MF_OK;
+    s->timer.start(F_COLLECTIVE);
+    MF_TRY(dist_allgather_blocks(s->dist, vec, bound, unit, s->st));
+    s->timer.stop();
+    return MF_OK;
+}
+
+// v = H[t] from the CSC copy and u = W[t]
+int solve_v(mf_session* s, int t, int mode, const SweepVectors& v) {
+    float* out = s->H + (int64_t)t * s->ldn;
+    MF_TRY(run_sweep(s, s->csc, mode, v, out));
+    return gather_blocks(s, out, s->col_bound, 1);
+}
+int solve_u(mf_session* s, int t, int mode, const SweepVectors& v) {
+    float* out = s->W + (int64_t)t * s->ldm;
+    MF_TRY(run_sweep(s, s->csr, mode, v, out));
+    return gather_blocks(s, out, s->row_bound, 1);
+}
+
+// residual (+|-)= u_t v_t^T on both copies — UpdateRating on R then Rt, src/CCD.cpp:100-103 / :133-134
+int update_both(mf_session* s, int t, bool add) {
+    const float* u = s->W + (int64_t)t * s->ldm;
+    const float* v = s->H + (int64_t)t * s->ldn;
+    SweepVectors a, b;
+    if (add) { a.g_new = u; a.s_add = v; b.g_new = v; b.s_add = u; }
+    else     { a.g_old = u; a.s_old = v; b.g_old = v; b.s_old = u; }
+    MF_TRY(run_sweep(s, s->csc, add ? kAdd : kSub, a, nullptr));
+    MF_TRY(run_sweep(s, s->csr, add ? kAdd : kSub, b, nullptr));
+    return MF_OK;
+}
+
+int flush_pending(mf_session* s) {
+    if (s->pending < 0) return MF_OK;
+    MF_TRY(update_both(s, s->pending, false));
+    s->pending = -1;
+    return MF_OK;
+}
+
+// one rank of one outer iteration, fused schedule: the deferred subtraction of the
+// previous rank and this rank's add-back ride on the first solve sweep of each copy.
+int ccd_rank_fused(mf_session* s, int t, bool add) {
+    const int T = s->prm.maxinneriter;
+    if (T <= 0) return MF_OK;
+    float* u = s->W + (int64_t)t * s->ldm;
+    float* v = s->H + (int64_t)t * s->ldn;
+    const int sub = s->pending;
+    const float* u_sub = sub >= 0 ? s->W + (int64_t)sub * s->ldm : nullptr;
+    const float* v_sub = sub >= 0 ? s->H + (int64_t)sub * s->ldn : nullptr;
+    if (add) MF_CUDA(cudaMemcpyAsync(s->v_old, v, sizeof(float) * (size_t)s->ldn, cudaMemcpyDeviceToDevice, s->st));
+    {   // CSC: [subtract `sub`] [add back t with the old (u_t, v_t)] solve v_t against u_t
+        SweepVectors a;
+        a.g_new = u; a.g_old = u_sub; a.s_add = v; a.s_old = v_sub;
+        MF_TRY(solve_v(s, t, kSolve | (sub >= 0 ? kSub : 0) | (add ? kAdd : 0), a));
+    }
+    {   // CSR: [subtract `sub`] [add back t with the old v_t (saved) and old u_t] solve u_t against the new v_t
+        SweepVectors a;
+        a.g_new = v; a.g_add = s->v_old; a.s_add = u; a.s_old = u_sub;
+        a.g_old = (sub == t) ? s->v_old : v_sub;  // k == 1: the subtracted rank's v was just overwritten
+        MF_TRY(solve_u(s, t, kSolve | (sub >= 0 ? kSub : 0) | (add ? (kAdd | kAddSep) : 0), a));
+    }
+    for (int it = 1; it < T; ++it) {
+        SweepVectors a, b;
+        a.g_new = u;
+        MF_TRY(solve_v(s, t, kSolve, a));
+        b.g_new = v;
+        MF_TRY(solve_u(s, t, kSolve, b));
+    }
+    s->pending = t;
+    return MF_OK;
+}
+
+// the reference's launch order: add-back, T x (v-solve, u-solve), subtract — CCD_CUDA.cu:347-378
+int ccd_rank_reference(mf_session* s, int t, bool add) {
+    const int T = s->prm.maxinneriter;
+    float* u = s->W + (int64_t)t * s->ldm;
+    float* v = s->H + (int64_t)t * s->ldn;
+    if (add) MF_TRY(update_both(s, t, true));
+    for (int it = 0; it < T; ++it) {
+        SweepVectors a, b;
+        a.g_new = u;
+        MF_TRY(solve_v(s, t, kSolve, a));
+        b.g_new = v;
+        MF_TRY(solve_u(s, t, kSolve, b));
+    }
+    return update_both(s, t, false);
+}
+
+int session_rmse(mf_session* s, double* out, double* seconds) {
+    if (s->nt <= 0) { *out = NAN; if (seconds) *seconds = 0; return MF_OK; }
+    MF_CUDA(cudaEventRecord(s->ev_c, s->st));
+    s->timer.start(F_RMSE);
+    if (s->prm.solver_type == MF_SOLVER_ALS)
+        MF_TRY(rmse_accumulate(s->nt, s->trow, s->tcol, s->tval, s->W, s->H, s->k, 1, s->k, 1, s->k, s->d_acc, s->sm_count, s->st));
+    else
+        MF_TRY(rmse_accumulate(s->nt, s->trow, s->tcol, s->tval, s->W, s->H, s->k, s->ldm, 1, s->ldn, 1, s->d_acc, s->sm_count, s->st));
+    s->timer.stop();
+    double acc = 0.0;
+    MF_CUDA(cudaMemcpyAsync(&acc, s->d_acc, sizeof(double), cudaMemcpyDeviceToHost, s->st));
+    MF_CUDA(cudaEventRecord(s->ev_b, s->st));
+    MF_CUDA(cudaStreamSynchronize(s->st));
+    *out = sqrt(acc / (double)s->nt);
+    if (seconds) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, s->ev_c, s->ev_b);
+        *seconds = ms * 1e-3;
+    }
+    return MF_OK;
+}
+
+int check_ratings(const mf_ratings* R) {
+    MF_REQUIRE(R != nullptr, "ratings pointer is NULL");
+    MF_REQUIRE(R->rows > 0 && R->cols > 0 && R->nnz >= 0, "bad shape %lld x %lld, nnz %lld", (long long)R->rows,
+               (long long)R->cols, (long long)R->nnz);
+    MF_REQUIRE(R->rows < ((int64_t)1 << 32) && R->cols < ((int64_t)1 << 32) && R->nnz < ((int64_t)1 << 32),
+               "indices are uint32 (src/pmf_util.h:146-148): shape out of range");
+    MF_REQUIRE(R->csr_row_ptr && R->csc_col_ptr, "ptr arrays are NULL");
+    MF_REQUIRE(R->nnz == 0 || (R->csr_col_idx && R->csr_val && R->csc_row_idx && R->csc_val), "index/value arrays are NULL");
+    return MF_OK;
+}
+
+int create_impl(const mf_ratings* R, const mf_testset* T, const mf_params* params, int rank, int nranks,
+                const void* nccl_id, mf_session** out) {
+    MF_REQUIRE(out != nullptr && params != nullptr, "NULL argument");
+    *out = nullptr;
+    MF_TRY(check_ratings(R));
+    MF_REQUIRE(params->k >= 1, "k must be >= 1");
+    MF_REQUIRE(nranks >= 1 && rank >= 0 && rank < nranks, "bad rank %d of %d", rank, nranks);
+    MF_REQUIRE(params->solver_type == MF_SOLVER_CCD || params->solver_type == MF_SOLVER_ALS, "bad solver_type");
+    int ndev = 0;
+    MF_CUDA(cudaGetDeviceCount(&ndev));
+    MF_REQUIRE(params->device >= 0 && params->device < ndev, "device %d not present (%d CUDA devices)", params->device, ndev);
+    MF_CUDA(cudaSetDevice(params->device));
+
+    mf_session* s = new mf_session();
+    s->prm = *params;
+    s->device = params->device;
+    s->rank = rank;
+    s->nranks = nranks;
+    s->rows = R->rows; s->cols = R->cols; s->nnz = R->nnz;
+    s->k = (int)params->k;
+    int rc = MF_OK;
+    auto fail = [&](int code) { mf_session_destroy(s); return code; };
+
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, s->device) != cudaSuccess) { set_error("cudaGetDeviceProperties failed"); return fail(MF_ERR_CUDA); }
+    s->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking) != cudaSuccess) { set_error("cudaStreamCreate failed"); return fail(MF_ERR_CUDA); }
+    cudaEventCreate(&s->ev_a); cudaEventCreate(&s->ev_b); cudaEventCreate(&s->ev_c);
+    s->timer.st = s->st;
+    s->timer.enabled = true;
+
+    std::vector<uint32_t> rp, cp;
+    if ((rc = fetch_ptr(R->csr_row_ptr, R->rows + 1, rp)) != MF_OK) return fail(rc);
+    if ((rc = fetch_ptr(R->csc_col_ptr, R->cols + 1, cp)) != MF_OK) return fail(rc);
+    if (rp[0] != 0 || cp[0] != 0 || rp[R->rows] != (uint32_t)R->nnz || cp[R->cols] != (uint32_t)R->nnz) {
+        set_error("ptr arrays inconsistent with nnz (ptr[0]=%u/%u, ptr[last]=%u/%u, nnz=%lld)", rp[0], cp[0], rp[R->rows],
+                  cp[R->cols], (long long)R->nnz);
+        return fail(MF_ERR_ARG);
+    }
+    partition_host(rp, nranks, s->row_bound);
+    partition_host(cp, nranks, s->col_bound);
+    if ((rc = upload_side(s->csr, rp, s->row_bound[rank], s->row_bound[rank + 1], R->csr_col_idx, R->csr_val, R->cols, s->st)) != MF_OK) return fail(rc);
+    if ((rc = upload_side(s->csc, cp, s->col_bound[rank], s->col_bound[rank + 1], R->csc_row_idx, R->csc_val, R->rows, s->st)) != MF_OK) return fail(rc);
+
+    const bool ccd = params->solver_type == MF_SOLVER_CCD;
+    if (ccd) {
+        s->panel = params->layout == MF_LAYOUT_PANEL;
+        if (s->panel) {
+            bool ok_r = true, ok_c = true;
+            if ((rc = side_check_sorted(s->csr, &ok_r, s->st)) != MF_OK) return fail(rc);
+            if ((rc = side_check_sorted(s->csc, &ok_c, s->st)) != MF_OK) return fail(rc);
+            if (!ok_r || !ok_c) s->panel = false;  // the panel cut needs ascending indices inside a segment
+        }
+        if (s->panel) {
+            // shared-memory vectors a sweep may need: CSC side 2 (u_new, u_old); CSR side 3 (v_new, v_add, v_old)
+            int cap_c = panel_cap(2), cap_r = panel_cap(3);
+            if (params->panel_rows > 0) { cap_c = std::min(cap_c, params->panel_rows / 8 * 8); cap_r = std::min(cap_r, params->panel_rows / 8 * 8); }
+            else cap_c = std::min(cap_c, 24576);
+            const int chunk = params->chunk > 0 ? std::max(8, params->chunk / 8 * 8) : 1024;
+            if ((rc = side_build_panels(s->csc, choose_panel_rows(s->csc.gdim, std::max(cap_c, 8)), chunk, s->sm_count, s->st)) != MF_OK) return fail(rc);
+            if ((rc = side_build_panels(s->csr, choose_panel_rows(s->csr.gdim, std::max(cap_r, 8)), chunk, s->sm_count, s->st)) != MF_OK) return fail(rc);
+            // the caller-order index/value arrays are no longer needed: the residual lives in the panel arrays
+            cudaFree(s->csc.idx); s->csc.idx = nullptr; cudaFree(s->csc.val); s->csc.val = nullptr;
+            cudaFree(s->csr.idx); s->csr.idx = nullptr; cudaFree(s->csr.val); s->csr.val = nullptr;
+        }
+        s->ldm = round_up(s->rows, 32);
+        s->ldn = round_up(s->cols, 32);
+        if ((rc = dev_alloc(&s->W, (size_t)s->k * s->ldm)) != MF_OK) return fail(rc);
+        if ((rc = dev_alloc(&s->H, (size_t)s->k * s->ldn)) != MF_OK) return fail(rc);
+        if ((rc = dev_alloc(&s->v_old, (size_t)s->ldn)) != MF_OK) return fail(rc);
+        cudaMemsetAsync(s->W, 0, sizeof(float) * (size_t)s->k * s->ldm, s->st);
+        cudaMemsetAsync(s->H, 0, sizeof(float) * (size_t)s->k * s->ldn, s->st);
+        cudaMemsetAsync(s->v_old, 0, sizeof(float) * (size_t)s->ldn, s->st);
+    } else {
+        s->ldm = s->k; s->ldn = s->k;
+        if ((rc = dev_alloc(&s->W, (size_t)s->rows * s->k)) != MF_OK) return fail(rc);
+        if ((rc = dev_alloc(&s->H, (size_t)s->cols * s->k)) != MF_OK) return fail(rc);
+        cudaMemsetAsync(s->W, 0, sizeof(float) * (size_t)s->rows * s->k, s->st);
+        cudaMemsetAsync(s->H, 0, sizeof(float) * (size_t)s->cols * s->k, s->st);
+    }
+
+    s->nt = T ? T->nnz : 0;
+    if (s->nt > 0) {
+        if (!(T->row && T->col && T->val)) { set_error("test arrays are NULL"); return fail(MF_ERR_ARG); }
+        if ((rc = dev_alloc(&s->trow, (size_t)s->nt)) != MF_OK) return fail(rc);
+        if ((rc = dev_alloc(&s->tcol, (size_t)s->nt)) != MF_OK) return fail(rc);
+        if ((rc = dev_alloc(&s->tval, (size_t)s->nt)) != MF_OK) return fail(rc);
+        cudaMemcpyAsync(s->trow, T->row, sizeof(uint32_t) * (size_t)s->nt, cudaMemcpyDefault, s->st);
+        cudaMemcpyAsync(s->tcol, T->col, sizeof(uint32_t) * (size_t)s->nt, cudaMemcpyDefault, s->st);
+        cudaMemcpyAsync(s->tval, T->val, sizeof(float) * (size_t)s->nt, cudaMemcpyDefault, s->st);
+    }
+    if ((rc = dev_alloc(&s->d_acc, 1)) != MF_OK) return fail(rc);
+    if (nranks > 1) {
+        if (!nccl_id) { set_error("multi-GPU session needs the shared ncclUniqueId"); return fail(MF_ERR_ARG); }
+        if ((rc = dist_create(&s->dist, rank, nranks, nccl_id, s->device)) != MF_OK) return fail(rc);
+    }
+    cudaError_t e = cudaStreamSynchronize(s->st);
+    if (e != cudaSuccess) { set_error("session setup failed: %s", cudaGetErrorString(e)); return fail(MF_ERR_CUDA); }
+    *out = s;
+    return MF_OK;
+}
+
+// HBM bytes one sweep launch of a family has to move on this session (compulsory traffic of the layout)
+int64_t sweep_bytes(const mf_session* s, const Side& sd, int mode) {
+    const bool write = mode & (kSub | kAdd);
+    if (s->panel) {
+        int64_t b = sd.npad * (2 + 4 + (write ? 4 : 0)) + sd.nitems * 16;
+        if (mode & kSolve) b += sd.nslots * 8 * 2 + sd.nseg * (4 + 4 + 4);
+        return b + (int64_t)panel_sweep_vectors(mode) * sd.gdim * 4;
+    }
+    int64_t b = sd.nnz * (4 + 4 + (write ? 4 : 0)) + sd.nseg * 4;
+    if (mode & kSolve) b += sd.nseg * 4;
+    return b + sd.gdim * 4;
+}
+
+}  // namespace
+}  // namespace mf
+
+using namespace mf;
+
+extern "C" {
+
+int mf_abi_version(void) { return MF_ABI_VERSION; }
+const char* mf_last_error(void) { return mf::get_error(); }
+
+int mf_device_count(int* count) {
+    MF_REQUIRE(count != nullptr, "NULL argument");
+    *count = 0;
+    MF_CUDA(cudaGetDeviceCount(count));
+    return MF_OK;
+}
+
+void mf_params_default(mf_params* p) {
+    if (!p) return;
+    memset(p, 0, sizeof(*p));
+    p->solver_type = MF_SOLVER_CCD;  // src/pmf.h:27-40
+    p->k = 10;
+    p->threads = 4;
+    p->maxiter = 5;
+    p->maxinneriter = 1;
+    p->lambda = 0.1f;
+    p->eps = 1e-3f;
+    p->nBlocks = 32;
+    p->nThreadsPerBlock = 256;
+}
+
+int mf_session_create(const mf_ratings* R, const mf_testset* T, const mf_params* params, mf_session** out) {
+    return create_impl(R, T, params, 0, 1, nullptr, out);
+}
+
+int mf_dist_unique_id(void* id128) { return dist_unique_id(id128); }
+
+int mf_session_create_dist(const mf_ratings* R, const mf_testset* T, const mf_params* params, int rank, int nranks,
+                           const void* nccl_unique_id, mf_session** out) {
+    return create_impl(R, T, params, rank, nranks, nccl_unique_id, out);
+}
+
+int mf_session_destroy(mf_session* s) {
+    if (!s) return MF_OK;
+    cudaSetDevice(s->device);
+    if (s->st) cudaStreamSynchronize(s->st);
+    if (s->dist) dist_destroy(s->dist);
+    side_free(s->csc);
+    side_free(s->csr);
+    void* ptrs[] = {s->W, s->H, s->v_old, s->trow, s->tcol, s->tval, s->d_acc};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    s->timer.destroy();
+    if (s->ev_a) cudaEventDestroy(s->ev_a);
+    if (s->ev_b) cudaEventDestroy(s->ev_b);
+    if (s->ev_c) cudaEventDestroy(s->ev_c);
+    if (s->st) cudaStreamDestroy(s->st);
+    delete s;
+    return MF_OK;
+}
+
+int mf_session_set_factors(mf_session* s, const float* W, const float* H) {
+    MF_REQUIRE(s && W, "NULL argument");
+    MF_CUDA(cudaSetDevice(s->device));
+    if (s->prm.solver_type == MF_SOLVER_CCD) {
+        MF_CUDA(cudaMemcpy2DAsync(s->W, sizeof(float) * s->ldm, W, sizeof(float) * s->rows, sizeof(float) * s->rows, s->k, cudaMemcpyDefault, s->st));
+        if (H) MF_CUDA(cudaMemcpy2DAsync(s->H, sizeof(float) * s->ldn, H, sizeof(float) * s->cols, sizeof(float) * s->cols, s->k, cudaMemcpyDefault, s->st));
+        else MF_CUDA(cudaMemsetAsync(s->H, 0, sizeof(float) * (size_t)s->k * s->ldn, s->st));  // CCD_CUDA.cu:287
+    } else {
+        MF_REQUIRE(H != nullptr, "ALS needs initial H (ALS_CUDA.cu:237-243)");
+        MF_CUDA(cudaMemcpyAsync(s->W, W, sizeof(float) * (size_t)s->rows * s->k, cudaMemcpyDefault, s->st));
+        MF_CUDA(cudaMemcpyAsync(s->H, H, sizeof(float) * (size_t)s->cols * s->k, cudaMemcpyDefault, s->st));
+    }
+    MF_CUDA(cudaStreamSynchronize(s->st));
+    return MF_OK;
+}
+
+int mf_session_get_factors(mf_session* s, float* W, float* H) {
+    MF_REQUIRE(s, "NULL argument");
+    MF_CUDA(cudaSetDevice(s->device));
+    if (s->prm.solver_type == MF_SOLVER_CCD) {
+        if (W) MF_CUDA(cudaMemcpy2DAsync(W, sizeof(float) * s->rows, s->W, sizeof(float) * s->ldm, sizeof(float) * s->rows, s->k, cudaMemcpyDefault, s->st));
+        if (H) MF_CUDA(cudaMemcpy2DAsync(H, sizeof(float) * s->cols, s->H, sizeof(float) * s->ldn, sizeof(float) * s->cols, s->k, cudaMemcpyDefault, s->st));
+    } else {
+        if (W) MF_CUDA(cudaMemcpyAsync(W, s->W, sizeof(float) * (size_t)s->rows * s->k, cudaMemcpyDefault, s->st));
+        if (H) MF_CUDA(cudaMemcpyAsync(H, s->H, sizeof(float) * (size_t)s->cols * s->k, cudaMemcpyDefault, s->st));
+    }
+    MF_CUDA(cudaStreamSynchronize(s->st));
+    return MF_OK;
+}
+
+int mf_session_get_values(mf_session* s, float* csr_val, float* csc_val) {
+    MF_REQUIRE(s, "NULL argument");
+    MF_CUDA(cudaSetDevice(s->device));
+    if (s->prm.solver_type == MF_SOLVER_CCD) MF_TRY(flush_pending(s));
+    Side* sides[2] = {&s->csr, &s->csc};
+    float* dsts[2] = {csr_val, csc_val};
+    for (int i = 0; i < 2; ++i) {
+        Side& sd = *sides[i];
+        if (!dsts[i] || sd.nnz == 0) continue;
+        if (s->panel) {
+            float* tmp = nullptr;
+            MF_TRY(dev_alloc(&tmp, (size_t)sd.nnz));
+            int rc = side_panel_to_raw(sd, tmp, s->st);
+            if (rc == MF_OK && cudaMemcpyAsync(dsts[i], tmp, sizeof(float) * (size_t)sd.nnz, cudaMemcpyDefault, s->st) != cudaSuccess) rc = MF_ERR_CUDA;
+            cudaStreamSynchronize(s->st);
+            cudaFree(tmp);
+            MF_TRY(rc);
+        } else {
+            MF_CUDA(cudaMemcpyAsync(dsts[i], sd.val, sizeof(float) * (size_t)sd.nnz, cudaMemcpyDefault, s->st));
+        }
+    }
+    MF_CUDA(cudaStreamSynchronize(s->st));
+    return MF_OK;
+}
+
+int mf_session_rmse(mf_session* s, double* rmse) {
+    MF_REQUIRE(s && rmse, "NULL argument");
+    MF_CUDA(cudaSetDevice(s->device));
+    int rc = session_rmse(s, rmse, nullptr);
+    s->timer.collect(s->fam_seconds, s->fam_launches);
+    return rc;
+}
+
+int mf_session_ccdpp_iterate(mf_session* s, int n_outer, mf_iter_stats* stats) {
+    MF_REQUIRE(s && n_outer >= 0, "bad argument");
+    if (s->prm.solver_type != MF_SOLVER_CCD) { set_error("not a CCD++ session"); return MF_ERR_STATE; }
+    MF_CUDA(cudaSetDevice(s->device));
+    s->timer.enabled = s->prm.no_launch_timing == 0;
+    for (int f = 0; f < F_COUNT; ++f) { s->fam_seconds[f] = 0; s->fam_launches[f] = 0; }
+    double total = 0.0;
+    for (int it = 0; it < n_outer; ++it) {
+        const bool add = s->outer_done > 0;  // src/CCD.cpp:100: add-back only from the second outer iteration on
+        double before[F_COUNT];
+        memcpy(before, s->fam_seconds, sizeof(before));
+        MF_CUDA(cudaEventRecord(s->ev_a, s->st));
+        for (int t = 0; t < s->k; ++t) {
+            if (s->prm.schedule == MF_SCHEDULE_REFERENCE) MF_TRY(ccd_rank_reference(s, t, add));
+            else MF_TRY(ccd_rank_fused(s, t, add));
+        }
+        MF_CUDA(cudaEventRecord(s->ev_b, s->st));
+        MF_CUDA(cudaStreamSynchronize(s->st));
+        float ms = 0.f;
+        MF_CUDA(cudaEventElapsedTime(&ms, s->ev_a, s->ev_b));
+        total += ms * 1e-3;
+        s->outer_done++;
+        s->timer.collect(s->fam_seconds, s->fam_launches);
+        if (stats) {
+            mf_iter_stats& o = stats[it];
+            const double upd = s->fam_seconds[F_UPDATE] - before[F_UPDATE];
+            o.update_time = upd;
+            o.rank_time = ms * 1e-3 - upd;
+            MF_TRY(session_rmse(s, &o.rmse, &o.rmse_time));
+            s->timer.collect(s->fam_seconds, s->fam_launches);
+        }
+    }
+    s->last_seconds = total;
+    return MF_OK;
+}
+
+int mf_session_als_iterate(mf_session* s, int n_iter, mf_iter_stats* stats) {
+    MF_REQUIRE(s && n_iter >= 0, "bad argument");
+    if (s->prm.solver_type != MF_SOLVER_ALS) { set_error("not an ALS session"); return MF_ERR_STATE; }
+    MF_CUDA(cudaSetDevice(s->device));
+    s->timer.enabled = s->prm.no_launch_timing == 0;
+    for (int f = 0; f < F_COUNT; ++f) { s->fam_seconds[f] = 0; s->fam_launches[f] = 0; }
+    double total = 0.0;
+    for (int it = 0; it < n_iter; ++it) {
+        MF_CUDA(cudaEventRecord(s->ev_a, s->st));
+        MF_TRY(mf_session_als_half(s, MF_SIDE_CSR));
+        MF_TRY(mf_session_als_half(s, MF_SIDE_CSC));
+        MF_CUDA(cudaEventRecord(s->ev_b, s->st));
+        MF_CUDA(cudaStreamSynchronize(s->st));
+        float ms = 0.f;
+        MF_CUDA(cudaEventElapsedTime(&ms, s->ev_a, s->ev_b));
+        total += ms * 1e-3;
+        s->outer_done++;
+        s->timer.collect(s->fam_seconds, s->fam_launches);
+        if (stats) {
+            mf_iter_stats& o = stats[it];
+            o.rank_time = 0.0;
+            o.update_time = ms * 1e-3;
+            MF_TRY(session_rmse(s, &o.rmse, &o.rmse_time));
+            s->timer.collect(s->fam_seconds, s->fam_launches);
+        }
+    }
+    s->last_seconds = total;
+    return MF_OK;
+}
+
+int mf_session_als_half(mf_session* s, int side) {
+    MF_REQUIRE(s && (side == MF_SIDE_CSR || side == MF_SIDE_CSC), "bad argument");
+    if (s->prm.solver_type != MF_SOLVER_ALS) { set_error("not an ALS session"); return MF_ERR_STATE; }
+    MF_CUDA(cudaSetDevice(s->device));
+    s->timer.start(F_ALS);
+    if (side == MF_SIDE_CSR) {  // W from H over the rows — src/ALS.cpp:98-158
+        MF_TRY(als_half_step(s->csr, s->H, s->W + s->csr.seg_offset * s->k, s->k, s->prm.lambda, s->sm_count, s->st));
+        s->timer.stop();
+        MF_TRY(gather_blocks(s, s->W, s->row_bound, s->k));
+    } else {                    // H from W over the columns — src/ALS.cpp:161-219
+        MF_TRY(als_half_step(s->csc, s->W, s->H + s->csc.seg_offset * s->k, s->k, s->prm.lambda, s->sm_count, s->st));
+        s->timer.stop();
+        MF_TRY(gather_blocks(s, s->H, s->col_bound, s->k));
+    }
+    return MF_OK;
+}
+
+int mf_session_ccd_solve(mf_session* s, int t, int side) {
+    MF_REQUIRE(s && t >= 0 && t < s->k && (side == MF_SIDE_CSR || side == MF_SIDE_CSC), "bad argument");
+    if (s->prm.solver_type != MF_SOLVER_CCD) { set_error("not a CCD++ session"); return MF_ERR_STATE; }
+    MF_CUDA(cudaSetDevice(s->device));
+    MF_TRY(flush_pending(s));
+    SweepVectors a;
+    if (side == MF_SIDE_CSC) { a.g_new = s->W + (int64_t)t * s->ldm; MF_TRY(solve_v(s, t, kSolve, a)); }
+    else                     { a.g_new = s->H + (int64_t)t * s->ldn; MF_TRY(solve_u(s, t, kSolve, a)); }
+    MF_CUDA(cudaStreamSynchronize(s->st));
+    s->timer.collect(s->fam_seconds, s->fam_launches);
+    return MF_OK;
+}
+
+int mf_session_ccd_update(mf_session* s, int t, int add) {
+    MF_REQUIRE(s && t >= 0 && t < s->k, "bad argument");
+    if (s->prm.solver_type != MF_SOLVER_CCD) { set_error("not a CCD++ session"); return MF_ERR_STATE; }
+    MF_CUDA(cudaSetDevice(s->device));
+    MF_TRY(flush_pending(s));
+    MF_TRY(update_both(s, t, add != 0));
+    MF_CUDA(cudaStreamSynchronize(s->st));
+    s->timer.collect(s->fam_seconds, s->fam_launches);
+    return MF_OK;
+}
+
+int mf_session_kernel_times(mf_session* s, mf_kernel_times* out) {
+    MF_REQUIRE(s && out, "NULL argument");
+    memset(out, 0, sizeof(*out));
+    out->solve_s = s->fam_seconds[F_SOLVE];       out->solve_launches = s->fam_launches[F_SOLVE];
+    out->fused_s = s->fam_seconds[F_FUSED];       out->fused_launches = s->fam_launches[F_FUSED];
+    out->update_s = s->fam_seconds[F_UPDATE];     out->update_launches = s->fam_launches[F_UPDATE];
+    out->finalize_s = s->fam_seconds[F_FINALIZE]; out->finalize_launches = s->fam_launches[F_FINALIZE];
+    out->als_s = s->fam_seconds[F_ALS];           out->als_launches = s->fam_launches[F_ALS];
+    out->rmse_s = s->fam_seconds[F_RMSE];         out->rmse_launches = s->fam_launches[F_RMSE];
+    out->collective_s = s->fam_seconds[F_COLLECTIVE]; out->collective_launches = s->fam_launches[F_COLLECTIVE];
+    if (s->prm.solver_type == MF_SOLVER_CCD) {
+        // average over the two copies: a "launch" of a family alternates between the CSC and the CSR side
+        out->solve_bytes = (sweep_bytes(s, s->csc, kSolve) + sweep_bytes(s, s->csr, kSolve)) / 2;
+        out->fused_bytes = (sweep_bytes(s, s->csc, kSolve | kSub | kAdd) + sweep_bytes(s, s->csr, kSolve | kSub | kAdd | kAddSep)) / 2;
+        out->update_bytes = (sweep_bytes(s, s->csc, kSub) + sweep_bytes(s, s->csr, kSub)) / 2;
+    }
+    return MF_OK;
+}
+
+int mf_session_last_seconds(mf_session* s, double* seconds) {
+    MF_REQUIRE(s && seconds, "NULL argument");
+    *seconds = s->last_seconds;
+    return MF_OK;
+}
+
+int mf_session_panel_layout(mf_session* s, int side, int64_t* n_padded, int64_t* n_items, int64_t* n_panels,
+                            uint16_t* idx16, float* val, uint32_t* items) {
+    MF_REQUIRE(s && (side == MF_SIDE_CSR || side == MF_SIDE_CSC), "bad argument");
+    if (!s->panel) { set_error("session does not use the panel layout"); return MF_ERR_STATE; }
+    MF_CUDA(cudaSetDevice(s->device));
+    const Side& sd = side == MF_SIDE_CSR ? s->csr : s->csc;
+    if (n_padded) *n_padded = sd.npad;
+    if (n_items) *n_items = sd.nitems;
+    if (n_panels) *n_panels = sd.npanels;
+    if (idx16 && sd.npad) MF_CUDA(cudaMemcpy(idx16, sd.idx16, sizeof(uint16_t) * (size_t)sd.npad, cudaMemcpyDefault));
+    if (val && sd.npad) MF_CUDA(cudaMemcpy(val, sd.pval, sizeof(float) * (size_t)sd.npad, cudaMemcpyDefault));
+    if (items && sd.nitems) MF_CUDA(cudaMemcpy(items, sd.items, sizeof(WorkItem) * (size_t)sd.nitems, cudaMemcpyDefault));
+    return MF_OK;
+}
+
+// ---- one-shot trainers ---------------------------------------------------------------------
+static int train_impl(const mf_ratings* R, const mf_testset* T, float* W, float* H, const mf_params* params,
+                      mf_iter_stats* stats, int solver) {
+    MF_REQUIRE(R && W && H && params, "NULL argument");
+    mf_params p = *params;
+    p.solver_type = solver;
+    mf_session* s = nullptr;
+    MF_TRY(mf_session_create(R, T, &p, &s));
+    int rc = mf_session_set_factors(s, W, solver == MF_SOLVER_CCD ? nullptr : H);
+    double rank_acc = 0.0, upd_acc = 0.0;
+    for (int it = 0; rc == MF_OK && it < p.maxiter; ++it) {
+        mf_iter_stats st;
+        rc = solver == MF_SOLVER_CCD ? mf_session_ccdpp_iterate(s, 1, &st) : mf_session_als_iterate(s, 1, &st);
+        if (rc != MF_OK) break;
+        rank_acc += st.rank_time;
+        upd_acc += st.update_time;
+        if (stats) stats[it] = st;
+        if (!p.quiet) {
+            if (solver == MF_SOLVER_CCD)  // line format of CCD_CUDA.cu:405
+                printf("[-INFO-] iteration num %d \trank_time %.4lf|%.4lf s \tupdate_time %.4lf|%.4lfs \tRMSE=%lf time:%fs\n",
+                       it + 1, st.rank_time, rank_acc, st.update_time, upd_acc, st.rmse, st.rmse_time);
+            else                          // line format of ALS_CUDA.cu:360
+                printf("[-INFO-] iteration num %d \tupdate_time %.4lf|%.4lfs \tRMSE=%lf time:%fs\n", it + 1,
+                       st.update_time, upd_acc, st.rmse, st.rmse_time);
+        }
+    }
+    if (rc == MF_OK) rc = mf_session_get_factors(s, W, H);
+    mf_session_destroy(s);
+    return rc;
+}
+
+int mf_ccdpp_train(const mf_ratings* R, const mf_testset* T, float* W, float* H, const mf_params* params,
+                   mf_iter_stats* stats) {
+    return train_impl(R, T, W, H, params, stats, MF_SOLVER_CCD);
+}
+
+int mf_als_train(const mf_ratings* R, const mf_testset* T, float* W, float* H, const mf_params* params,
+                 mf_iter_stats* stats) {
+    return train_impl(R, T, W, H, params, stats, MF_SOLVER_ALS);
+}
+
+}  // extern "C"

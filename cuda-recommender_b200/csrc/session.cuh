@@ -1,0 +1,71 @@
+// session.cuh — device-resident training state behind the C-ABI (include/mf_abi.h).
+#pragma once
+#include <vector>
+
+#include "ccd_kernels.cuh"
+#include "layout.cuh"
+
+namespace mf {
+
+enum Family { F_SOLVE = 0, F_FUSED, F_UPDATE, F_FINALIZE, F_ALS, F_RMSE, F_COLLECTIVE, F_COUNT };
+
+// CUDA-event stopwatch per kernel family, on the session stream.  Events are pooled; durations are
+// read back after the stream has been synchronised (collect()).
+struct FamilyTimer {
+    struct Span { cudaEvent_t a, b; int fam; };
+    std::vector<cudaEvent_t> pool;
+    size_t used = 0;
+    std::vector<Span> spans;
+    bool enabled = true;
+    cudaStream_t st = nullptr;
+    int open_fam = -1;
+    cudaEvent_t open_ev = nullptr;
+
+    cudaEvent_t take();
+    void start(int fam);
+    void stop();
+    void collect(double* seconds, int64_t* launches);  // adds into seconds[F_COUNT], launches[F_COUNT]
+    void destroy();
+};
+
+struct Dist;  // dist.cu
+
+}  // namespace mf
+
+struct mf_session {
+    mf_params prm;
+    int device = 0, sm_count = 148;
+    cudaStream_t st = nullptr;
+    int64_t rows = 0, cols = 0, nnz = 0;
+    int rank = 0, nranks = 1;
+    std::vector<int64_t> row_bound, col_bound;  // nranks+1 each
+    mf::Side csc, csr;
+    bool panel = false;
+    int k = 0;
+    int64_t ldm = 0, ldn = 0;  // CCD++: leading dimensions of W[k][ldm], H[k][ldn]
+    float *W = nullptr, *H = nullptr, *v_old = nullptr;
+    int64_t nt = 0;
+    uint32_t *trow = nullptr, *tcol = nullptr;
+    float* tval = nullptr;
+    double* d_acc = nullptr;
+    int outer_done = 0;
+    int pending = -1;  // rank whose subtraction from the residual is still deferred (fused schedule)
+    mf::FamilyTimer timer;
+    double fam_seconds[mf::F_COUNT] = {0};
+    int64_t fam_launches[mf::F_COUNT] = {0};
+    double last_seconds = 0.0;
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr;
+    mf::Dist* dist = nullptr;
+};
+
+namespace mf {
+// dist.cu
+int dist_unique_id(void* id128);
+int dist_create(Dist** out, int rank, int nranks, const void* id128, int device);
+int dist_destroy(Dist* d);
+// in-place all-gather of a full-length vector whose block r = [bound[r], bound[r+1]) was produced by rank r
+int dist_allgather_blocks(Dist* d, float* vec, const std::vector<int64_t>& bound, int64_t elems_per_unit, cudaStream_t st);
+int dist_allreduce_sum_double(Dist* d, double* dev_value, cudaStream_t st);
+// als.cu
+int als_half_step(const Side& s, const float* Y, float* X, int k, float lambda, int sm_count, cudaStream_t st);
+}  // namespace mf
