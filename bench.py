@@ -1,0 +1,399 @@
+#!/usr/bin/env python
+"""bench.py — seconds per CCD++ outer iteration on synthetic Netflix-shape ratings (BASELINE.json
+configs[2]: 480 189 x 17 770, 100 M nnz, k=40, lambda=0.05, T=3 inner iterations).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload NAME] ...
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+One "step" = one steady-state outer iteration (oiter >= 2, so the add-back of src/CCD.cpp:100 is
+included) over the whole rating matrix: k ranks x (fused first sweep of each copy + (T-1) x (v-solve,
+u-solve)).  Prints ONE JSON line (see the contract in the task statement):
+  value / ms_per_step  device time (CUDA events on the library's stream), ratings resident in HBM, max over ranks
+  e2e                  the same metric through the drop-in C-ABI call with HOST (pinned) buffers:
+                       mf_ccdpp_train(..., maxiter=E) wall time / E, uploads, layout build, per-iteration
+                       RMSE and the factor download included
+  roofline             dominant kernel family: compulsory HBM bytes of one launch / average launch time
+  cpu_baseline         the reference's own OpenMP path (oracle/_ref, unmodified sources) on this box's host
+                       cores, on a bounded sample (a few ranks of one steady-state outer iteration, scaled to k)
+`--impl reference` prints the reference-arm line: that CPU path alone, same config/metric/unit.
+"""
+import argparse
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "ccdpp_seconds_per_outer_iteration"
+UNIT = "s"
+
+WORKLOADS = {
+    # name: (shape, k, lambda, T)
+    "netflix_k40": ("netflix", 40, 0.05, 3),
+    "ml20m_k10": ("ml20m", 10, 0.05, 3),
+    "ml100k_k10": ("ml100k", 10, 0.05, 3),
+    "yahoo_k100": ("yahoo", 100, 0.05, 3),
+}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="netflix_k40", choices=sorted(WORKLOADS))
+    ap.add_argument("--schedule", default="fused", choices=["fused", "reference"])
+    ap.add_argument("--layout", default="panel", choices=["panel", "direct"])
+    ap.add_argument("--e2e-iters", type=int, default=3)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-ranks", type=int, default=2)
+    ap.add_argument("--no-launch-timing", action="store_true")
+    ap.add_argument("--panel-rows", type=int, default=0)
+    ap.add_argument("--chunk", type=int, default=0)
+    return ap.parse_args()
+
+
+def config_dict(args, extra=None):
+    shape, k, lam, T = WORKLOADS[args.workload]
+    from __graft_entry__ import load_package
+    load_package()
+    import cuda_recommender_b200.datagen as dg
+    rows, cols, nnz, nt = dg.SHAPES[shape]
+    cfg = {"workload": f"CCD++ k={k} lambda={lam} T={T} on synthetic {shape}-shape ratings ({rows}x{cols}, {nnz} nnz)",
+           "solver": "ccd++", "k": k, "lambda": lam, "inner_iters": T, "rows": rows, "cols": cols, "nnz": nnz,
+           "nnz_test": nt, "step": "one steady-state outer iteration over all ratings",
+           "l2_policy": "inputs larger than L2 (every sweep streams >= 0.6 GB; L2 is 126 MB)",
+           "parallelism": f"rowblock-csr x colblock-csc over {args.gpus} gpu(s)"}
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self):
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        if not shutil.which("nvidia-smi"):
+            return
+        fd, self.path = tempfile.mkstemp(suffix=".csv")
+        os.close(fd)
+        self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                     stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+
+    def stop(self, gpu_indices):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                if int(f[0]) not in gpu_indices:
+                    continue
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.path)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------
+# the reference CPU path on a bounded sample
+# ---------------------------------------------------------------------------------------------
+def cpu_reference_sample(dataset_dir, k_full, lam, T, sample_ranks, threads):
+    """Runs the unmodified reference ccdr1_OMP (oracle/_ref) with k = sample_ranks for two outer
+    iterations and scales the second (steady-state) iteration's rank_time + update_time — the
+    reference's own timers, src/CCD.cpp:158 — by k_full / sample_ranks.  Every rank does identical
+    work (two residual updates + T solve pairs over all nnz), so the scaling is exact in work."""
+    from oracle import ref
+    out = ref.train(dataset_dir, 0, sample_ranks, lam, 2, T, threads=threads)
+    it = out["iters"][-1]
+    per_outer = (it["rank_time"] + it["update_time"]) * (k_full / sample_ranks)
+    return per_outer, out
+
+
+def write_timing_dataset(data_np, tmpdir):
+    import cuda_recommender_b200.datagen as dg
+    # the reference's per-iteration RMSE is serial over the test set (src/tools.cpp:235-248) and not part
+    # of the metric: keep 1000 test ratings so it costs nothing
+    return dg.write_dataset(tmpdir, data_np, nnz_test_limit=1000)
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from __graft_entry__ import load_package
+    load_package()
+    import cuda_recommender_b200.datagen as dg
+    from oracle import ref
+    shape, k, lam, T = WORKLOADS[args.workload]
+    if not ref.available():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libmfref.so was not built"}))
+        return 0
+    import torch
+    dev = "cuda" if torch.cuda.is_available() else "cpu"
+    seed = 1 + list(dg.SHAPES).index(shape)
+    data = dg.to_numpy(dg.synth_named(shape, seed=seed, device=dev))
+    threads = os.cpu_count() or 1
+    tmp = tempfile.mkdtemp(prefix="mfref_", dir=os.environ.get("TMPDIR", "/tmp"))
+    try:
+        write_timing_dataset(data, tmp)
+        del data
+        times = []
+        for i in range(args.warmup + args.steps):
+            per_outer, _ = cpu_reference_sample(tmp, k, lam, T, args.cpu_sample_ranks, threads)
+            if i >= args.warmup:
+                times.append(per_outer)
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+    val = sum(times) / len(times)
+    sample = (f"ccdr1_OMP (unmodified reference sources) with k={args.cpu_sample_ranks} of {k} ranks, 2 outer iterations, "
+              f"steady-state iteration's rank_time+update_time scaled x{k / args.cpu_sample_ranks:g}")
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": val * 1e3, "higher_is_better": False, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_dict(args),
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "reference", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------
+# the B200 arm
+# ---------------------------------------------------------------------------------------------
+def run_b200_arm(args):
+    import numpy as np
+    import torch
+    from __graft_entry__ import load_package
+    pkg = load_package()
+    import cuda_recommender_b200.datagen as dg
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if args.gpus > 1 and world == 1:
+        raise SystemExit("launch multi-GPU runs with torch.distributed.run (one process per GPU)")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the product path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier(device_ids=[local_rank])
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    shape, k, lam, T = WORKLOADS[args.workload]
+    seed = 1 + list(dg.SHAPES).index(shape)
+    t0 = time.time()
+    data = dg.synth_named(shape, seed=seed, device=dev)  # same seed on every rank -> identical ratings
+    torch.cuda.synchronize()
+    gen_s = time.time() - t0
+    rows, cols, nnz = data["rows"], data["cols"], data["nnz"]
+
+    params = pkg.make_params(pkg.SOLVER_CCD, k=k, lam=lam, maxiter=args.steps, maxinner=T, device=local_rank,
+                             schedule=pkg.SCHEDULE_REFERENCE if args.schedule == "reference" else pkg.SCHEDULE_FUSED,
+                             layout=pkg.LAYOUT_DIRECT if args.layout == "direct" else pkg.LAYOUT_PANEL,
+                             panel_rows=args.panel_rows, chunk=args.chunk, no_launch_timing=int(args.no_launch_timing))
+    nccl_id = None
+    if world > 1:
+        idt = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            idt.copy_(torch.tensor(list(pkg.nccl_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        nccl_id = bytes(idt.cpu().tolist())
+
+    # factors exactly as the reference seeds them (tools.cpp:165-173): libc srand(0)/rand()
+    W0 = pkg.initial_col(k, rows)
+
+    sess = pkg.Session(data, params, rank=rank, nranks=world, nccl_id=nccl_id)
+    sess.set_factors(W0)
+    # host copies for the end-to-end leg / CPU baseline before the device copies go away
+    need_host = (not args.no_e2e) or (rank == 0 and world == 1 and not args.no_cpu_baseline)
+    for key in ("coo_row", "coo_col", "coo_val"):
+        data.pop(key, None)
+    host = dg.to_numpy(data) if need_host else None
+    del data
+    torch.cuda.empty_cache()
+
+    # ---- warm-up, then K timed steps bracketed by barrier + synchronize
+    if args.warmup > 0:
+        sess.iterate(args.warmup, want_stats=False)
+    sampler = ClockSampler()
+    barrier()
+    if rank == 0:
+        sampler.start()
+    t0 = time.perf_counter()
+    sess.iterate(args.steps, want_stats=False)
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop(set(range(world))) if rank == 0 else None
+    dev_s = max_over_ranks(sess.last_seconds())
+    wall = max_over_ranks(wall)
+    kt = sess.kernel_times()
+    rmse = sess.rmse()
+    sec_per_iter = dev_s / args.steps
+
+    launches = int(sum(kt[n] for n in kt if n.endswith("_launches") and not n.startswith("collective")))
+    fam = {}
+    for name in ("solve", "fused", "update"):
+        if kt[name + "_launches"]:
+            fam[name] = (kt[name + "_s"], kt[name + "_launches"], kt[name + "_bytes"])
+    roofline = None
+    if fam:
+        top = max(fam, key=lambda n: fam[n][0])
+        secs, n, nbytes = fam[top]
+        avg = secs / n
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        achieved = nbytes / avg / 1e9
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get(args.workload, {}).get(top)
+        except Exception:
+            pass
+        survey_bytes = {"solve": 8, "fused": 12, "update": 12}[top] * (nnz / world)
+        roofline = {"bound": "hbm", "kernel": f"ccd {top} sweep ({args.layout} layout)", "achieved": achieved, "peak": peak,
+                    "unit": "GB/s", "frac": achieved / peak, "peak_source": "measured" if peaks else "fallback",
+                    "traffic": traffic, "bytes_per_launch": nbytes, "avg_launch_ms": avg * 1e3, "launches": n,
+                    "share_of_step": secs / dev_s if dev_s > 0 else None,
+                    "achieved_at_survey_bytes": survey_bytes / avg / 1e9,
+                    "families_ms_per_step": {f: fam[f][0] / args.steps * 1e3 for f in fam} |
+                                            {"finalize": kt["finalize_s"] / args.steps * 1e3,
+                                             "collective": kt["collective_s"] / args.steps * 1e3}}
+
+    # ---- end to end through the public drop-in call, host buffers, every copy inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        E = max(1, args.e2e_iters)
+        sess.close()
+        pinned = {}
+        for key, v in host.items():
+            if isinstance(v, np.ndarray):
+                tns = torch.from_numpy(v.view(np.int32) if v.dtype == np.uint32 else v).pin_memory()
+                pinned[key] = tns.numpy().view(v.dtype)
+                pinned["_keep_" + key] = tns
+            else:
+                pinned[key] = v
+        Wt = torch.from_numpy(W0.copy()).pin_memory()
+        Ht = torch.zeros((k, cols), dtype=torch.float32).pin_memory()
+        p2 = pkg.make_params(pkg.SOLVER_CCD, k=k, lam=lam, maxiter=E, maxinner=T, device=local_rank,
+                             schedule=params.schedule, layout=params.layout, panel_rows=args.panel_rows, chunk=args.chunk,
+                             no_launch_timing=1)
+        h2d = sum(v.nbytes for kk, v in pinned.items() if isinstance(v, np.ndarray) and not kk.startswith("coo_")) + Wt.numel() * 4
+        d2h = (Wt.numel() + Ht.numel()) * 4 + 8 * E
+        barrier()
+        t0 = time.perf_counter()
+        if world == 1:
+            st = pkg.ccdpp_train(pinned, Wt.numpy(), Ht.numpy(), p2)
+            e2e_rmse = st[-1]["rmse"]
+        else:
+            s2 = pkg.Session(pinned, p2, rank=rank, nranks=world, nccl_id=nccl_id_again(pkg, dist, dev, rank))
+            s2.set_factors(Wt.numpy())
+            st = s2.iterate(E)
+            Wout, Hout = s2.get_factors()
+            e2e_rmse = st[-1]["rmse"]
+            s2.close()
+        barrier()
+        e2e_wall = max_over_ranks(time.perf_counter() - t0)
+        e2e = {"value": e2e_wall / E, "unit": UNIT, "h2d_bytes_per_step": int(h2d / E), "d2h_bytes_per_step": int(d2h / E),
+               "call": "mf_ccdpp_train" if world == 1 else "mf_session_create_dist+iterate+get_factors",
+               "outer_iters_per_call": E, "call_seconds": e2e_wall, "rmse": e2e_rmse}
+
+    # ---- the reference's CPU path on this box's host cores (rank 0, single-GPU runs only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import ref
+        if ref.available():
+            threads = os.cpu_count() or 1
+            tmp = tempfile.mkdtemp(prefix="mfref_", dir=os.environ.get("TMPDIR", "/tmp"))
+            try:
+                write_timing_dataset(host, tmp)
+                val, _ = cpu_reference_sample(tmp, k, lam, T, args.cpu_sample_ranks, threads)
+            finally:
+                shutil.rmtree(tmp, ignore_errors=True)
+            cpu = {"value": val, "unit": UNIT, "cores": threads, "kind": "reference",
+                   "sample": f"unmodified reference ccdr1_OMP, k={args.cpu_sample_ranks} of {k} ranks x 2 outer iterations, "
+                             f"steady-state iteration scaled x{k / args.cpu_sample_ranks:g}"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": sec_per_iter, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": sec_per_iter * 1e3, "higher_is_better": False, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": config_dict(args, {"schedule": args.schedule, "layout": args.layout, "datagen_s": round(gen_s, 2)}),
+                "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+                "wall_ms_per_step": wall / args.steps * 1e3, "rmse_after_run": rmse,
+                "outer_iterations_done": args.warmup + args.steps}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+def nccl_id_again(pkg, dist, dev, rank):
+    import torch
+    idt = torch.zeros(128, dtype=torch.uint8, device=dev)
+    if rank == 0:
+        idt.copy_(torch.tensor(list(pkg.nccl_unique_id()), dtype=torch.uint8))
+    dist.broadcast(idt, 0)
+    return bytes(idt.cpu().tolist())
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_b200_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -63,7 +63,7 @@ class mf_kernel_times(C.Structure):
 
 # every symbol include/mf_abi.h declares (tests/test_abi_symbols.py checks header <-> library <-> this list)
 ABI_SYMBOLS = [
-    "mf_abi_version", "mf_last_error", "mf_device_count", "mf_params_default",
+    "mf_abi_version", "mf_last_error", "mf_device_count", "mf_params_default", "mf_host_initial_col",
     "mf_ccdpp_train", "mf_als_train",
     "mf_session_create", "mf_session_destroy", "mf_dist_unique_id", "mf_session_create_dist",
     "mf_session_set_factors", "mf_session_get_factors", "mf_session_get_values",
@@ -94,6 +94,8 @@ def lib():
         L.mf_params_default.argtypes = [C.POINTER(mf_params)]
         L.mf_params_default.restype = None
         L.mf_device_count.argtypes = [C.POINTER(C.c_int)]
+        L.mf_host_initial_col.argtypes = [vp, C.c_int64, C.c_int64]
+        L.mf_host_initial_col.restype = None
         L.mf_ccdpp_train.argtypes = [C.POINTER(mf_ratings), C.POINTER(mf_testset), vp, vp, C.POINTER(mf_params), vp]
         L.mf_als_train.argtypes = L.mf_ccdpp_train.argtypes
         L.mf_session_create.argtypes = [C.POINTER(mf_ratings), C.POINTER(mf_testset), C.POINTER(mf_params), C.POINTER(vp)]
@@ -123,6 +125,13 @@ def lib():
 def _check(rc):
     if rc != MF_OK:
         raise MFError(f"mf error {rc}: {lib().mf_last_error().decode(errors='replace')}")
+
+
+def initial_col(k, n):
+    """Host-side factor seeding as the reference's initial_col(X, k, n) (tools.cpp:165): X[k, n]."""
+    X = np.empty((k, n), np.float32)
+    lib().mf_host_initial_col(X.ctypes.data, k, n)
+    return X
 
 
 def device_count():

@@ -125,6 +125,9 @@ int mf_abi_version(void);
 const char* mf_last_error(void);
 int mf_device_count(int* count);
 void mf_params_default(mf_params* p); /* the reference defaults, src/pmf.h:26-42 */
+/* host-side factor seeding exactly as the reference does it (initial_col, src/tools.cpp:165-173):
+ * srand(0); for i<n, for j<k: X[j*n + i] = 0.1f*(float(rand())/RAND_MAX) + 0.001f                 */
+void mf_host_initial_col(float* X, int64_t k, int64_t n);
 
 /* ---- one-shot trainers: the drop-in for kernel_wrapper_ccdpp_NV / kernel_wrapper_als_NV ----
  * W/H in: initial factors (CCD++ ignores H and starts it at zero, CCD_CUDA.cu:263-269,287);

@@ -1,0 +1,64 @@
+"""numpy restatement of the PANEL layout (cuda-recommender_b200/csrc/layout.cuh, prep.cu) — the
+integer-tier checker for the layout the GPU builds: pieces = (panel, segment) cuts of every segment,
+panel-major storage, 8-entry padding with idx16 = panel_rows / val = 0, work items of <= chunk
+entries, slots of a segment ordered (panel, chunk).  Test infrastructure only."""
+import numpy as np
+
+SMEM_MAX = 227 * 1024 - 64
+
+
+def panel_cap(nvec):
+    return (SMEM_MAX // (4 * nvec) - 8) // 8 * 8
+
+
+def choose_panel_rows(gdim, cap):
+    if gdim <= cap:
+        return max(8, -(-gdim // 8) * 8)
+    npan = -(-gdim // cap)
+    return -(-(-(-gdim // npan)) // 8) * 8
+
+
+def session_panel_rows(gdim, side_is_csr, user_panel_rows=0):
+    cap = panel_cap(3 if side_is_csr else 2)
+    if user_panel_rows > 0:
+        cap = min(cap, user_panel_rows // 8 * 8)
+    elif not side_is_csr:
+        cap = min(cap, 24576)
+    return choose_panel_rows(gdim, max(cap, 8))
+
+
+def panel_layout(ptr, idx, val, gdim, panel_rows, chunk):
+    ptr = ptr.astype(np.int64)
+    nseg = len(ptr) - 1
+    P = max(1, -(-gdim // panel_rows))
+    idx16, pval, items = [], [], []
+    seg_items = np.zeros(nseg, np.int64)
+    pieces = []
+    for p in range(P):
+        lo_key, hi_key = p * panel_rows, (p + 1) * panel_rows
+        for s in range(nseg):
+            seg = idx[ptr[s]:ptr[s + 1]]
+            a = ptr[s] + np.searchsorted(seg, lo_key, "left")
+            b = ptr[s] + np.searchsorted(seg, hi_key, "left")
+            cnt = b - a
+            pd = -(-cnt // 8) * 8
+            nit = -(-pd // chunk)
+            pieces.append((p, s, a, cnt, pd, nit))
+            seg_items[s] += nit
+    slot_ptr = np.concatenate([[0], np.cumsum(seg_items)])
+    before = np.zeros(nseg, np.int64)
+    pos = 0
+    for p, s, a, cnt, pd, nit in pieces:
+        if pd == 0:
+            continue
+        loc = (idx[a:a + cnt].astype(np.int64) - p * panel_rows)
+        idx16.append(np.concatenate([loc, np.full(pd - cnt, panel_rows)]).astype(np.uint16))
+        pval.append(np.concatenate([val[a:a + cnt], np.zeros(pd - cnt, np.float32)]).astype(np.float32))
+        for j in range(nit):
+            items.append((pos + j * chunk, min(chunk, pd - j * chunk), s, slot_ptr[s] + before[s] + j))
+        before[s] += nit
+        pos += pd
+    return dict(n_panels=P, n_padded=pos, n_items=len(items),
+                idx16=np.concatenate(idx16) if idx16 else np.zeros(0, np.uint16),
+                val=np.concatenate(pval) if pval else np.zeros(0, np.float32),
+                items=np.array(items, np.uint32).reshape(-1, 4))
