@@ -1,0 +1,11 @@
+#!/bin/bash
+# parameter sweep of the bench (short runs, no e2e / CPU legs); one JSON line per variant in gpurun_out/sweep.jsonl
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out; : > gpurun_out/sweep.jsonl
+while read -r ARGS; do
+  [ -z "$ARGS" ] && continue
+  echo "== $ARGS"
+  OUT=$(timeout 600 python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline $ARGS 2> gpurun_out/sweep.err | tail -1)
+  echo "{\"args\": \"$ARGS\", \"line\": $OUT}" >> gpurun_out/sweep.jsonl
+  echo "$OUT" | python -c "import sys,json; l=json.loads(sys.stdin.read()); r=l['roofline']; print(round(l['ms_per_step'],2),'ms/step', r['kernel'], round(r['achieved']), 'GB/s', {k:round(v,2) for k,v in r['families_ms_per_step'].items()})" 2>/dev/null || tail -3 gpurun_out/sweep.err
+done

@@ -39,12 +39,24 @@ def test_half_step_parity(gpu, port, data_factory, shape, k):
 
 @pytest.mark.parametrize("name", GOLDEN_ALS)
 def test_trajectory_vs_reference_fixture(gpu, port, golden, name):
+    """RMSE within 1e-4 of the reference at every iteration.  Factors: the reference's FP32
+    explicit-inverse path is itself ~2e-3 (relative l2 of H) away from FP64 arithmetic on these
+    fixtures after 2-3 iterations (ill-conditioned rows with fewer ratings than k, lambda unscaled), so
+    the bar is (i) no further from the FP64 yardstick than the reference is, (ii) distance to the
+    reference bounded by 1.5x the reference's own distance to FP64 (+5e-4)."""
     d, z = golden(name)
+    csr, csc, test = sides(d)
     k, lam, iters = int(z["k"]), float(z["lam"]), int(z["maxiter"])
-    W, H = port.initial_col(d["rows"], k), port.initial_col(d["cols"], k)
+    W0, H0 = port.initial_col(d["rows"], k), port.initial_col(d["cols"], k)
+    W, H = W0.copy(), H0.copy()
     st = gpu.als_train(d, W, H, gpu.make_params(gpu.SOLVER_ALS, k=k, lam=lam, maxiter=iters))
     assert np.allclose([x["rmse"] for x in st], z["rmse_printed"], atol=1e-4, rtol=0)
-    assert rel_l2(W, z["W"]) <= 2e-3 and rel_l2(H, z["H"]) <= 2e-3
+    hi = port.als(d["rows"], d["cols"], csr, csc, W0, H0, k, lam, iters, test=test, f64=True)
+    for got, ref32, f64 in ((W, z["W"], hi["W"]), (H, z["H"], hi["H"])):
+        ref_err = rel_l2(ref32, f64)
+        print(name, "gpu-f64", rel_l2(got, f64), "ref-f64", ref_err, "gpu-ref", rel_l2(got, ref32))
+        assert rel_l2(got, f64) <= ref_err + 5e-4
+        assert rel_l2(got, ref32) <= 1.5 * ref_err + 5e-4
 
 
 def test_als_rejects_ccd_calls(gpu, data_factory):
