@@ -1,0 +1,47 @@
+"""GPU (-m gpu): the two executables.
+  * oracle/_ref/cuda_andre_dropin — the reference's UNMODIFIED src/main.cpp + CPU solvers linked against
+    this repo's shim + library: `-CUDA -OMP` runs our GPU path and the reference's CPU path back to back
+    and the reference's own golden_compare (10 % elementwise, src/extras.cpp:218-238) must PASS.
+  * cuda-recommender_b200/host/b200_recommender — this build's CLI over the same boundary."""
+import os
+import re
+import subprocess
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DROPIN = os.path.join(ROOT, "oracle", "_ref", "cuda_andre_dropin")
+CLI = os.path.join(ROOT, "cuda-recommender_b200", "host", "b200_recommender")
+LINE = re.compile(r"\[-INFO-\] iteration num (\d+) .*?RMSE=([\d.]+)")
+
+
+def _run(cmd):
+    return subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600).stdout
+
+
+@pytest.mark.parametrize("als", [False, True])
+def test_reference_main_runs_on_our_gpu_path(gpu, datagen, data_factory, tmp_path, als):
+    if not os.path.exists(DROPIN):
+        pytest.skip("oracle/_ref/cuda_andre_dropin not built (needs /root/reference at build time)")
+    datagen.write_dataset(str(tmp_path), data_factory("ml100k"))
+    out = _run([DROPIN, "-CUDA", "-OMP", "-k", "10", "-l", "0.05", "-t", "3", "-T", "3", "-n", "4"] + (["-ALS"] if als else []) + [str(tmp_path)])
+    assert "FAILED" not in out, out
+    lines = LINE.findall(out)
+    assert len(lines) == 6, out  # 3 from the CUDA path, 3 from the OMP path
+    for (i, a), (j, b) in zip(lines[:3], lines[3:]):
+        assert i == j and abs(float(a) - float(b)) <= 1e-4, out
+    assert out.count("Check... PASS!") == 2, out
+    finals = re.findall(r"Test RMSE = ([\d.]+)", out)
+    assert len(finals) == 2 and abs(float(finals[0]) - float(finals[1])) <= 1e-4
+
+
+def test_own_cli(gpu, datagen, data_factory, tmp_path):
+    assert os.path.exists(CLI), "build the CLI with make -C cuda-recommender_b200"
+    datagen.write_dataset(str(tmp_path), data_factory("small"))
+    out = _run([CLI, "-CUDA", "-k", "6", "-l", "0.05", "-t", "2", "-T", "2", "-save", str(tmp_path)])
+    assert "FAILED" not in out and len(LINE.findall(out)) == 2, out
+    assert re.search(r"Test RMSE = [\d.]+", out)
+    assert os.path.getsize(os.path.join(str(tmp_path), "model")) == 2 * 16 + 4 * 6 * (300 + 500)
+    assert "Usage:" in _run([CLI])
