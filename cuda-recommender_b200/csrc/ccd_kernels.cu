@@ -12,11 +12,14 @@
 //
 // PANEL kernel (layout.cuh): persistent CTAs, one per SM.  A CTA owns an equal-cost contiguous range
 // of work items; for every panel its range touches it stages that panel of the gathered factor
-// vector(s) in shared memory, then its warps pull batches of four items from a shared-memory counter.
-// Four short items (<= 64 entries) are handled at once by the four 8-lane groups of the warp;
-// otherwise the warp walks the items one after another with all 32 lanes, 256 entries per step,
-// two steps in flight.  Ratings are streamed with 16-byte loads (8 x uint16 indices, 2 x float4
-// values) and 16-byte stores; the factor gathers never leave shared memory.
+// vector(s) in shared memory, then its warps pull batches of four items from a shared-memory counter
+// (the next batch's descriptors are fetched one batch ahead).  Four short items (<= 32 entries) are
+// handled at once by the four 8-lane groups of the warp; otherwise the warp walks the items one after
+// another with all 32 lanes in rounds of 256 entries, software-pipelined: the loads of the next round
+// (of the same item or of the next item) are issued before the current round is consumed, so every
+// warp keeps ~1.5 KB of HBM traffic in flight.  A lane owns 4 consecutive entries per 128-entry step,
+// so each warp-wide load covers one contiguous span (8-byte index vectors, 16-byte value vectors);
+// values are written back with 16-byte stores; the factor gathers never leave shared memory.
 #include "ccd_kernels.cuh"
 
 namespace mf {
@@ -24,47 +27,72 @@ namespace {
 
 constexpr unsigned kFull = 0xffffffffu;
 
-struct Elems {
-    uint4 i;        // 8 x uint16 panel-local indices
-    float4 a, b;    // 8 values
+// One lane's share of a 128-entry step: 4 consecutive entries (8 bytes of indices, 16 bytes of values),
+// so that every warp-wide load instruction covers one contiguous 256- or 512-byte span.
+struct Step {
+    uint2 i;   // 4 x uint16 panel-local indices
+    float4 v;  // 4 values
+};
+// A round = two steps, 128 entries apart: the unit of the software pipeline (one round in flight per warp
+// while the previous one is being consumed).
+struct Round {
+    Step s0, s1;
 };
 
-__device__ __forceinline__ Elems load8(const uint16_t* __restrict__ idx16, const float* __restrict__ val, uint32_t pos) {
-    Elems e;
-    e.i = __ldcs(reinterpret_cast<const uint4*>(idx16 + pos));
-    e.a = __ldcs(reinterpret_cast<const float4*>(val + pos));
-    e.b = __ldcs(reinterpret_cast<const float4*>(val + pos + 4));
+__device__ __forceinline__ Step load_step(const uint16_t* __restrict__ idx16, const float* __restrict__ val, uint32_t pos) {
+    Step e;
+    e.i = __ldcs(reinterpret_cast<const uint2*>(idx16 + pos));
+    e.v = __ldcs(reinterpret_cast<const float4*>(val + pos));
     return e;
 }
 
+// entries [off, off+256) of an item of `len` entries starting at `start`; lane l owns off+4l.. and off+128+4l..
+__device__ __forceinline__ Round load_round(const uint16_t* __restrict__ idx16, const float* __restrict__ val, uint32_t start,
+                                            uint32_t len, uint32_t off, int lane) {
+    Round r;
+    r.s0.i = make_uint2(0u, 0u); r.s0.v = make_float4(0.f, 0.f, 0.f, 0.f);
+    r.s1 = r.s0;
+    const uint32_t o0 = off + 4u * (uint32_t)lane;
+    if (o0 < len) r.s0 = load_step(idx16, val, start + o0);
+    if (o0 + 128u < len) r.s1 = load_step(idx16, val, start + o0 + 128u);
+    return r;
+}
+
 template <int MODE>
-__device__ __forceinline__ void calc8(Elems& e, const float* __restrict__ sm_new, const float* __restrict__ sm_add,
+__device__ __forceinline__ void calc4(Step& e, const float* __restrict__ sm_new, const float* __restrict__ sm_add,
                                       const float* __restrict__ sm_old, float s_add, float s_old, float& g, float& h) {
     constexpr bool SUB = MODE & kSub, ADD = MODE & kAdd, SOLVE = MODE & kSolve;
-    float v[8] = {e.a.x, e.a.y, e.a.z, e.a.w, e.b.x, e.b.y, e.b.z, e.b.w};
-    const uint32_t w[4] = {e.i.x, e.i.y, e.i.z, e.i.w};
+    float v[4] = {e.v.x, e.v.y, e.v.z, e.v.w};
+    const uint32_t ix[4] = {e.i.x & 0xffffu, e.i.x >> 16, e.i.y & 0xffffu, e.i.y >> 16};
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const uint32_t i = (j & 1) ? (w[j >> 1] >> 16) : (w[j >> 1] & 0xffffu);
+    for (int j = 0; j < 4; ++j) {
         float x = v[j];
-        if (SUB) x = __fsub_rn(x, __fmul_rn(sm_old[i], s_old));
-        if (ADD) x = __fadd_rn(x, __fmul_rn(sm_add[i], s_add));
+        if (SUB) x = __fsub_rn(x, __fmul_rn(sm_old[ix[j]], s_old));
+        if (ADD) x = __fadd_rn(x, __fmul_rn(sm_add[ix[j]], s_add));
         if (SOLVE) {
-            const float un = sm_new[i];
+            const float un = sm_new[ix[j]];
             g = fmaf(un, x, g);
             h = fmaf(un, un, h);
         }
         v[j] = x;
     }
-    if (SUB || ADD) {
-        e.a = make_float4(v[0], v[1], v[2], v[3]);
-        e.b = make_float4(v[4], v[5], v[6], v[7]);
-    }
+    if (SUB || ADD) e.v = make_float4(v[0], v[1], v[2], v[3]);
 }
 
-__device__ __forceinline__ void store8(float* __restrict__ val, uint32_t pos, const Elems& e) {
-    __stcs(reinterpret_cast<float4*>(val + pos), e.a);
-    __stcs(reinterpret_cast<float4*>(val + pos + 4), e.b);
+template <int MODE>
+__device__ __forceinline__ void consume_round(Round& r, float* __restrict__ val, uint32_t start, uint32_t len, uint32_t off,
+                                              int lane, const float* __restrict__ sm_new, const float* __restrict__ sm_add,
+                                              const float* __restrict__ sm_old, float s_add, float s_old, float& g, float& h) {
+    constexpr bool WRITE = (MODE & kSub) || (MODE & kAdd);
+    const uint32_t o0 = off + 4u * (uint32_t)lane;
+    if (o0 < len) {
+        calc4<MODE>(r.s0, sm_new, sm_add, sm_old, s_add, s_old, g, h);
+        if (WRITE) __stcs(reinterpret_cast<float4*>(val + start + o0), r.s0.v);
+    }
+    if (o0 + 128u < len) {
+        calc4<MODE>(r.s1, sm_new, sm_add, sm_old, s_add, s_old, g, h);
+        if (WRITE) __stcs(reinterpret_cast<float4*>(val + start + o0 + 128u), r.s1.v);
+    }
 }
 
 template <int MODE>
@@ -114,25 +142,31 @@ __global__ void __launch_bounds__(1024, 1) k_panel_sweep(PanelSweepArgs a) {
             if (threadIdx.x == 0) s_ctr = ib;
             __syncthreads();
 
-            for (;;) {
-                uint32_t i0 = 0;
-                if (lane == 0) i0 = atomicAdd(&s_ctr, 4u);
-                i0 = __shfl_sync(kFull, i0, 0);
-                if (i0 >= pe) break;
-                const uint32_t mine = i0 + grp;
-                uint4 d = make_uint4(0u, 0u, 0u, 0u);  // {start, len, seg, slot}; len 0 = no item
-                if (mine < pe) d = __ldg(items + mine);
-                const bool all_short = __all_sync(kFull, d.y <= 64u);
+            // batches of four items; the next batch's descriptors are fetched while this one is processed
+            uint32_t i0 = 0;
+            if (lane == 0) i0 = atomicAdd(&s_ctr, 4u);
+            i0 = __shfl_sync(kFull, i0, 0);
+            uint4 d = make_uint4(0u, 0u, 0u, 0u);  // {start, len, seg, slot}; len 0 = no item
+            if (i0 + grp < pe) d = __ldg(items + i0 + grp);
+            while (i0 < pe) {
+                uint32_t i0n = 0;
+                if (lane == 0) i0n = atomicAdd(&s_ctr, 4u);
+                i0n = __shfl_sync(kFull, i0n, 0);
+                uint4 dn = make_uint4(0u, 0u, 0u, 0u);
+                if (i0n + grp < pe) dn = __ldg(items + i0n + grp);
+
+                const bool all_short = __all_sync(kFull, d.y <= 32u);
                 if (all_short) {
-                    // four items at once, 8 lanes x 8 entries each
-                    float g = 0.0f, h = 0.0f, s_add = 0.0f, s_old = 0.0f;
-                    const uint32_t off = (uint32_t)sl * 8u;
+                    // four short items at once: 8 lanes x 4 entries each, one step
+                    float g = 0.0f, h = 0.0f;
+                    const uint32_t off = 4u * (uint32_t)sl;
                     if (off < d.y) {
+                        float s_add = 0.0f, s_old = 0.0f;
                         if (ADD) s_add = __ldg(a.s_add + a.seg_offset + d.z);
                         if (SUB) s_old = __ldg(a.s_old + a.seg_offset + d.z);
-                        Elems e = load8(a.idx16, a.val, d.x + off);
-                        calc8<MODE>(e, sm_new, sm_add, sm_old, s_add, s_old, g, h);
-                        if (WRITE) store8(a.val, d.x + off, e);
+                        Step e = load_step(a.idx16, a.val, d.x + off);
+                        calc4<MODE>(e, sm_new, sm_add, sm_old, s_add, s_old, g, h);
+                        if (WRITE) __stcs(reinterpret_cast<float4*>(a.val + d.x + off), e.v);
                     }
                     if (SOLVE) {
 #pragma unroll
@@ -143,40 +177,63 @@ __global__ void __launch_bounds__(1024, 1) k_panel_sweep(PanelSweepArgs a) {
                         if (sl == 0 && d.y != 0u) a.partials[d.w] = make_float2(g, h);
                     }
                 } else {
-                    // one item at a time with the whole warp
-#pragma unroll 1
-                    for (int gi = 0; gi < 4; ++gi) {
-                        const uint32_t start = __shfl_sync(kFull, d.x, gi * 8);
-                        const uint32_t len = __shfl_sync(kFull, d.y, gi * 8);
-                        const uint32_t seg = __shfl_sync(kFull, d.z, gi * 8);
-                        const uint32_t slot = __shfl_sync(kFull, d.w, gi * 8);
-                        if (len == 0u) continue;
-                        float g = 0.0f, h = 0.0f, s_add = 0.0f, s_old = 0.0f;
-                        if (ADD) s_add = __ldg(a.s_add + a.seg_offset + seg);
-                        if (SUB) s_old = __ldg(a.s_old + a.seg_offset + seg);
-#pragma unroll 1
-                        for (uint32_t off = (uint32_t)lane * 8u; off < len; off += 512u) {
-                            const bool two = off + 256u < len;
-                            Elems e0 = load8(a.idx16, a.val, start + off);
-                            Elems e1;
-                            if (two) e1 = load8(a.idx16, a.val, start + off + 256u);
-                            calc8<MODE>(e0, sm_new, sm_add, sm_old, s_add, s_old, g, h);
-                            if (WRITE) store8(a.val, start + off, e0);
-                            if (two) {
-                                calc8<MODE>(e1, sm_new, sm_add, sm_old, s_add, s_old, g, h);
-                                if (WRITE) store8(a.val, start + off + 256u, e1);
+                    // one item after the other with the whole warp, 256 entries per round, the next round
+                    // (of this item or of the next one) already in flight
+                    int j = 0;
+                    uint32_t start = __shfl_sync(kFull, d.x, 0), len = __shfl_sync(kFull, d.y, 0);
+                    uint32_t seg = __shfl_sync(kFull, d.z, 0), slot = __shfl_sync(kFull, d.w, 0);
+                    float s_add = 0.0f, s_old = 0.0f;
+                    if (ADD) s_add = __ldg(a.s_add + a.seg_offset + seg);
+                    if (SUB) s_old = __ldg(a.s_old + a.seg_offset + seg);
+                    uint32_t off = 0;
+                    Round cur = load_round(a.idx16, a.val, start, len, off, lane);
+                    float g = 0.0f, h = 0.0f;
+                    for (;;) {
+                        int nj = j;
+                        uint32_t noff = off + 256u, nstart = start, nlen = len, nseg = seg, nslot = slot;
+                        float ns_add = s_add, ns_old = s_old;
+                        const bool item_done = noff >= len;
+                        if (item_done) {
+                            nj = j + 1;
+                            noff = 0u;
+                            nlen = 0u;
+                            if (nj < 4) {
+                                nstart = __shfl_sync(kFull, d.x, nj * 8);
+                                nlen = __shfl_sync(kFull, d.y, nj * 8);
+                                nseg = __shfl_sync(kFull, d.z, nj * 8);
+                                nslot = __shfl_sync(kFull, d.w, nj * 8);
                             }
                         }
-                        if (SOLVE) {
+                        const bool has_next = nlen != 0u;
+                        Round nxt;
+                        if (has_next) {
+                            if (item_done) {
+                                if (ADD) ns_add = __ldg(a.s_add + a.seg_offset + nseg);
+                                if (SUB) ns_old = __ldg(a.s_old + a.seg_offset + nseg);
+                            }
+                            nxt = load_round(a.idx16, a.val, nstart, nlen, noff, lane);
+                        }
+                        consume_round<MODE>(cur, a.val, start, len, off, lane, sm_new, sm_add, sm_old, s_add, s_old, g, h);
+                        if (item_done) {
+                            if (SOLVE) {
 #pragma unroll
-                            for (int o = 1; o < 32; o <<= 1) {
-                                g += __shfl_xor_sync(kFull, g, o);
-                                h += __shfl_xor_sync(kFull, h, o);
+                                for (int o = 1; o < 32; o <<= 1) {
+                                    g += __shfl_xor_sync(kFull, g, o);
+                                    h += __shfl_xor_sync(kFull, h, o);
+                                }
+                                if (lane == 0) a.partials[slot] = make_float2(g, h);
                             }
-                            if (lane == 0) a.partials[slot] = make_float2(g, h);
+                            g = 0.0f;
+                            h = 0.0f;
                         }
+                        if (!has_next) break;
+                        cur = nxt;
+                        j = nj; off = noff; start = nstart; len = nlen; seg = nseg; slot = nslot;
+                        s_add = ns_add; s_old = ns_old;
                     }
                 }
+                i0 = i0n;
+                d = dn;
             }
         }
         ib = pe;
@@ -184,26 +241,43 @@ __global__ void __launch_bounds__(1024, 1) k_panel_sweep(PanelSweepArgs a) {
     }
 }
 
-// one thread per segment: add the segment's slots in order, apply the regulariser, divide.
-// h = lambda*deg + sum u^2 with lambda*deg a float*unsigned product as at src/CCD.cpp:112,120;
-// empty segment -> 0 (src/CCD.cpp:8).
-__global__ void k_finalize(int64_t nseg, const uint32_t* __restrict__ slot_ptr, const float2* __restrict__ partials,
-                           const uint32_t* __restrict__ seg_ptr, float lambda, int nmf, float* __restrict__ out) {
-    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+// Adds a segment's slots, applies the regulariser, divides: out = g / (lambda*deg + h), with lambda*deg a
+// float*unsigned product as at src/CCD.cpp:112,120; empty segment -> 0 (src/CCD.cpp:8).
+// LANES = 1: one thread per segment (slots added in order); LANES = 32: one warp per segment, lane l adds
+// slots l, l+32, ... in order and the lanes are combined by an xor-butterfly — both are fixed trees.
+template <int LANES>
+__global__ void __launch_bounds__(256) k_finalize(int64_t nseg, const uint32_t* __restrict__ slot_ptr,
+                                                  const float2* __restrict__ partials, const uint32_t* __restrict__ seg_ptr,
+                                                  float lambda, int nmf, float* __restrict__ out) {
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t s = tid / LANES;
+    const int l = (int)(tid % LANES);
     if (s >= nseg) return;
     const uint32_t deg = seg_ptr[s + 1] - seg_ptr[s];
-    float r = 0.0f;
+    float g = 0.0f, h = 0.0f;
     if (deg != 0u) {
-        float g = 0.0f, h = 0.0f;
-        for (uint32_t q = slot_ptr[s]; q < slot_ptr[s + 1]; ++q) {
+        const uint32_t hi = slot_ptr[s + 1];
+        for (uint32_t q = slot_ptr[s] + l; q < hi; q += LANES) {
             const float2 pr = partials[q];
             g += pr.x;
             h += pr.y;
         }
-        r = g / (lambda * deg + h);
-        if (nmf) r = fmaxf(r, 0.0f);
     }
-    out[s] = r;
+    if (LANES > 1) {
+#pragma unroll
+        for (int o = 1; o < LANES; o <<= 1) {
+            g += __shfl_xor_sync(0xffffffffu, g, o);
+            h += __shfl_xor_sync(0xffffffffu, h, o);
+        }
+    }
+    if (l == 0) {
+        float r = 0.0f;
+        if (deg != 0u) {
+            r = g / (lambda * deg + h);
+            if (nmf) r = fmaxf(r, 0.0f);
+        }
+        out[s] = r;
+    }
 }
 
 // DIRECT layout: one warp per segment on the caller's arrays (uint32 indices, gathers through L1/L2).
@@ -302,10 +376,13 @@ int panel_sweep(int mode, const PanelSweepArgs& a, int ncta, int threads, cudaSt
     }
 }
 
-int panel_finalize(int64_t nseg, const uint32_t* slot_ptr, const float2* partials, const uint32_t* seg_ptr, float lambda,
-                   int nmf, float* out, cudaStream_t st) {
+int panel_finalize(int64_t nseg, int64_t nslots, const uint32_t* slot_ptr, const float2* partials, const uint32_t* seg_ptr,
+                   float lambda, int nmf, float* out, cudaStream_t st) {
     if (nseg <= 0) return MF_OK;
-    k_finalize<<<(unsigned)((nseg + 255) / 256), 256, 0, st>>>(nseg, slot_ptr, partials, seg_ptr, lambda, nmf, out);
+    if (nslots > 4 * nseg)  // many slots per segment (long columns cut by panels and chunks): a warp per segment
+        k_finalize<32><<<(unsigned)((nseg * 32 + 255) / 256), 256, 0, st>>>(nseg, slot_ptr, partials, seg_ptr, lambda, nmf, out);
+    else
+        k_finalize<1><<<(unsigned)((nseg + 255) / 256), 256, 0, st>>>(nseg, slot_ptr, partials, seg_ptr, lambda, nmf, out);
     MF_CUDA(cudaGetLastError());
     return MF_OK;
 }

@@ -155,7 +155,7 @@ int run_sweep(mf_session* s, Side& sd, int mode, const SweepVectors& v, float* o
         }
         if (mode & kSolve) {
             s->timer.start(F_FINALIZE);
-            MF_TRY(panel_finalize(sd.nseg, sd.slot_ptr, sd.partials, sd.ptr, s->prm.lambda, nmf, out + sd.seg_offset, s->st));
+            MF_TRY(panel_finalize(sd.nseg, sd.nslots, sd.slot_ptr, sd.partials, sd.ptr, s->prm.lambda, nmf, out + sd.seg_offset, s->st));
             s->timer.stop();
         }
     } else {
@@ -349,7 +349,7 @@ int create_impl(const mf_ratings* R, const mf_testset* T, const mf_params* param
             int cap_c = panel_cap(2), cap_r = panel_cap(3);
             if (params->panel_rows > 0) { cap_c = std::min(cap_c, params->panel_rows / 8 * 8); cap_r = std::min(cap_r, params->panel_rows / 8 * 8); }
             else cap_c = std::min(cap_c, 24576);
-            const int chunk = params->chunk > 0 ? std::max(8, params->chunk / 8 * 8) : 1024;
+            const int chunk = params->chunk > 0 ? std::max(8, params->chunk / 8 * 8) : 2048;
             if ((rc = side_build_panels(s->csc, choose_panel_rows(s->csc.gdim, std::max(cap_c, 8)), chunk, s->sm_count, s->st)) != MF_OK) return fail(rc);
             if ((rc = side_build_panels(s->csr, choose_panel_rows(s->csr.gdim, std::max(cap_r, 8)), chunk, s->sm_count, s->st)) != MF_OK) return fail(rc);
             // the caller-order index/value arrays are no longer needed: the residual lives in the panel arrays
