@@ -13,13 +13,13 @@
 // PANEL kernel (layout.cuh): persistent CTAs, one per SM.  A CTA owns an equal-cost contiguous range
 // of work items; for every panel its range touches it stages that panel of the gathered factor
 // vector(s) in shared memory, then its warps pull batches of four items from a shared-memory counter
-// (the next batch's descriptors are fetched one batch ahead).  Four short items (<= 32 entries) are
-// handled at once by the four 8-lane groups of the warp; otherwise the warp walks the items one after
-// another with all 32 lanes in rounds of 256 entries, software-pipelined: the loads of the next round
-// (of the same item or of the next item) are issued before the current round is consumed, so every
-// warp keeps ~1.5 KB of HBM traffic in flight.  A lane owns 4 consecutive entries per 128-entry step,
-// so each warp-wide load covers one contiguous span (8-byte index vectors, 16-byte value vectors);
-// values are written back with 16-byte stores; the factor gathers never leave shared memory.
+// (the next batch's descriptors are fetched one batch ahead).  Each 8-lane group of the warp streams
+// one item in steps of 32 entries — a lane owns 4 consecutive entries of a step (8-byte index vector,
+// 16-byte value vector), a group's load covers one contiguous 64/128-byte span — with four steps in
+// flight per group (register ring).  Items are stored longest-first inside a panel (degree-binned
+// order, prep.cu), so the four items of a batch have nearly equal length and the groups stay in step.
+// Values are written back with 16-byte stores; the factor gathers never leave shared memory.
+// Reduction tree of an item: lane-serial over its steps, xor-butterfly over the 8 lanes.
 #include "ccd_kernels.cuh"
 
 namespace mf {
@@ -27,35 +27,17 @@ namespace {
 
 constexpr unsigned kFull = 0xffffffffu;
 
-// One lane's share of a 128-entry step: 4 consecutive entries (8 bytes of indices, 16 bytes of values),
-// so that every warp-wide load instruction covers one contiguous 256- or 512-byte span.
+// One lane's share of a 32-entry step of its 8-lane group: 4 consecutive entries (8 bytes of indices,
+// 16 bytes of values), so that a group's load covers one contiguous 64- or 128-byte span.
 struct Step {
     uint2 i;   // 4 x uint16 panel-local indices
     float4 v;  // 4 values
 };
-// A round = two steps, 128 entries apart: the unit of the software pipeline (one round in flight per warp
-// while the previous one is being consumed).
-struct Round {
-    Step s0, s1;
-};
-
 __device__ __forceinline__ Step load_step(const uint16_t* __restrict__ idx16, const float* __restrict__ val, uint32_t pos) {
     Step e;
     e.i = __ldcs(reinterpret_cast<const uint2*>(idx16 + pos));
     e.v = __ldcs(reinterpret_cast<const float4*>(val + pos));
     return e;
-}
-
-// entries [off, off+256) of an item of `len` entries starting at `start`; lane l owns off+4l.. and off+128+4l..
-__device__ __forceinline__ Round load_round(const uint16_t* __restrict__ idx16, const float* __restrict__ val, uint32_t start,
-                                            uint32_t len, uint32_t off, int lane) {
-    Round r;
-    r.s0.i = make_uint2(0u, 0u); r.s0.v = make_float4(0.f, 0.f, 0.f, 0.f);
-    r.s1 = r.s0;
-    const uint32_t o0 = off + 4u * (uint32_t)lane;
-    if (o0 < len) r.s0 = load_step(idx16, val, start + o0);
-    if (o0 + 128u < len) r.s1 = load_step(idx16, val, start + o0 + 128u);
-    return r;
 }
 
 template <int MODE>
@@ -77,22 +59,6 @@ __device__ __forceinline__ void calc4(Step& e, const float* __restrict__ sm_new,
         v[j] = x;
     }
     if (SUB || ADD) e.v = make_float4(v[0], v[1], v[2], v[3]);
-}
-
-template <int MODE>
-__device__ __forceinline__ void consume_round(Round& r, float* __restrict__ val, uint32_t start, uint32_t len, uint32_t off,
-                                              int lane, const float* __restrict__ sm_new, const float* __restrict__ sm_add,
-                                              const float* __restrict__ sm_old, float s_add, float s_old, float& g, float& h) {
-    constexpr bool WRITE = (MODE & kSub) || (MODE & kAdd);
-    const uint32_t o0 = off + 4u * (uint32_t)lane;
-    if (o0 < len) {
-        calc4<MODE>(r.s0, sm_new, sm_add, sm_old, s_add, s_old, g, h);
-        if (WRITE) __stcs(reinterpret_cast<float4*>(val + start + o0), r.s0.v);
-    }
-    if (o0 + 128u < len) {
-        calc4<MODE>(r.s1, sm_new, sm_add, sm_old, s_add, s_old, g, h);
-        if (WRITE) __stcs(reinterpret_cast<float4*>(val + start + o0 + 128u), r.s1.v);
-    }
 }
 
 template <int MODE>
@@ -142,7 +108,9 @@ __global__ void __launch_bounds__(1024, 1) k_panel_sweep(PanelSweepArgs a) {
             if (threadIdx.x == 0) s_ctr = ib;
             __syncthreads();
 
-            // batches of four items; the next batch's descriptors are fetched while this one is processed
+            // Batches of four items (one per 8-lane group); items are stored longest-first inside a panel, so
+            // the four items of a batch have (nearly) the same length.  The next batch's descriptors are
+            // fetched while this batch is processed.
             uint32_t i0 = 0;
             if (lane == 0) i0 = atomicAdd(&s_ctr, 4u);
             i0 = __shfl_sync(kFull, i0, 0);
@@ -155,82 +123,48 @@ __global__ void __launch_bounds__(1024, 1) k_panel_sweep(PanelSweepArgs a) {
                 uint4 dn = make_uint4(0u, 0u, 0u, 0u);
                 if (i0n + grp < pe) dn = __ldg(items + i0n + grp);
 
-                const bool all_short = __all_sync(kFull, d.y <= 32u);
-                if (all_short) {
-                    // four short items at once: 8 lanes x 4 entries each, one step
-                    float g = 0.0f, h = 0.0f;
-                    const uint32_t off = 4u * (uint32_t)sl;
-                    if (off < d.y) {
-                        float s_add = 0.0f, s_old = 0.0f;
-                        if (ADD) s_add = __ldg(a.s_add + a.seg_offset + d.z);
-                        if (SUB) s_old = __ldg(a.s_old + a.seg_offset + d.z);
-                        Step e = load_step(a.idx16, a.val, d.x + off);
-                        calc4<MODE>(e, sm_new, sm_add, sm_old, s_add, s_old, g, h);
-                        if (WRITE) __stcs(reinterpret_cast<float4*>(a.val + d.x + off), e.v);
-                    }
-                    if (SOLVE) {
+                const uint32_t len = d.y;
+                const uint32_t lane_off = 4u * (uint32_t)sl;     // this lane's 4 entries inside a 32-entry step
+                const uint32_t pos = d.x + lane_off;
+                float s_add = 0.0f, s_old = 0.0f;
+                if (len != 0u) {
+                    if (ADD) s_add = __ldg(a.s_add + a.seg_offset + d.z);
+                    if (SUB) s_old = __ldg(a.s_old + a.seg_offset + d.z);
+                }
+                const uint32_t maxlen = __reduce_max_sync(kFull, len);
+                float g = 0.0f, h = 0.0f;
+                // four 32-entry steps in flight per group (register ring e0..e3)
+                Step e0, e1, e2, e3;
+#define MF_LOAD(e, o) if ((o) + lane_off < len) e = load_step(a.idx16, a.val, pos + (o))
+#define MF_USE(e, o)                                                                        \
+    if ((o) + lane_off < len) {                                                             \
+        calc4<MODE>(e, sm_new, sm_add, sm_old, s_add, s_old, g, h);                         \
+        if (WRITE) __stcs(reinterpret_cast<float4*>(a.val + pos + (o)), e.v);               \
+    }
+                MF_LOAD(e0, 0u);
+                MF_LOAD(e1, 32u);
+                MF_LOAD(e2, 64u);
+                MF_LOAD(e3, 96u);
+#pragma unroll 1
+                for (uint32_t o = 0; o < maxlen; o += 128u) {
+                    MF_USE(e0, o);
+                    MF_LOAD(e0, o + 128u);
+                    MF_USE(e1, o + 32u);
+                    MF_LOAD(e1, o + 160u);
+                    MF_USE(e2, o + 64u);
+                    MF_LOAD(e2, o + 192u);
+                    MF_USE(e3, o + 96u);
+                    MF_LOAD(e3, o + 224u);
+                }
+#undef MF_LOAD
+#undef MF_USE
+                if (SOLVE) {
 #pragma unroll
-                        for (int o = 1; o < 8; o <<= 1) {
-                            g += __shfl_xor_sync(kFull, g, o);
-                            h += __shfl_xor_sync(kFull, h, o);
-                        }
-                        if (sl == 0 && d.y != 0u) a.partials[d.w] = make_float2(g, h);
+                    for (int o = 1; o < 8; o <<= 1) {
+                        g += __shfl_xor_sync(kFull, g, o);
+                        h += __shfl_xor_sync(kFull, h, o);
                     }
-                } else {
-                    // one item after the other with the whole warp, 256 entries per round, the next round
-                    // (of this item or of the next one) already in flight
-                    int j = 0;
-                    uint32_t start = __shfl_sync(kFull, d.x, 0), len = __shfl_sync(kFull, d.y, 0);
-                    uint32_t seg = __shfl_sync(kFull, d.z, 0), slot = __shfl_sync(kFull, d.w, 0);
-                    float s_add = 0.0f, s_old = 0.0f;
-                    if (ADD) s_add = __ldg(a.s_add + a.seg_offset + seg);
-                    if (SUB) s_old = __ldg(a.s_old + a.seg_offset + seg);
-                    uint32_t off = 0;
-                    Round cur = load_round(a.idx16, a.val, start, len, off, lane);
-                    float g = 0.0f, h = 0.0f;
-                    for (;;) {
-                        int nj = j;
-                        uint32_t noff = off + 256u, nstart = start, nlen = len, nseg = seg, nslot = slot;
-                        float ns_add = s_add, ns_old = s_old;
-                        const bool item_done = noff >= len;
-                        if (item_done) {
-                            nj = j + 1;
-                            noff = 0u;
-                            nlen = 0u;
-                            if (nj < 4) {
-                                nstart = __shfl_sync(kFull, d.x, nj * 8);
-                                nlen = __shfl_sync(kFull, d.y, nj * 8);
-                                nseg = __shfl_sync(kFull, d.z, nj * 8);
-                                nslot = __shfl_sync(kFull, d.w, nj * 8);
-                            }
-                        }
-                        const bool has_next = nlen != 0u;
-                        Round nxt;
-                        if (has_next) {
-                            if (item_done) {
-                                if (ADD) ns_add = __ldg(a.s_add + a.seg_offset + nseg);
-                                if (SUB) ns_old = __ldg(a.s_old + a.seg_offset + nseg);
-                            }
-                            nxt = load_round(a.idx16, a.val, nstart, nlen, noff, lane);
-                        }
-                        consume_round<MODE>(cur, a.val, start, len, off, lane, sm_new, sm_add, sm_old, s_add, s_old, g, h);
-                        if (item_done) {
-                            if (SOLVE) {
-#pragma unroll
-                                for (int o = 1; o < 32; o <<= 1) {
-                                    g += __shfl_xor_sync(kFull, g, o);
-                                    h += __shfl_xor_sync(kFull, h, o);
-                                }
-                                if (lane == 0) a.partials[slot] = make_float2(g, h);
-                            }
-                            g = 0.0f;
-                            h = 0.0f;
-                        }
-                        if (!has_next) break;
-                        cur = nxt;
-                        j = nj; off = noff; start = nstart; len = nlen; seg = nseg; slot = nslot;
-                        s_add = ns_add; s_old = ns_old;
-                    }
+                    if (sl == 0 && len != 0u) a.partials[d.w] = make_float2(g, h);
                 }
                 i0 = i0n;
                 d = dn;

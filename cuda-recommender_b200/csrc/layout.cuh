@@ -19,6 +19,8 @@
 // (g, h) to a fixed slot, slots of one segment are contiguous and ordered (panel, chunk), and a
 // finalize pass adds them in that order — the reduction tree of a segment depends only on its own
 // entries and the global panel grid, never on scheduling or on the multi-GPU shard it sits in.
+// Inside a panel the work items are listed longest-first (degree-binned order), so that a batch of
+// consecutive items has nearly uniform length.
 #pragma once
 #include "common.cuh"
 

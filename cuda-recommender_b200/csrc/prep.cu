@@ -103,6 +103,37 @@ __global__ void k_fill(int64_t nseg, int npanels, uint32_t panel_rows, uint32_t 
     }
 }
 
+// Degree-binned order: inside every panel the work items are re-ordered longest-first (bin = len/8,
+// counting sort with per-bin cursors).  The order inside one bin is arbitrary — it only affects which
+// warp picks an item up, never a result (every item writes its own slot).
+__device__ __forceinline__ int panel_of_item(const uint32_t* __restrict__ panel_item_ptr, int npanels, uint32_t i) {
+    int lo = 0, hi = npanels;  // last p with panel_item_ptr[p] <= i
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (panel_item_ptr[mid] <= i) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+__global__ void k_item_bin_count(int64_t nitems, int npanels, uint32_t nbins, const uint32_t* __restrict__ panel_item_ptr,
+                                 const WorkItem* __restrict__ items, uint32_t* __restrict__ bin_count) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nitems) return;
+    const int p = panel_of_item(panel_item_ptr, npanels, (uint32_t)i);
+    atomicAdd(&bin_count[(uint32_t)p * nbins + (nbins - 1u - items[i].len / kPad)], 1u);
+}
+__global__ void k_item_bin_scatter(int64_t nitems, int npanels, uint32_t nbins, const uint32_t* __restrict__ panel_item_ptr,
+                                   const WorkItem* __restrict__ items, const uint32_t* __restrict__ bin_ptr,
+                                   uint32_t* __restrict__ bin_cursor, WorkItem* __restrict__ sorted, uint32_t* __restrict__ cost) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nitems) return;
+    const WorkItem w = items[i];
+    const int p = panel_of_item(panel_item_ptr, npanels, (uint32_t)i);
+    const uint32_t b = (uint32_t)p * nbins + (nbins - 1u - w.len / kPad);
+    const uint32_t dst = bin_ptr[b] + atomicAdd(&bin_cursor[b], 1u);
+    sorted[dst] = w;
+    cost[dst] = w.len / kPad + kCost0;
+}
+
 __global__ void k_panel_item_ptr(int64_t nseg, int npanels, const uint32_t* __restrict__ item_ptr,
                                  uint32_t* __restrict__ panel_item_ptr) {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -282,9 +313,33 @@ int side_build_panels(Side& s, int panel_rows, int chunk, int ncta, cudaStream_t
                                                          s.idx16, s.pval, s.items, cost);
     }
     MF_CUDA(cudaGetLastError());
+    k_panel_item_ptr<<<grid_for(s.npanels + 1, 128), 128, 0, st>>>(s.nseg, s.npanels, s.item_ptr, s.panel_item_ptr);
+    MF_CUDA(cudaGetLastError());
+    // longest-first inside each panel
+    if (s.nitems > 0) {
+        const uint32_t nbins = (uint32_t)chunk / kPad + 1u;
+        const size_t nb = (size_t)s.npanels * nbins;
+        uint32_t *bin_count = nullptr, *bin_ptr = nullptr, *tmp2 = nullptr;
+        WorkItem* sorted = nullptr;
+        MF_TRY(dev_alloc(&bin_count, nb));
+        MF_TRY(dev_alloc(&bin_ptr, nb + 1));
+        MF_TRY(dev_alloc(&tmp2, scan_tmp_elems(nb)));
+        MF_TRY(dev_alloc(&sorted, (size_t)s.nitems));
+        MF_CUDA(cudaMemsetAsync(bin_count, 0, sizeof(uint32_t) * nb, st));
+        k_item_bin_count<<<grid_for(s.nitems, 256), 256, 0, st>>>(s.nitems, s.npanels, nbins, s.panel_item_ptr, s.items, bin_count);
+        MF_CUDA(cudaGetLastError());
+        MF_TRY(exclusive_scan_u32(bin_count, bin_ptr, nb, tmp2, st));
+        MF_CUDA(cudaMemsetAsync(bin_count, 0, sizeof(uint32_t) * nb, st));
+        k_item_bin_scatter<<<grid_for(s.nitems, 256), 256, 0, st>>>(s.nitems, s.npanels, nbins, s.panel_item_ptr, s.items, bin_ptr,
+                                                                   bin_count, sorted, cost);
+        MF_CUDA(cudaGetLastError());
+        MF_CUDA(cudaStreamSynchronize(st));
+        cudaFree(s.items);
+        s.items = sorted;
+        cudaFree(bin_count); cudaFree(bin_ptr); cudaFree(tmp2);
+    }
     MF_TRY(exclusive_scan_u32(cost, cost_prefix, (size_t)s.nitems, tmp, st));
     k_cta_ranges<<<grid_for(ncta + 1, 128), 128, 0, st>>>(ncta, s.nitems, cost_prefix, s.cta_item_ptr);
-    k_panel_item_ptr<<<grid_for(s.npanels + 1, 128), 128, 0, st>>>(s.nseg, s.npanels, s.item_ptr, s.panel_item_ptr);
     MF_CUDA(cudaGetLastError());
     MF_CUDA(cudaStreamSynchronize(st));
     cudaFree(padded); cudaFree(nitem); cudaFree(seg_items); cudaFree(tmp); cudaFree(cost); cudaFree(cost_prefix);

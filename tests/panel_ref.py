@@ -31,7 +31,7 @@ def panel_layout(ptr, idx, val, gdim, panel_rows, chunk):
     ptr = ptr.astype(np.int64)
     nseg = len(ptr) - 1
     P = max(1, -(-gdim // panel_rows))
-    idx16, pval, items = [], [], []
+    idx16, pval, items, item_panel = [], [], [], []
     seg_items = np.zeros(nseg, np.int64)
     pieces = []
     for p in range(P):
@@ -56,9 +56,26 @@ def panel_layout(ptr, idx, val, gdim, panel_rows, chunk):
         pval.append(np.concatenate([val[a:a + cnt], np.zeros(pd - cnt, np.float32)]).astype(np.float32))
         for j in range(nit):
             items.append((pos + j * chunk, min(chunk, pd - j * chunk), s, slot_ptr[s] + before[s] + j))
+            item_panel.append(p)
         before[s] += nit
         pos += pd
     return dict(n_panels=P, n_padded=pos, n_items=len(items),
                 idx16=np.concatenate(idx16) if idx16 else np.zeros(0, np.uint16),
                 val=np.concatenate(pval) if pval else np.zeros(0, np.float32),
-                items=np.array(items, np.uint32).reshape(-1, 4))
+                items=np.array(items, np.uint32).reshape(-1, 4), item_panel=np.array(item_panel, np.int64))
+
+
+def check_items(got_items, want):
+    """The GPU lists the same work items, re-ordered longest-first inside every panel (ties in any order)."""
+    w = want["items"]
+    assert got_items.shape == w.shape
+    if len(w) == 0:
+        return
+    assert np.array_equal(got_items[np.argsort(got_items[:, 0])], w[np.argsort(w[:, 0])])
+    counts = np.bincount(want["item_panel"], minlength=want["n_panels"])
+    lo = 0
+    for c in counts:
+        seg_got, seg_want = got_items[lo:lo + c], w[lo:lo + c]
+        assert np.all(np.diff(seg_got[:, 1].astype(np.int64)) <= 0)          # longest first
+        assert set(seg_got[:, 0].tolist()) == set(seg_want[:, 0].tolist())  # same panel membership
+        lo += c
