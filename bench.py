@@ -39,6 +39,12 @@ WORKLOADS = {
     "ml20m_k10": ("ml20m", 10, 0.05, 3),
     "ml100k_k10": ("ml100k", 10, 0.05, 3),
     "yahoo_k100": ("yahoo", 100, 0.05, 3),
+    # ALS workloads (BASELINE.json configs[1] and configs[3]); T is unused.  Not the headline metric: run with
+    # --workload to get seconds per ALS iteration in the same JSON shape (metric name changes accordingly).
+    "als_ml100k_k10": ("ml100k", 10, 0.05, 0),
+    "als_ml20m_k10": ("ml20m", 10, 0.05, 0),
+    "als_netflix_k100": ("netflix", 100, 0.05, 0),
+    "als_netflix_k40": ("netflix", 40, 0.05, 0),
 }
 
 
@@ -67,8 +73,10 @@ def config_dict(args, extra=None):
     load_package()
     import cuda_recommender_b200.datagen as dg
     rows, cols, nnz, nt = dg.SHAPES[shape]
-    cfg = {"workload": f"CCD++ k={k} lambda={lam} T={T} on synthetic {shape}-shape ratings ({rows}x{cols}, {nnz} nnz)",
-           "solver": "ccd++", "k": k, "lambda": lam, "inner_iters": T, "rows": rows, "cols": cols, "nnz": nnz,
+    als = args.workload.startswith("als_")
+    cfg = {"workload": (f"ALS k={k} lambda={lam}" if als else f"CCD++ k={k} lambda={lam} T={T}") +
+                       f" on synthetic {shape}-shape ratings ({rows}x{cols}, {nnz} nnz)",
+           "solver": "als" if als else "ccd++", "k": k, "lambda": lam, "inner_iters": T, "rows": rows, "cols": cols, "nnz": nnz,
            "nnz_test": nt, "step": "one steady-state outer iteration over all ratings",
            "l2_policy": "inputs larger than L2 (every sweep streams >= 0.6 GB; L2 is 126 MB)",
            "parallelism": f"rowblock-csr x colblock-csc over {args.gpus} gpu(s)"}
@@ -236,7 +244,8 @@ def run_b200_arm(args):
     gen_s = time.time() - t0
     rows, cols, nnz = data["rows"], data["cols"], data["nnz"]
 
-    params = pkg.make_params(pkg.SOLVER_CCD, k=k, lam=lam, maxiter=args.steps, maxinner=T, device=local_rank,
+    als = args.workload.startswith("als_")
+    params = pkg.make_params(pkg.SOLVER_ALS if als else pkg.SOLVER_CCD, k=k, lam=lam, maxiter=args.steps, maxinner=max(T, 1), device=local_rank,
                              schedule=pkg.SCHEDULE_REFERENCE if args.schedule == "reference" else pkg.SCHEDULE_FUSED,
                              layout=pkg.LAYOUT_DIRECT if args.layout == "direct" else pkg.LAYOUT_PANEL,
                              panel_rows=args.panel_rows, chunk=args.chunk, no_launch_timing=int(args.no_launch_timing))
@@ -249,11 +258,15 @@ def run_b200_arm(args):
         nccl_id = bytes(idt.cpu().tolist())
 
     # factors exactly as the reference seeds them (tools.cpp:165-173): libc srand(0)/rand()
-    W0 = pkg.initial_col(k, rows)
+    W0 = pkg.initial_col(rows, k) if als else pkg.initial_col(k, rows)
+    H0 = pkg.initial_col(cols, k) if als else None
 
     sess = pkg.Session(data, params, rank=rank, nranks=world, nccl_id=nccl_id)
-    sess.set_factors(W0)
+    sess.set_factors(W0, H0)
     # host copies for the end-to-end leg / CPU baseline before the device copies go away
+    if als:
+        args.no_e2e = True          # the ALS workloads report the device-resident number only
+        args.no_cpu_baseline = True
     need_host = (not args.no_e2e) or (rank == 0 and world == 1 and not args.no_cpu_baseline)
     for key in ("coo_row", "coo_col", "coo_val"):
         data.pop(key, None)
@@ -281,6 +294,12 @@ def run_b200_arm(args):
 
     launches = int(sum(kt[n] for n in kt if n.endswith("_launches") and not n.startswith("collective")))
     fam = {}
+    if als and kt["als_launches"]:
+        # Gram + RHS flops of one iteration (symmetric count): 2*nnz*k*(k+1) + 4*nnz*k, both half-steps
+        flops = 2.0 * (2.0 * nnz * k * (k + 1) / 2 + 2.0 * nnz * k)
+        als_info = {"als_ms_per_iteration": kt["als_s"] / args.steps * 1e3, "gram_rhs_tflops": flops / (kt["als_s"] / args.steps) / 1e12}
+    else:
+        als_info = None
     for name in ("solve", "fused", "update"):
         if kt[name + "_launches"]:
             fam[name] = (kt[name + "_s"], kt[name + "_launches"], kt[name + "_bytes"])
@@ -366,12 +385,12 @@ def run_b200_arm(args):
                              f"steady-state iteration scaled x{k / args.cpu_sample_ranks:g}"}
 
     if rank == 0:
-        line = {"metric": METRIC, "value": sec_per_iter, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        line = {"metric": "als_seconds_per_iteration" if als else METRIC, "value": sec_per_iter, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": sec_per_iter * 1e3, "higher_is_better": False, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": config_dict(args, {"schedule": args.schedule, "layout": args.layout, "datagen_s": round(gen_s, 2)}),
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
-                "wall_ms_per_step": wall / args.steps * 1e3, "rmse_after_run": rmse,
+                "wall_ms_per_step": wall / args.steps * 1e3, "rmse_after_run": rmse, "als": als_info,
                 "outer_iterations_done": args.warmup + args.steps}
         print(json.dumps(line))
     if dist is not None:

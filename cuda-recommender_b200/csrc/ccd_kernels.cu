@@ -10,22 +10,25 @@
 // path, so both copies stay bit-identical to the oracle's residual; g and h use FMA and a fixed
 // reduction tree (lane-serial over 8 entries, xor-butterfly over lanes, slots in order).
 //
-// PANEL kernel (layout.cuh): persistent CTAs, one per SM.  A CTA owns an equal-cost contiguous range
-// of work items; for every panel its range touches it stages that panel of the gathered factor
-// vector(s) in shared memory, then its warps pull batches of four items from a shared-memory counter
-// (the next batch's descriptors are fetched one batch ahead).  Each 8-lane group of the warp streams
-// one item in steps of 32 entries — a lane owns 4 consecutive entries of a step (8-byte index vector,
-// 16-byte value vector), a group's load covers one contiguous 64/128-byte span — with four steps in
-// flight per group (register ring).  Items are stored longest-first inside a panel (degree-binned
-// order, prep.cu), so the four items of a batch have nearly equal length and the groups stay in step.
-// Values are written back with 16-byte stores; the factor gathers never leave shared memory.
-// Reduction tree of an item: lane-serial over its steps, xor-butterfly over the 8 lanes.
+// PANEL kernel (layout.cuh): persistent CTAs, one per SM.  Every CTA has a home panel (CTAs are dealt to
+// panels in proportion to the panels' work); it stages that panel of the gathered factor vector(s) in
+// shared memory, then its warps pull 32 work items at a time from the panel's global queue (the next 32
+// descriptors are fetched one pull ahead).  A batch is 4 consecutive items, one per 8-lane group of the
+// warp; a group streams its item in steps of 32 entries — a lane owns 4 consecutive entries of a step
+// (8-byte index vector, 16-byte value vector), a group's load covers one contiguous 64/128-byte span —
+// with four steps in flight per group (register ring).  Items are stored longest-first inside a panel
+// (degree-binned order, prep.cu), so the four items of a batch have nearly equal length and a panel's
+// queue ends with its shortest items.  When a panel's queue is drained the CTA re-stages the panel with
+// the most items left and helps there (work stealing), so all SMs finish together.  The last CTA out
+// resets the queues.  Values are written back with 16-byte stores; the factor gathers never leave shared
+// memory.  Reduction tree of an item: lane-serial over its steps, xor-butterfly over the 8 lanes.
 #include "ccd_kernels.cuh"
 
 namespace mf {
 namespace {
 
 constexpr unsigned kFull = 0xffffffffu;
+constexpr uint32_t kStealMin = 256;  // a drained CTA re-stages a panel only if that panel still has more items than this
 
 // One lane's share of a 32-entry step of its 8-lane group: 4 consecutive entries (8 bytes of indices,
 // 16 bytes of values), so that a group's load covers one contiguous 64- or 128-byte span.
@@ -66,7 +69,6 @@ __global__ void __launch_bounds__(1024, 1) k_panel_sweep(PanelSweepArgs a) {
     constexpr bool SUB = MODE & kSub, ADD = MODE & kAdd, SOLVE = MODE & kSolve, ADDSEP = MODE & kAddSep;
     constexpr bool WRITE = SUB || ADD;
     extern __shared__ __align__(16) float smem[];
-    __shared__ unsigned s_ctr;
 
     const uint32_t PR = a.panel_rows;
     const uint32_t stride = PR + 8;  // 8 zeroed floats behind each panel: the padding slot idx16 == PR
@@ -86,52 +88,60 @@ __global__ void __launch_bounds__(1024, 1) k_panel_sweep(PanelSweepArgs a) {
     const int lane = threadIdx.x & 31;
     const int grp = lane >> 3, sl = lane & 7;
     const uint4* __restrict__ items = reinterpret_cast<const uint4*>(a.items);
+    __shared__ int s_next_panel;
 
-    uint32_t ib = a.cta_item_ptr[blockIdx.x];
-    const uint32_t ie = a.cta_item_ptr[blockIdx.x + 1];
+    // home panel: the one holding the first item of this CTA's equal-cost share
     int p = 0;
-    while (p < a.npanels && a.panel_item_ptr[p + 1] <= ib) ++p;
+    {
+        const uint32_t first = a.cta_item_ptr[blockIdx.x];
+        while (p + 1 < a.npanels && a.panel_item_ptr[p + 1] <= first) ++p;
+    }
 
-    while (ib < ie && p < a.npanels) {
-        const uint32_t pend = a.panel_item_ptr[p + 1];
-        const uint32_t pe = ie < pend ? ie : pend;
-        if (pe > ib) {
-            __syncthreads();  // every warp is done with the previous panel and counter
-            const int64_t base = (int64_t)p * PR;
-            const uint32_t cnt = (uint32_t)((a.gdim - base) < (int64_t)PR ? (a.gdim - base) : (int64_t)PR);
-            for (uint32_t i = threadIdx.x; i < stride; i += blockDim.x) {
-                const bool in = i < cnt;
-                if (NEEDNEW) sm_new[i] = in ? a.g_new[base + i] : 0.0f;
-                if (ADD && ADDSEP) sm_add[i] = in ? g_add[base + i] : 0.0f;
-                if (SUB) sm_old[i] = in ? a.g_old[base + i] : 0.0f;
-            }
-            if (threadIdx.x == 0) s_ctr = ib;
-            __syncthreads();
+    while (p >= 0) {
+        // ---- stage panel p of the gathered vector(s)
+        const int64_t base = (int64_t)p * PR;
+        const uint32_t cnt = (uint32_t)((a.gdim - base) < (int64_t)PR ? (a.gdim - base) : (int64_t)PR);
+        for (uint32_t i = threadIdx.x; i < stride; i += blockDim.x) {
+            const bool in = i < cnt;
+            if (NEEDNEW) sm_new[i] = in ? a.g_new[base + i] : 0.0f;
+            if (ADD && ADDSEP) sm_add[i] = in ? g_add[base + i] : 0.0f;
+            if (SUB) sm_old[i] = in ? a.g_old[base + i] : 0.0f;
+        }
+        __syncthreads();
 
-            // Batches of four items (one per 8-lane group); items are stored longest-first inside a panel, so
-            // the four items of a batch have (nearly) the same length.  The next batch's descriptors are
-            // fetched while this batch is processed.
-            uint32_t i0 = 0;
-            if (lane == 0) i0 = atomicAdd(&s_ctr, 4u);
-            i0 = __shfl_sync(kFull, i0, 0);
-            uint4 d = make_uint4(0u, 0u, 0u, 0u);  // {start, len, seg, slot}; len 0 = no item
-            if (i0 + grp < pe) d = __ldg(items + i0 + grp);
-            while (i0 < pe) {
-                uint32_t i0n = 0;
-                if (lane == 0) i0n = atomicAdd(&s_ctr, 4u);
-                i0n = __shfl_sync(kFull, i0n, 0);
-                uint4 dn = make_uint4(0u, 0u, 0u, 0u);
-                if (i0n + grp < pe) dn = __ldg(items + i0n + grp);
+        // ---- warps pull 32 items at a time from the panel's queue (the next 32 descriptors are fetched while
+        //      the current ones are processed); a batch = 4 consecutive items, one per 8-lane group.  Items are
+        //      stored longest-first inside a panel, so the four items of a batch have nearly the same length.
+        const uint32_t pbeg = a.panel_item_ptr[p], pend = a.panel_item_ptr[p + 1];
+        unsigned* qctr = a.queue + p;
+        uint32_t q = 0;
+        if (lane == 0) q = pbeg + atomicAdd(qctr, 32u);
+        q = __shfl_sync(kFull, q, 0);
+        uint4 d = make_uint4(0u, 0u, 0u, 0u);  // {start, len, seg, slot}; len 0 = no item
+        if (q < pend && q + lane < pend) d = __ldg(items + q + lane);
+        while (q < pend) {
+            uint32_t qn = 0;
+            if (lane == 0) qn = pbeg + atomicAdd(qctr, 32u);
+            qn = __shfl_sync(kFull, qn, 0);
+            uint4 dn = make_uint4(0u, 0u, 0u, 0u);
+            if (qn < pend && qn + lane < pend) dn = __ldg(items + qn + lane);
 
-                const uint32_t len = d.y;
-                const uint32_t lane_off = 4u * (uint32_t)sl;     // this lane's 4 entries inside a 32-entry step
-                const uint32_t pos = d.x + lane_off;
+#pragma unroll 1
+            for (int b = 0; b < 8; ++b) {
+                const int src = 4 * b + grp;
+                const uint32_t start = __shfl_sync(kFull, d.x, src);
+                const uint32_t len = __shfl_sync(kFull, d.y, src);
+                const uint32_t seg = __shfl_sync(kFull, d.z, src);
+                const uint32_t slot = __shfl_sync(kFull, d.w, src);
+                const uint32_t maxlen = __reduce_max_sync(kFull, len);
+                if (maxlen == 0u) break;  // past the end of the panel
+                const uint32_t lane_off = 4u * (uint32_t)sl;  // this lane's 4 entries inside a 32-entry step
+                const uint32_t pos = start + lane_off;
                 float s_add = 0.0f, s_old = 0.0f;
                 if (len != 0u) {
-                    if (ADD) s_add = __ldg(a.s_add + a.seg_offset + d.z);
-                    if (SUB) s_old = __ldg(a.s_old + a.seg_offset + d.z);
+                    if (ADD) s_add = __ldg(a.s_add + a.seg_offset + seg);
+                    if (SUB) s_old = __ldg(a.s_old + a.seg_offset + seg);
                 }
-                const uint32_t maxlen = __reduce_max_sync(kFull, len);
                 float g = 0.0f, h = 0.0f;
                 // four 32-entry steps in flight per group (register ring e0..e3)
                 Step e0, e1, e2, e3;
@@ -164,14 +174,36 @@ __global__ void __launch_bounds__(1024, 1) k_panel_sweep(PanelSweepArgs a) {
                         g += __shfl_xor_sync(kFull, g, o);
                         h += __shfl_xor_sync(kFull, h, o);
                     }
-                    if (sl == 0 && len != 0u) a.partials[d.w] = make_float2(g, h);
+                    if (sl == 0 && len != 0u) a.partials[slot] = make_float2(g, h);
                 }
-                i0 = i0n;
-                d = dn;
             }
+            q = qn;
+            d = dn;
         }
-        ib = pe;
-        ++p;
+
+        // ---- this panel's queue is drained: help the panel with the most items left, or leave
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int best = -1;
+            uint32_t best_left = kStealMin;
+            for (int pp = 0; pp < a.npanels; ++pp) {
+                const uint32_t n = a.panel_item_ptr[pp + 1] - a.panel_item_ptr[pp];
+                const uint32_t taken = atomicAdd(a.queue + pp, 0u);
+                const uint32_t left = taken < n ? n - taken : 0u;
+                if (left > best_left) { best_left = left; best = pp; }
+            }
+            s_next_panel = best;
+        }
+        __syncthreads();
+        p = s_next_panel;
+    }
+
+    // ---- the last CTA out resets the queues for the next launch
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(a.queue + a.npanels, 1u) == gridDim.x - 1) {
+            for (int pp = 0; pp <= a.npanels; ++pp) a.queue[pp] = 0u;
+        }
     }
 }
 

@@ -56,6 +56,7 @@ struct Side {
     float2* partials = nullptr;       // [nslots]
     uint32_t* cta_item_ptr = nullptr; // [ncta+1] equal-cost contiguous item ranges
     uint32_t* panel_item_ptr = nullptr; // [npanels+1]
+    unsigned* queue = nullptr;          // [npanels+1] work cursors of the sweep kernel (zero between launches)
     int ncta = 0;
     bool sorted = true;
 };

@@ -231,7 +231,7 @@ inline unsigned grid_for(int64_t n, int block) { return (unsigned)((n + block - 
 
 int side_free(Side& s) {
     void* ptrs[] = {s.ptr, s.idx, s.val, s.piece_ptr, s.piece_first, s.item_ptr, s.idx16, s.pval, s.items,
-                    s.slot_ptr, s.partials, s.cta_item_ptr, s.panel_item_ptr};
+                    s.slot_ptr, s.partials, s.cta_item_ptr, s.panel_item_ptr, s.queue};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     s = Side();
@@ -275,6 +275,8 @@ int side_build_panels(Side& s, int panel_rows, int chunk, int ncta, cudaStream_t
     MF_TRY(dev_alloc(&seg_items, (size_t)s.nseg));
     MF_TRY(dev_alloc(&s.slot_ptr, (size_t)s.nseg + 1));
     MF_TRY(dev_alloc(&s.panel_item_ptr, (size_t)s.npanels + 1));
+    MF_TRY(dev_alloc(&s.queue, (size_t)s.npanels + 1));
+    MF_CUDA(cudaMemsetAsync(s.queue, 0, sizeof(unsigned) * ((size_t)s.npanels + 1), st));
     MF_TRY(dev_alloc(&s.cta_item_ptr, (size_t)ncta + 1));
     size_t tmp_n = scan_tmp_elems((size_t)(Q > s.nseg ? Q : s.nseg));
     MF_TRY(dev_alloc(&tmp, tmp_n));

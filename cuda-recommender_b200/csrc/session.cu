@@ -143,7 +143,7 @@ int run_sweep(mf_session* s, Side& sd, int mode, const SweepVectors& v, float* o
     if (s->panel) {
         PanelSweepArgs a;
         a.idx16 = sd.idx16; a.val = sd.pval; a.items = sd.items;
-        a.cta_item_ptr = sd.cta_item_ptr; a.panel_item_ptr = sd.panel_item_ptr;
+        a.cta_item_ptr = sd.cta_item_ptr; a.panel_item_ptr = sd.panel_item_ptr; a.queue = sd.queue;
         a.npanels = sd.npanels; a.panel_rows = (uint32_t)sd.panel_rows; a.gdim = sd.gdim;
         a.seg_offset = sd.seg_offset;
         a.g_new = v.g_new; a.g_add = v.g_add; a.g_old = v.g_old; a.s_add = v.s_add; a.s_old = v.s_old;
