@@ -10,25 +10,25 @@
 // path, so both copies stay bit-identical to the oracle's residual; g and h use FMA and a fixed
 // reduction tree (lane-serial over 8 entries, xor-butterfly over lanes, slots in order).
 //
-// PANEL kernel (layout.cuh): persistent CTAs, one per SM.  Every CTA has a home panel (CTAs are dealt to
-// panels in proportion to the panels' work); it stages that panel of the gathered factor vector(s) in
-// shared memory, then its warps pull 32 work items at a time from the panel's global queue (the next 32
-// descriptors are fetched one pull ahead).  A batch is 4 consecutive items, one per 8-lane group of the
-// warp; a group streams its item in steps of 32 entries — a lane owns 4 consecutive entries of a step
-// (8-byte index vector, 16-byte value vector), a group's load covers one contiguous 64/128-byte span —
-// with four steps in flight per group (register ring).  Items are stored longest-first inside a panel
-// (degree-binned order, prep.cu), so the four items of a batch have nearly equal length and a panel's
-// queue ends with its shortest items.  When a panel's queue is drained the CTA re-stages the panel with
-// the most items left and helps there (work stealing), so all SMs finish together.  The last CTA out
-// resets the queues.  Values are written back with 16-byte stores; the factor gathers never leave shared
-// memory.  Reduction tree of an item: lane-serial over its steps, xor-butterfly over the 8 lanes.
+// PANEL kernel (layout.cuh): persistent CTAs, one per SM.  A CTA owns an equal-cost contiguous range of
+// work items; for every panel its range touches it stages that panel of the gathered factor vector(s) in
+// shared memory, then its warps pull work from two shared-memory counters (descriptors are fetched one
+// pull ahead).  Inside a panel the items are stored longest-first (degree-binned order, prep.cu):
+//   * long items (len >= long_len) come first: one warp streams one item, 128 entries per step — a lane
+//     owns 4 consecutive entries, so a warp load is one contiguous 256-byte (uint16 indices) / 512-byte
+//     (values) span;
+//   * short items follow: four consecutive items per warp, one per 8-lane group, 32 entries per step and
+//     group (64/128-byte spans); neighbours in the sorted order have nearly the same length, so the four
+//     groups stay in step.
+// Either way four steps are in flight per lane group (register ring).  Values are written back with
+// 16-byte stores; the factor gathers never leave shared memory.  The reduction tree of an item is a
+// function of its length only: lane-serial over its steps, xor-butterfly over the lanes of its group.
 #include "ccd_kernels.cuh"
 
 namespace mf {
 namespace {
 
 constexpr unsigned kFull = 0xffffffffu;
-constexpr uint32_t kStealMin = 256;  // a drained CTA re-stages a panel only if that panel still has more items than this
 
 // One lane's share of a 32-entry step of its 8-lane group: 4 consecutive entries (8 bytes of indices,
 // 16 bytes of values), so that a group's load covers one contiguous 64- or 128-byte span.
@@ -64,11 +64,48 @@ __device__ __forceinline__ void calc4(Step& e, const float* __restrict__ sm_new,
     if (SUB || ADD) e.v = make_float4(v[0], v[1], v[2], v[3]);
 }
 
+// Streams one work item through a lane group: `lane_off` is this lane's offset inside a step (4 entries per
+// lane), STEP the entries a step covers (8 lanes -> 32, 32 lanes -> 128), `maxlen` the longest item among the
+// groups of the warp (loop bound, warp-uniform).  Four steps are kept in flight (register ring e0..e3): the
+// load of step s+4 is issued right after step s is consumed.
+template <int MODE, uint32_t STEP>
+__device__ __forceinline__ void stream_item(const PanelSweepArgs& a, uint32_t start, uint32_t len, uint32_t maxlen,
+                                            uint32_t lane_off, const float* __restrict__ sm_new,
+                                            const float* __restrict__ sm_add, const float* __restrict__ sm_old, float s_add,
+                                            float s_old, float& g, float& h) {
+    constexpr bool WRITE = (MODE & kSub) || (MODE & kAdd);
+    const uint32_t pos = start + lane_off;
+    Step e0, e1, e2, e3;
+#define MF_LOAD(e, o) if ((o) + lane_off < len) e = load_step(a.idx16, a.val, pos + (o))
+#define MF_USE(e, o)                                                                        \
+    if ((o) + lane_off < len) {                                                             \
+        calc4<MODE>(e, sm_new, sm_add, sm_old, s_add, s_old, g, h);                         \
+        if (WRITE) __stcs(reinterpret_cast<float4*>(a.val + pos + (o)), e.v);               \
+    }
+    MF_LOAD(e0, 0u);
+    MF_LOAD(e1, STEP);
+    MF_LOAD(e2, 2u * STEP);
+    MF_LOAD(e3, 3u * STEP);
+#pragma unroll 1
+    for (uint32_t o = 0; o < maxlen; o += 4u * STEP) {
+        MF_USE(e0, o);
+        MF_LOAD(e0, o + 4u * STEP);
+        MF_USE(e1, o + STEP);
+        MF_LOAD(e1, o + 5u * STEP);
+        MF_USE(e2, o + 2u * STEP);
+        MF_LOAD(e2, o + 6u * STEP);
+        MF_USE(e3, o + 3u * STEP);
+        MF_LOAD(e3, o + 7u * STEP);
+    }
+#undef MF_LOAD
+#undef MF_USE
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(1024, 1) k_panel_sweep(PanelSweepArgs a) {
     constexpr bool SUB = MODE & kSub, ADD = MODE & kAdd, SOLVE = MODE & kSolve, ADDSEP = MODE & kAddSep;
-    constexpr bool WRITE = SUB || ADD;
     extern __shared__ __align__(16) float smem[];
+    __shared__ unsigned s_ctr_long, s_ctr_short;
 
     const uint32_t PR = a.panel_rows;
     const uint32_t stride = PR + 8;  // 8 zeroed floats behind each panel: the padding slot idx16 == PR
@@ -88,122 +125,96 @@ __global__ void __launch_bounds__(1024, 1) k_panel_sweep(PanelSweepArgs a) {
     const int lane = threadIdx.x & 31;
     const int grp = lane >> 3, sl = lane & 7;
     const uint4* __restrict__ items = reinterpret_cast<const uint4*>(a.items);
-    __shared__ int s_next_panel;
 
-    // home panel: the one holding the first item of this CTA's equal-cost share
+    uint32_t ib = a.cta_item_ptr[blockIdx.x];
+    const uint32_t ie = a.cta_item_ptr[blockIdx.x + 1];
     int p = 0;
-    {
-        const uint32_t first = a.cta_item_ptr[blockIdx.x];
-        while (p + 1 < a.npanels && a.panel_item_ptr[p + 1] <= first) ++p;
-    }
+    while (p < a.npanels && a.panel_item_ptr[p + 1] <= ib) ++p;
 
-    while (p >= 0) {
-        // ---- stage panel p of the gathered vector(s)
-        const int64_t base = (int64_t)p * PR;
-        const uint32_t cnt = (uint32_t)((a.gdim - base) < (int64_t)PR ? (a.gdim - base) : (int64_t)PR);
-        for (uint32_t i = threadIdx.x; i < stride; i += blockDim.x) {
-            const bool in = i < cnt;
-            if (NEEDNEW) sm_new[i] = in ? a.g_new[base + i] : 0.0f;
-            if (ADD && ADDSEP) sm_add[i] = in ? g_add[base + i] : 0.0f;
-            if (SUB) sm_old[i] = in ? a.g_old[base + i] : 0.0f;
-        }
-        __syncthreads();
+    while (ib < ie && p < a.npanels) {
+        const uint32_t pend = a.panel_item_ptr[p + 1];
+        const uint32_t pe = ie < pend ? ie : pend;
+        if (pe > ib) {
+            __syncthreads();  // every warp is done with the previous panel and its counters
+            const int64_t base = (int64_t)p * PR;
+            const uint32_t cnt = (uint32_t)((a.gdim - base) < (int64_t)PR ? (a.gdim - base) : (int64_t)PR);
+            for (uint32_t i = threadIdx.x; i < stride; i += blockDim.x) {
+                const bool in = i < cnt;
+                if (NEEDNEW) sm_new[i] = in ? a.g_new[base + i] : 0.0f;
+                if (ADD && ADDSEP) sm_add[i] = in ? g_add[base + i] : 0.0f;
+                if (SUB) sm_old[i] = in ? a.g_old[base + i] : 0.0f;
+            }
+            // items [ib, mid) are long (len >= long_len): one warp each; items [mid, pe) are short: four per warp
+            uint32_t mid = a.panel_mid[p];
+            mid = mid < ib ? ib : (mid > pe ? pe : mid);
+            if (threadIdx.x == 0) { s_ctr_long = ib; s_ctr_short = mid; }
+            __syncthreads();
 
-        // ---- warps pull 32 items at a time from the panel's queue (the next 32 descriptors are fetched while
-        //      the current ones are processed); a batch = 4 consecutive items, one per 8-lane group.  Items are
-        //      stored longest-first inside a panel, so the four items of a batch have nearly the same length.
-        const uint32_t pbeg = a.panel_item_ptr[p], pend = a.panel_item_ptr[p + 1];
-        unsigned* qctr = a.queue + p;
-        uint32_t q = 0;
-        if (lane == 0) q = pbeg + atomicAdd(qctr, 32u);
-        q = __shfl_sync(kFull, q, 0);
-        uint4 d = make_uint4(0u, 0u, 0u, 0u);  // {start, len, seg, slot}; len 0 = no item
-        if (q < pend && q + lane < pend) d = __ldg(items + q + lane);
-        while (q < pend) {
-            uint32_t qn = 0;
-            if (lane == 0) qn = pbeg + atomicAdd(qctr, 32u);
-            qn = __shfl_sync(kFull, qn, 0);
-            uint4 dn = make_uint4(0u, 0u, 0u, 0u);
-            if (qn < pend && qn + lane < pend) dn = __ldg(items + qn + lane);
-
-#pragma unroll 1
-            for (int b = 0; b < 8; ++b) {
-                const int src = 4 * b + grp;
-                const uint32_t start = __shfl_sync(kFull, d.x, src);
-                const uint32_t len = __shfl_sync(kFull, d.y, src);
-                const uint32_t seg = __shfl_sync(kFull, d.z, src);
-                const uint32_t slot = __shfl_sync(kFull, d.w, src);
-                const uint32_t maxlen = __reduce_max_sync(kFull, len);
-                if (maxlen == 0u) break;  // past the end of the panel
-                const uint32_t lane_off = 4u * (uint32_t)sl;  // this lane's 4 entries inside a 32-entry step
-                const uint32_t pos = start + lane_off;
-                float s_add = 0.0f, s_old = 0.0f;
-                if (len != 0u) {
-                    if (ADD) s_add = __ldg(a.s_add + a.seg_offset + seg);
-                    if (SUB) s_old = __ldg(a.s_old + a.seg_offset + seg);
-                }
-                float g = 0.0f, h = 0.0f;
-                // four 32-entry steps in flight per group (register ring e0..e3)
-                Step e0, e1, e2, e3;
-#define MF_LOAD(e, o) if ((o) + lane_off < len) e = load_step(a.idx16, a.val, pos + (o))
-#define MF_USE(e, o)                                                                        \
-    if ((o) + lane_off < len) {                                                             \
-        calc4<MODE>(e, sm_new, sm_add, sm_old, s_add, s_old, g, h);                         \
-        if (WRITE) __stcs(reinterpret_cast<float4*>(a.val + pos + (o)), e.v);               \
-    }
-                MF_LOAD(e0, 0u);
-                MF_LOAD(e1, 32u);
-                MF_LOAD(e2, 64u);
-                MF_LOAD(e3, 96u);
-#pragma unroll 1
-                for (uint32_t o = 0; o < maxlen; o += 128u) {
-                    MF_USE(e0, o);
-                    MF_LOAD(e0, o + 128u);
-                    MF_USE(e1, o + 32u);
-                    MF_LOAD(e1, o + 160u);
-                    MF_USE(e2, o + 64u);
-                    MF_LOAD(e2, o + 192u);
-                    MF_USE(e3, o + 96u);
-                    MF_LOAD(e3, o + 224u);
-                }
-#undef MF_LOAD
-#undef MF_USE
-                if (SOLVE) {
+            // ---- long items: the whole warp streams one item, 128 entries per step (512-byte value loads)
+            {
+                uint32_t i = 0;
+                if (lane == 0) i = atomicAdd(&s_ctr_long, 1u);
+                i = __shfl_sync(kFull, i, 0);
+                uint4 d = make_uint4(0u, 0u, 0u, 0u);  // {start, len, seg, slot}
+                if (i < mid) d = __ldg(items + i);
+                while (i < mid) {
+                    uint32_t in = 0;
+                    if (lane == 0) in = atomicAdd(&s_ctr_long, 1u);
+                    in = __shfl_sync(kFull, in, 0);
+                    uint4 dn = make_uint4(0u, 0u, 0u, 0u);
+                    if (in < mid) dn = __ldg(items + in);  // next descriptor, one item ahead
+                    float s_add = 0.0f, s_old = 0.0f, g = 0.0f, h = 0.0f;
+                    if (ADD) s_add = __ldg(a.s_add + a.seg_offset + d.z);
+                    if (SUB) s_old = __ldg(a.s_old + a.seg_offset + d.z);
+                    stream_item<MODE, 128u>(a, d.x, d.y, d.y, 4u * (uint32_t)lane, sm_new, sm_add, sm_old, s_add, s_old, g, h);
+                    if (SOLVE) {
 #pragma unroll
-                    for (int o = 1; o < 8; o <<= 1) {
-                        g += __shfl_xor_sync(kFull, g, o);
-                        h += __shfl_xor_sync(kFull, h, o);
+                        for (int o = 1; o < 32; o <<= 1) {
+                            g += __shfl_xor_sync(kFull, g, o);
+                            h += __shfl_xor_sync(kFull, h, o);
+                        }
+                        if (lane == 0) a.partials[d.w] = make_float2(g, h);
                     }
-                    if (sl == 0 && len != 0u) a.partials[slot] = make_float2(g, h);
+                    i = in;
+                    d = dn;
                 }
             }
-            q = qn;
-            d = dn;
-        }
-
-        // ---- this panel's queue is drained: help the panel with the most items left, or leave
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            int best = -1;
-            uint32_t best_left = kStealMin;
-            for (int pp = 0; pp < a.npanels; ++pp) {
-                const uint32_t n = a.panel_item_ptr[pp + 1] - a.panel_item_ptr[pp];
-                const uint32_t taken = atomicAdd(a.queue + pp, 0u);
-                const uint32_t left = taken < n ? n - taken : 0u;
-                if (left > best_left) { best_left = left; best = pp; }
+            // ---- short items: batches of four, one item per 8-lane group, 32 entries per step and group; the
+            //      items are stored longest-first, so the four items of a batch have nearly the same length
+            {
+                uint32_t i0 = 0;
+                if (lane == 0) i0 = atomicAdd(&s_ctr_short, 4u);
+                i0 = __shfl_sync(kFull, i0, 0);
+                uint4 d = make_uint4(0u, 0u, 0u, 0u);  // len 0 = no item
+                if (i0 + grp < pe) d = __ldg(items + i0 + grp);
+                while (i0 < pe) {
+                    uint32_t i0n = 0;
+                    if (lane == 0) i0n = atomicAdd(&s_ctr_short, 4u);
+                    i0n = __shfl_sync(kFull, i0n, 0);
+                    uint4 dn = make_uint4(0u, 0u, 0u, 0u);
+                    if (i0n + grp < pe) dn = __ldg(items + i0n + grp);
+                    float s_add = 0.0f, s_old = 0.0f, g = 0.0f, h = 0.0f;
+                    if (d.y != 0u) {
+                        if (ADD) s_add = __ldg(a.s_add + a.seg_offset + d.z);
+                        if (SUB) s_old = __ldg(a.s_old + a.seg_offset + d.z);
+                    }
+                    const uint32_t maxlen = __reduce_max_sync(kFull, d.y);
+                    stream_item<MODE, 32u>(a, d.x, d.y, maxlen, 4u * (uint32_t)sl, sm_new, sm_add, sm_old, s_add, s_old, g, h);
+                    if (SOLVE) {
+#pragma unroll
+                        for (int o = 1; o < 8; o <<= 1) {
+                            g += __shfl_xor_sync(kFull, g, o);
+                            h += __shfl_xor_sync(kFull, h, o);
+                        }
+                        if (sl == 0 && d.y != 0u) a.partials[d.w] = make_float2(g, h);
+                    }
+                    i0 = i0n;
+                    d = dn;
+                }
             }
-            s_next_panel = best;
         }
-        __syncthreads();
-        p = s_next_panel;
-    }
-
-    // ---- the last CTA out resets the queues for the next launch
-    if (threadIdx.x == 0) {
-        __threadfence();
-        if (atomicAdd(a.queue + a.npanels, 1u) == gridDim.x - 1) {
-            for (int pp = 0; pp <= a.npanels; ++pp) a.queue[pp] = 0u;
-        }
+        ib = pe;
+        ++p;
     }
 }
 

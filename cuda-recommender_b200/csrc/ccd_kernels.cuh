@@ -18,7 +18,7 @@ struct PanelSweepArgs {
     const WorkItem* items;
     const uint32_t* cta_item_ptr;
     const uint32_t* panel_item_ptr;
-    unsigned* queue;      // [npanels + 1] per-panel item cursors + exit counter, all zero between launches
+    const uint32_t* panel_mid;  // [npanels] first short item (len < long_len) of each panel
     int npanels;
     uint32_t panel_rows;
     int64_t gdim;

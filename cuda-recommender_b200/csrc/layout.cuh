@@ -56,14 +56,15 @@ struct Side {
     float2* partials = nullptr;       // [nslots]
     uint32_t* cta_item_ptr = nullptr; // [ncta+1] equal-cost contiguous item ranges
     uint32_t* panel_item_ptr = nullptr; // [npanels+1]
-    unsigned* queue = nullptr;          // [npanels+1] work cursors of the sweep kernel (zero between launches)
+    uint32_t* panel_mid = nullptr;      // [npanels] first item of the panel with len < long_len (items are longest-first)
+    int long_len = 0;                   // items at least this long are streamed by a whole warp
     int ncta = 0;
     bool sorted = true;
 };
 
 int side_free(Side& s);
 // raw device arrays must be set (ptr, idx, val, nseg, gdim, nnz); builds everything else.
-int side_build_panels(Side& s, int panel_rows, int chunk, int ncta, cudaStream_t st);
+int side_build_panels(Side& s, int panel_rows, int chunk, int long_len, int ncta, cudaStream_t st);
 // dst_raw[nnz] <- current panel values in the caller's order; and the inverse
 int side_panel_to_raw(const Side& s, float* dst_raw, cudaStream_t st);
 int side_raw_to_panel(Side& s, const float* src_raw, cudaStream_t st);

@@ -11,6 +11,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 
 #include "rmse.cuh"
 
@@ -143,7 +144,7 @@ int run_sweep(mf_session* s, Side& sd, int mode, const SweepVectors& v, float* o
     if (s->panel) {
         PanelSweepArgs a;
         a.idx16 = sd.idx16; a.val = sd.pval; a.items = sd.items;
-        a.cta_item_ptr = sd.cta_item_ptr; a.panel_item_ptr = sd.panel_item_ptr; a.queue = sd.queue;
+        a.cta_item_ptr = sd.cta_item_ptr; a.panel_item_ptr = sd.panel_item_ptr; a.panel_mid = sd.panel_mid;
         a.npanels = sd.npanels; a.panel_rows = (uint32_t)sd.panel_rows; a.gdim = sd.gdim;
         a.seg_offset = sd.seg_offset;
         a.g_new = v.g_new; a.g_add = v.g_add; a.g_old = v.g_old; a.s_add = v.s_add; a.s_old = v.s_old;
@@ -291,8 +292,22 @@ int check_ratings(const mf_ratings* R) {
     return MF_OK;
 }
 
+// MF_TRACE=1 in the environment prints host-side phase timings of session creation to stderr
+struct Trace {
+    bool on;
+    std::chrono::steady_clock::time_point t0;
+    Trace() : on(getenv("MF_TRACE") != nullptr), t0(std::chrono::steady_clock::now()) {}
+    void mark(const char* what) {
+        if (!on) return;
+        auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[mf trace] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
+
 int create_impl(const mf_ratings* R, const mf_testset* T, const mf_params* params, int rank, int nranks,
                 const void* nccl_id, mf_session** out) {
+    Trace trace;
     MF_REQUIRE(out != nullptr && params != nullptr, "NULL argument");
     *out = nullptr;
     MF_TRY(check_ratings(R));
@@ -322,6 +337,7 @@ int create_impl(const mf_ratings* R, const mf_testset* T, const mf_params* param
     s->timer.st = s->st;
     s->timer.enabled = true;
 
+    trace.mark("device/stream setup");
     std::vector<uint32_t> rp, cp;
     if ((rc = fetch_ptr(R->csr_row_ptr, R->rows + 1, rp)) != MF_OK) return fail(rc);
     if ((rc = fetch_ptr(R->csc_col_ptr, R->cols + 1, cp)) != MF_OK) return fail(rc);
@@ -335,6 +351,7 @@ int create_impl(const mf_ratings* R, const mf_testset* T, const mf_params* param
     if ((rc = upload_side(s->csr, rp, s->row_bound[rank], s->row_bound[rank + 1], R->csr_col_idx, R->csr_val, R->cols, s->st)) != MF_OK) return fail(rc);
     if ((rc = upload_side(s->csc, cp, s->col_bound[rank], s->col_bound[rank + 1], R->csc_row_idx, R->csc_val, R->rows, s->st)) != MF_OK) return fail(rc);
 
+    trace.mark("upload CSR + CSC");
     const bool ccd = params->solver_type == MF_SOLVER_CCD;
     if (ccd) {
         s->panel = params->layout == MF_LAYOUT_PANEL;
@@ -350,12 +367,14 @@ int create_impl(const mf_ratings* R, const mf_testset* T, const mf_params* param
             if (params->panel_rows > 0) { cap_c = std::min(cap_c, params->panel_rows / 8 * 8); cap_r = std::min(cap_r, params->panel_rows / 8 * 8); }
             else cap_c = std::min(cap_c, 24576);
             const int chunk = params->chunk > 0 ? std::max(8, params->chunk / 8 * 8) : 2048;
-            if ((rc = side_build_panels(s->csc, choose_panel_rows(s->csc.gdim, std::max(cap_c, 8)), chunk, s->sm_count, s->st)) != MF_OK) return fail(rc);
-            if ((rc = side_build_panels(s->csr, choose_panel_rows(s->csr.gdim, std::max(cap_r, 8)), chunk, s->sm_count, s->st)) != MF_OK) return fail(rc);
+            const int long_len = params->long_len > 0 ? params->long_len : 512;
+            if ((rc = side_build_panels(s->csc, choose_panel_rows(s->csc.gdim, std::max(cap_c, 8)), chunk, long_len, s->sm_count, s->st)) != MF_OK) return fail(rc);
+            if ((rc = side_build_panels(s->csr, choose_panel_rows(s->csr.gdim, std::max(cap_r, 8)), chunk, long_len, s->sm_count, s->st)) != MF_OK) return fail(rc);
             // the caller-order index/value arrays are no longer needed: the residual lives in the panel arrays
             cudaFree(s->csc.idx); s->csc.idx = nullptr; cudaFree(s->csc.val); s->csc.val = nullptr;
             cudaFree(s->csr.idx); s->csr.idx = nullptr; cudaFree(s->csr.val); s->csr.val = nullptr;
         }
+        trace.mark("sortedness + panel layout");
         s->ldm = round_up(s->rows, 32);
         s->ldn = round_up(s->cols, 32);
         if ((rc = dev_alloc(&s->W, (size_t)s->k * s->ldm)) != MF_OK) return fail(rc);
@@ -389,6 +408,7 @@ int create_impl(const mf_ratings* R, const mf_testset* T, const mf_params* param
     }
     cudaError_t e = cudaStreamSynchronize(s->st);
     if (e != cudaSuccess) { set_error("session setup failed: %s", cudaGetErrorString(e)); return fail(MF_ERR_CUDA); }
+    trace.mark("factors + test set + comm");
     *out = s;
     return MF_OK;
 }
