@@ -10,19 +10,17 @@
 // path, so both copies stay bit-identical to the oracle's residual; g and h use FMA and a fixed
 // reduction tree (lane-serial over 8 entries, xor-butterfly over lanes, slots in order).
 //
-// PANEL kernel (layout.cuh): persistent CTAs, one per SM.  A CTA owns an equal-cost contiguous range of
-// work items; for every panel its range touches it stages that panel of the gathered factor vector(s) in
-// shared memory, then its warps pull work from two shared-memory counters (descriptors are fetched one
-// pull ahead).  Inside a panel the items are stored longest-first (degree-binned order, prep.cu):
-//   * long items (len >= long_len) come first: one warp streams one item, 128 entries per step — a lane
-//     owns 4 consecutive entries, so a warp load is one contiguous 256-byte (uint16 indices) / 512-byte
-//     (values) span;
-//   * short items follow: four consecutive items per warp, one per 8-lane group, 32 entries per step and
-//     group (64/128-byte spans); neighbours in the sorted order have nearly the same length, so the four
-//     groups stay in step.
-// Either way four steps are in flight per lane group (register ring).  Values are written back with
-// 16-byte stores; the factor gathers never leave shared memory.  The reduction tree of an item is a
-// function of its length only: lane-serial over its steps, xor-butterfly over the lanes of its group.
+// PANEL kernel (layout.cuh): persistent CTAs, one per SM.  A CTA owns an equal-cost contiguous range
+// of work items; for every panel its range touches it stages that panel of the gathered factor
+// vector(s) in shared memory, then its warps pull batches of four items from a shared-memory counter
+// (the next batch's descriptors are fetched one batch ahead).  Each 8-lane group of the warp streams
+// one item in steps of 32 entries — a lane owns 4 consecutive entries of a step (8-byte index vector,
+// 16-byte value vector), a group's load covers one contiguous 64/128-byte span — with four steps in
+// flight per group (register ring).  Inside a panel the items are length-ranked and dealt into lanes
+// (degree-binned order, prep.cu), so the four items of a batch have nearly equal length (the groups
+// stay in step) and every CTA range holds the same mix of lengths (the CTAs finish together).
+// Values are written back with 16-byte stores; the factor gathers never leave shared memory.
+// Reduction tree of an item: lane-serial over its steps, xor-butterfly over the 8 lanes.
 #include "ccd_kernels.cuh"
 
 namespace mf {
@@ -64,48 +62,12 @@ __device__ __forceinline__ void calc4(Step& e, const float* __restrict__ sm_new,
     if (SUB || ADD) e.v = make_float4(v[0], v[1], v[2], v[3]);
 }
 
-// Streams one work item through a lane group: `lane_off` is this lane's offset inside a step (4 entries per
-// lane), STEP the entries a step covers (8 lanes -> 32, 32 lanes -> 128), `maxlen` the longest item among the
-// groups of the warp (loop bound, warp-uniform).  Four steps are kept in flight (register ring e0..e3): the
-// load of step s+4 is issued right after step s is consumed.
-template <int MODE, uint32_t STEP>
-__device__ __forceinline__ void stream_item(const PanelSweepArgs& a, uint32_t start, uint32_t len, uint32_t maxlen,
-                                            uint32_t lane_off, const float* __restrict__ sm_new,
-                                            const float* __restrict__ sm_add, const float* __restrict__ sm_old, float s_add,
-                                            float s_old, float& g, float& h) {
-    constexpr bool WRITE = (MODE & kSub) || (MODE & kAdd);
-    const uint32_t pos = start + lane_off;
-    Step e0, e1, e2, e3;
-#define MF_LOAD(e, o) if ((o) + lane_off < len) e = load_step(a.idx16, a.val, pos + (o))
-#define MF_USE(e, o)                                                                        \
-    if ((o) + lane_off < len) {                                                             \
-        calc4<MODE>(e, sm_new, sm_add, sm_old, s_add, s_old, g, h);                         \
-        if (WRITE) __stcs(reinterpret_cast<float4*>(a.val + pos + (o)), e.v);               \
-    }
-    MF_LOAD(e0, 0u);
-    MF_LOAD(e1, STEP);
-    MF_LOAD(e2, 2u * STEP);
-    MF_LOAD(e3, 3u * STEP);
-#pragma unroll 1
-    for (uint32_t o = 0; o < maxlen; o += 4u * STEP) {
-        MF_USE(e0, o);
-        MF_LOAD(e0, o + 4u * STEP);
-        MF_USE(e1, o + STEP);
-        MF_LOAD(e1, o + 5u * STEP);
-        MF_USE(e2, o + 2u * STEP);
-        MF_LOAD(e2, o + 6u * STEP);
-        MF_USE(e3, o + 3u * STEP);
-        MF_LOAD(e3, o + 7u * STEP);
-    }
-#undef MF_LOAD
-#undef MF_USE
-}
-
 template <int MODE>
 __global__ void __launch_bounds__(1024, 1) k_panel_sweep(PanelSweepArgs a) {
     constexpr bool SUB = MODE & kSub, ADD = MODE & kAdd, SOLVE = MODE & kSolve, ADDSEP = MODE & kAddSep;
+    constexpr bool WRITE = SUB || ADD;
     extern __shared__ __align__(16) float smem[];
-    __shared__ unsigned s_ctr_long, s_ctr_short;
+    __shared__ unsigned s_ctr;
 
     const uint32_t PR = a.panel_rows;
     const uint32_t stride = PR + 8;  // 8 zeroed floats behind each panel: the padding slot idx16 == PR
@@ -135,7 +97,7 @@ __global__ void __launch_bounds__(1024, 1) k_panel_sweep(PanelSweepArgs a) {
         const uint32_t pend = a.panel_item_ptr[p + 1];
         const uint32_t pe = ie < pend ? ie : pend;
         if (pe > ib) {
-            __syncthreads();  // every warp is done with the previous panel and its counters
+            __syncthreads();  // every warp is done with the previous panel and counter
             const int64_t base = (int64_t)p * PR;
             const uint32_t cnt = (uint32_t)((a.gdim - base) < (int64_t)PR ? (a.gdim - base) : (int64_t)PR);
             for (uint32_t i = threadIdx.x; i < stride; i += blockDim.x) {
@@ -144,73 +106,68 @@ __global__ void __launch_bounds__(1024, 1) k_panel_sweep(PanelSweepArgs a) {
                 if (ADD && ADDSEP) sm_add[i] = in ? g_add[base + i] : 0.0f;
                 if (SUB) sm_old[i] = in ? a.g_old[base + i] : 0.0f;
             }
-            // items [ib, mid) are long (len >= long_len): one warp each; items [mid, pe) are short: four per warp
-            uint32_t mid = a.panel_mid[p];
-            mid = mid < ib ? ib : (mid > pe ? pe : mid);
-            if (threadIdx.x == 0) { s_ctr_long = ib; s_ctr_short = mid; }
+            if (threadIdx.x == 0) s_ctr = ib;
             __syncthreads();
 
-            // ---- long items: the whole warp streams one item, 128 entries per step (512-byte value loads)
-            {
-                uint32_t i = 0;
-                if (lane == 0) i = atomicAdd(&s_ctr_long, 1u);
-                i = __shfl_sync(kFull, i, 0);
-                uint4 d = make_uint4(0u, 0u, 0u, 0u);  // {start, len, seg, slot}
-                if (i < mid) d = __ldg(items + i);
-                while (i < mid) {
-                    uint32_t in = 0;
-                    if (lane == 0) in = atomicAdd(&s_ctr_long, 1u);
-                    in = __shfl_sync(kFull, in, 0);
-                    uint4 dn = make_uint4(0u, 0u, 0u, 0u);
-                    if (in < mid) dn = __ldg(items + in);  // next descriptor, one item ahead
-                    float s_add = 0.0f, s_old = 0.0f, g = 0.0f, h = 0.0f;
+            // Batches of four items (one per 8-lane group); neighbours in the list have (nearly) the same length.  The next batch's descriptors are
+            // fetched while this batch is processed.
+            uint32_t i0 = 0;
+            if (lane == 0) i0 = atomicAdd(&s_ctr, 4u);
+            i0 = __shfl_sync(kFull, i0, 0);
+            uint4 d = make_uint4(0u, 0u, 0u, 0u);  // {start, len, seg, slot}; len 0 = no item
+            if (i0 + grp < pe) d = __ldg(items + i0 + grp);
+            while (i0 < pe) {
+                uint32_t i0n = 0;
+                if (lane == 0) i0n = atomicAdd(&s_ctr, 4u);
+                i0n = __shfl_sync(kFull, i0n, 0);
+                uint4 dn = make_uint4(0u, 0u, 0u, 0u);
+                if (i0n + grp < pe) dn = __ldg(items + i0n + grp);
+
+                const uint32_t len = d.y;
+                const uint32_t lane_off = 4u * (uint32_t)sl;     // this lane's 4 entries inside a 32-entry step
+                const uint32_t pos = d.x + lane_off;
+                float s_add = 0.0f, s_old = 0.0f;
+                if (len != 0u) {
                     if (ADD) s_add = __ldg(a.s_add + a.seg_offset + d.z);
                     if (SUB) s_old = __ldg(a.s_old + a.seg_offset + d.z);
-                    stream_item<MODE, 128u>(a, d.x, d.y, d.y, 4u * (uint32_t)lane, sm_new, sm_add, sm_old, s_add, s_old, g, h);
-                    if (SOLVE) {
-#pragma unroll
-                        for (int o = 1; o < 32; o <<= 1) {
-                            g += __shfl_xor_sync(kFull, g, o);
-                            h += __shfl_xor_sync(kFull, h, o);
-                        }
-                        if (lane == 0) a.partials[d.w] = make_float2(g, h);
-                    }
-                    i = in;
-                    d = dn;
                 }
-            }
-            // ---- short items: batches of four, one item per 8-lane group, 32 entries per step and group; the
-            //      items are stored longest-first, so the four items of a batch have nearly the same length
-            {
-                uint32_t i0 = 0;
-                if (lane == 0) i0 = atomicAdd(&s_ctr_short, 4u);
-                i0 = __shfl_sync(kFull, i0, 0);
-                uint4 d = make_uint4(0u, 0u, 0u, 0u);  // len 0 = no item
-                if (i0 + grp < pe) d = __ldg(items + i0 + grp);
-                while (i0 < pe) {
-                    uint32_t i0n = 0;
-                    if (lane == 0) i0n = atomicAdd(&s_ctr_short, 4u);
-                    i0n = __shfl_sync(kFull, i0n, 0);
-                    uint4 dn = make_uint4(0u, 0u, 0u, 0u);
-                    if (i0n + grp < pe) dn = __ldg(items + i0n + grp);
-                    float s_add = 0.0f, s_old = 0.0f, g = 0.0f, h = 0.0f;
-                    if (d.y != 0u) {
-                        if (ADD) s_add = __ldg(a.s_add + a.seg_offset + d.z);
-                        if (SUB) s_old = __ldg(a.s_old + a.seg_offset + d.z);
-                    }
-                    const uint32_t maxlen = __reduce_max_sync(kFull, d.y);
-                    stream_item<MODE, 32u>(a, d.x, d.y, maxlen, 4u * (uint32_t)sl, sm_new, sm_add, sm_old, s_add, s_old, g, h);
-                    if (SOLVE) {
-#pragma unroll
-                        for (int o = 1; o < 8; o <<= 1) {
-                            g += __shfl_xor_sync(kFull, g, o);
-                            h += __shfl_xor_sync(kFull, h, o);
-                        }
-                        if (sl == 0 && d.y != 0u) a.partials[d.w] = make_float2(g, h);
-                    }
-                    i0 = i0n;
-                    d = dn;
+                const uint32_t maxlen = __reduce_max_sync(kFull, len);
+                float g = 0.0f, h = 0.0f;
+                // four 32-entry steps in flight per group (register ring e0..e3)
+                Step e0, e1, e2, e3;
+#define MF_LOAD(e, o) if ((o) + lane_off < len) e = load_step(a.idx16, a.val, pos + (o))
+#define MF_USE(e, o)                                                                        \
+    if ((o) + lane_off < len) {                                                             \
+        calc4<MODE>(e, sm_new, sm_add, sm_old, s_add, s_old, g, h);                         \
+        if (WRITE) __stcs(reinterpret_cast<float4*>(a.val + pos + (o)), e.v);               \
+    }
+                MF_LOAD(e0, 0u);
+                MF_LOAD(e1, 32u);
+                MF_LOAD(e2, 64u);
+                MF_LOAD(e3, 96u);
+#pragma unroll 1
+                for (uint32_t o = 0; o < maxlen; o += 128u) {
+                    MF_USE(e0, o);
+                    MF_LOAD(e0, o + 128u);
+                    MF_USE(e1, o + 32u);
+                    MF_LOAD(e1, o + 160u);
+                    MF_USE(e2, o + 64u);
+                    MF_LOAD(e2, o + 192u);
+                    MF_USE(e3, o + 96u);
+                    MF_LOAD(e3, o + 224u);
                 }
+#undef MF_LOAD
+#undef MF_USE
+                if (SOLVE) {
+#pragma unroll
+                    for (int o = 1; o < 8; o <<= 1) {
+                        g += __shfl_xor_sync(kFull, g, o);
+                        h += __shfl_xor_sync(kFull, h, o);
+                    }
+                    if (sl == 0 && len != 0u) a.partials[d.w] = make_float2(g, h);
+                }
+                i0 = i0n;
+                d = dn;
             }
         }
         ib = pe;

@@ -18,7 +18,6 @@ struct PanelSweepArgs {
     const WorkItem* items;
     const uint32_t* cta_item_ptr;
     const uint32_t* panel_item_ptr;
-    const uint32_t* panel_mid;  // [npanels] first short item (len < long_len) of each panel
     int npanels;
     uint32_t panel_rows;
     int64_t gdim;

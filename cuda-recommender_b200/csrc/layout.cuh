@@ -19,8 +19,9 @@
 // (g, h) to a fixed slot, slots of one segment are contiguous and ordered (panel, chunk), and a
 // finalize pass adds them in that order — the reduction tree of a segment depends only on its own
 // entries and the global panel grid, never on scheduling or on the multi-GPU shard it sits in.
-// Inside a panel the work items are listed longest-first (degree-binned order), so that a batch of
-// consecutive items has nearly uniform length.
+// Inside a panel the work items are ranked longest-first (degree bins) and dealt round-robin into 148
+// lanes stored back to back (prep.cu): four consecutive items have nearly the same length, and every
+// contiguous range of the list holds the same mix of lengths.
 #pragma once
 #include "common.cuh"
 
@@ -56,15 +57,13 @@ struct Side {
     float2* partials = nullptr;       // [nslots]
     uint32_t* cta_item_ptr = nullptr; // [ncta+1] equal-cost contiguous item ranges
     uint32_t* panel_item_ptr = nullptr; // [npanels+1]
-    uint32_t* panel_mid = nullptr;      // [npanels] first item of the panel with len < long_len (items are longest-first)
-    int long_len = 0;                   // items at least this long are streamed by a whole warp
     int ncta = 0;
     bool sorted = true;
 };
 
 int side_free(Side& s);
 // raw device arrays must be set (ptr, idx, val, nseg, gdim, nnz); builds everything else.
-int side_build_panels(Side& s, int panel_rows, int chunk, int long_len, int ncta, cudaStream_t st);
+int side_build_panels(Side& s, int panel_rows, int chunk, int ncta, cudaStream_t st);
 // dst_raw[nnz] <- current panel values in the caller's order; and the inverse
 int side_panel_to_raw(const Side& s, float* dst_raw, cudaStream_t st);
 int side_raw_to_panel(Side& s, const float* src_raw, cudaStream_t st);

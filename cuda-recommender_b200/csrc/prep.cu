@@ -103,9 +103,20 @@ __global__ void k_fill(int64_t nseg, int npanels, uint32_t panel_rows, uint32_t 
     }
 }
 
-// Degree-binned order: inside every panel the work items are re-ordered longest-first (bin = len/8,
-// counting sort with per-bin cursors).  The order inside one bin is arbitrary — it only affects which
-// warp picks an item up, never a result (every item writes its own slot).
+// Degree-binned order: inside every panel the work items are ranked longest-first (bin = len/8, counting
+// sort with per-bin cursors; the order inside one bin is arbitrary) and then DEALT round-robin into
+// kDealLanes lanes that are stored one after the other: item of rank k goes to lane k % kDealLanes.  So
+//   * consecutive items of a lane are neighbours-at-distance-kDealLanes in the length ranking: the four
+//     items a warp processes together have nearly the same length;
+//   * every contiguous stretch of the list — in particular every CTA's equal-cost range — holds the same
+//     mix of long and short items, so errors of the cost model cancel instead of piling up on some CTAs.
+// The order only affects which warp picks an item up, never a result (every item writes its own slot).
+constexpr uint32_t kDealLanes = 148;
+__device__ __forceinline__ uint32_t deal_position(uint32_t k, uint32_t n) {
+    const uint32_t lane = k % kDealLanes, r = k / kDealLanes;
+    const uint32_t q = n / kDealLanes, rem = n % kDealLanes;
+    return lane * q + (lane < rem ? lane : rem) + r;
+}
 __device__ __forceinline__ int panel_of_item(const uint32_t* __restrict__ panel_item_ptr, int npanels, uint32_t i) {
     int lo = 0, hi = npanels;  // last p with panel_item_ptr[p] <= i
     while (hi - lo > 1) {
@@ -129,19 +140,11 @@ __global__ void k_item_bin_scatter(int64_t nitems, int npanels, uint32_t nbins, 
     const WorkItem w = items[i];
     const int p = panel_of_item(panel_item_ptr, npanels, (uint32_t)i);
     const uint32_t b = (uint32_t)p * nbins + (nbins - 1u - w.len / kPad);
-    const uint32_t dst = bin_ptr[b] + atomicAdd(&bin_cursor[b], 1u);
+    const uint32_t rank = bin_ptr[b] + atomicAdd(&bin_cursor[b], 1u);  // longest-first rank, global index
+    const uint32_t pbeg = panel_item_ptr[p];
+    const uint32_t dst = pbeg + deal_position(rank - pbeg, panel_item_ptr[p + 1] - pbeg);
     sorted[dst] = w;
     cost[dst] = w.len / kPad + kCost0;
-}
-
-// first short item of every panel: bins are ordered longest-first, bin b holds len = (nbins-1-b)*8
-__global__ void k_panel_mid(int npanels, uint32_t nbins, uint32_t long_len, const uint32_t* __restrict__ bin_ptr,
-                            uint32_t* __restrict__ panel_mid) {
-    int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= npanels) return;
-    const uint32_t q = long_len / kPad;                     // len >= long_len  <=>  len/8 >= q  <=>  b <= nbins-1-q
-    const uint32_t first_short = q >= nbins ? 0u : nbins - q;  // first bin with len < long_len
-    panel_mid[p] = bin_ptr[(uint32_t)p * nbins + (first_short < nbins ? first_short : nbins)];
 }
 
 __global__ void k_panel_item_ptr(int64_t nseg, int npanels, const uint32_t* __restrict__ item_ptr,
@@ -241,7 +244,7 @@ inline unsigned grid_for(int64_t n, int block) { return (unsigned)((n + block - 
 
 int side_free(Side& s) {
     void* ptrs[] = {s.ptr, s.idx, s.val, s.piece_ptr, s.piece_first, s.item_ptr, s.idx16, s.pval, s.items,
-                    s.slot_ptr, s.partials, s.cta_item_ptr, s.panel_item_ptr, s.panel_mid};
+                    s.slot_ptr, s.partials, s.cta_item_ptr, s.panel_item_ptr};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     s = Side();
@@ -264,13 +267,12 @@ int side_check_sorted(const Side& s, bool* sorted, cudaStream_t st) {
     return MF_OK;
 }
 
-int side_build_panels(Side& s, int panel_rows, int chunk, int long_len, int ncta, cudaStream_t st) {
+int side_build_panels(Side& s, int panel_rows, int chunk, int ncta, cudaStream_t st) {
     MF_REQUIRE(panel_rows > 0 && panel_rows <= 65528 && panel_rows % 8 == 0, "panel_rows must be a multiple of 8 in (0, 65528]");
     MF_REQUIRE(chunk >= 8 && chunk % 8 == 0, "chunk must be a positive multiple of 8");
     MF_REQUIRE(ncta > 0, "ncta must be positive");
     s.panel_rows = panel_rows;
     s.chunk = chunk;
-    s.long_len = long_len > 0 ? (long_len + kPad - 1) / kPad * kPad : chunk + kPad;
     s.ncta = ncta;
     s.npanels = (int)((s.gdim + panel_rows - 1) / panel_rows);
     if (s.npanels < 1) s.npanels = 1;
@@ -286,7 +288,6 @@ int side_build_panels(Side& s, int panel_rows, int chunk, int long_len, int ncta
     MF_TRY(dev_alloc(&seg_items, (size_t)s.nseg));
     MF_TRY(dev_alloc(&s.slot_ptr, (size_t)s.nseg + 1));
     MF_TRY(dev_alloc(&s.panel_item_ptr, (size_t)s.npanels + 1));
-    MF_TRY(dev_alloc(&s.panel_mid, (size_t)s.npanels));
     MF_TRY(dev_alloc(&s.cta_item_ptr, (size_t)ncta + 1));
     size_t tmp_n = scan_tmp_elems((size_t)(Q > s.nseg ? Q : s.nseg));
     MF_TRY(dev_alloc(&tmp, tmp_n));
@@ -328,7 +329,6 @@ int side_build_panels(Side& s, int panel_rows, int chunk, int long_len, int ncta
     k_panel_item_ptr<<<grid_for(s.npanels + 1, 128), 128, 0, st>>>(s.nseg, s.npanels, s.item_ptr, s.panel_item_ptr);
     MF_CUDA(cudaGetLastError());
     // longest-first inside each panel
-    MF_CUDA(cudaMemsetAsync(s.panel_mid, 0, sizeof(uint32_t) * (size_t)s.npanels, st));
     if (s.nitems > 0) {
         const uint32_t nbins = (uint32_t)chunk / kPad + 1u;
         const size_t nb = (size_t)s.npanels * nbins;
@@ -345,8 +345,6 @@ int side_build_panels(Side& s, int panel_rows, int chunk, int long_len, int ncta
         MF_CUDA(cudaMemsetAsync(bin_count, 0, sizeof(uint32_t) * nb, st));
         k_item_bin_scatter<<<grid_for(s.nitems, 256), 256, 0, st>>>(s.nitems, s.npanels, nbins, s.panel_item_ptr, s.items, bin_ptr,
                                                                    bin_count, sorted, cost);
-        MF_CUDA(cudaGetLastError());
-        k_panel_mid<<<grid_for(s.npanels, 128), 128, 0, st>>>(s.npanels, nbins, (uint32_t)s.long_len, bin_ptr, s.panel_mid);
         MF_CUDA(cudaGetLastError());
         MF_CUDA(cudaStreamSynchronize(st));
         cudaFree(s.items);

@@ -144,7 +144,7 @@ int run_sweep(mf_session* s, Side& sd, int mode, const SweepVectors& v, float* o
     if (s->panel) {
         PanelSweepArgs a;
         a.idx16 = sd.idx16; a.val = sd.pval; a.items = sd.items;
-        a.cta_item_ptr = sd.cta_item_ptr; a.panel_item_ptr = sd.panel_item_ptr; a.panel_mid = sd.panel_mid;
+        a.cta_item_ptr = sd.cta_item_ptr; a.panel_item_ptr = sd.panel_item_ptr;
         a.npanels = sd.npanels; a.panel_rows = (uint32_t)sd.panel_rows; a.gdim = sd.gdim;
         a.seg_offset = sd.seg_offset;
         a.g_new = v.g_new; a.g_add = v.g_add; a.g_old = v.g_old; a.s_add = v.s_add; a.s_old = v.s_old;
@@ -367,9 +367,8 @@ int create_impl(const mf_ratings* R, const mf_testset* T, const mf_params* param
             if (params->panel_rows > 0) { cap_c = std::min(cap_c, params->panel_rows / 8 * 8); cap_r = std::min(cap_r, params->panel_rows / 8 * 8); }
             else cap_c = std::min(cap_c, 24576);
             const int chunk = params->chunk > 0 ? std::max(8, params->chunk / 8 * 8) : 2048;
-            const int long_len = params->long_len > 0 ? params->long_len : 512;
-            if ((rc = side_build_panels(s->csc, choose_panel_rows(s->csc.gdim, std::max(cap_c, 8)), chunk, long_len, s->sm_count, s->st)) != MF_OK) return fail(rc);
-            if ((rc = side_build_panels(s->csr, choose_panel_rows(s->csr.gdim, std::max(cap_r, 8)), chunk, long_len, s->sm_count, s->st)) != MF_OK) return fail(rc);
+            if ((rc = side_build_panels(s->csc, choose_panel_rows(s->csc.gdim, std::max(cap_c, 8)), chunk, s->sm_count, s->st)) != MF_OK) return fail(rc);
+            if ((rc = side_build_panels(s->csr, choose_panel_rows(s->csr.gdim, std::max(cap_r, 8)), chunk, s->sm_count, s->st)) != MF_OK) return fail(rc);
             // the caller-order index/value arrays are no longer needed: the residual lives in the panel arrays
             cudaFree(s->csc.idx); s->csc.idx = nullptr; cudaFree(s->csc.val); s->csc.val = nullptr;
             cudaFree(s->csr.idx); s->csr.idx = nullptr; cudaFree(s->csr.val); s->csr.val = nullptr;

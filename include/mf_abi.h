@@ -94,8 +94,7 @@ typedef struct mf_params {
     int32_t chunk;             /* 0 = default (2048); max rating entries per work item */
     int32_t nmf_project;       /* 1: clamp solved coordinates at 0 (extension; the reference never does) */
     int32_t no_launch_timing;  /* 1: skip the per-launch CUDA events (mf_kernel_times stays zero) */
-    int32_t long_len;          /* 0 = default (512); work items at least this long are streamed by a whole warp */
-    int32_t reserved[7];
+    int32_t reserved[8];
 } mf_params;
 
 /* One line of the reference's per-iteration report (CCD_CUDA.cu:405, ALS_CUDA.cu:360). */

@@ -38,7 +38,7 @@ def test_reference_main_runs_on_our_gpu_path(gpu, datagen, data_factory, tmp_pat
     assert len(checks) == 2, out
     for verdict, pct in checks:
         assert verdict == "PASS!" or float(pct) < 2.0, out
-    finals = re.findall(r"Test RMSE = ([\d.]+)", out)
+    finals = re.findall(r"Test RMSE = (\d+\.\d+)", out)
     assert len(finals) == 2 and abs(float(finals[0]) - float(finals[1])) <= 1e-4
 
 
