@@ -16,7 +16,7 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmfb200.so")
+LIB_PATH = os.environ.get("MF_LIB") or os.path.join(_HERE, "libmfb200.so")  # MF_LIB: an experimental build of the same library
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "mf_abi.h")
 
 MF_OK = 0

@@ -36,8 +36,15 @@ struct Step {
 };
 __device__ __forceinline__ Step load_step(const uint16_t* __restrict__ idx16, const float* __restrict__ val, uint32_t pos) {
     Step e;
+#if defined(MF_STREAM_NO_ALLOCATE)
+    // streaming loads that do not allocate in L1 (the shared-memory panels leave little L1 behind)
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(e.i.x), "=r"(e.i.y) : "l"(idx16 + pos));
+    asm volatile("ld.global.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(e.v.x), "=f"(e.v.y), "=f"(e.v.z), "=f"(e.v.w) : "l"(val + pos));
+#else
     e.i = __ldcs(reinterpret_cast<const uint2*>(idx16 + pos));
     e.v = __ldcs(reinterpret_cast<const float4*>(val + pos));
+#endif
     return e;
 }
 

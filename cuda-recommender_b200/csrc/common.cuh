@@ -46,6 +46,17 @@ static inline int dev_alloc(T** p, size_t n) {
     return MF_OK;
 }
 
+// stream-ordered scratch (cudaMallocAsync pool): for temporaries that live on one stream only
+template <typename T>
+static inline int tmp_alloc(T** p, size_t n, cudaStream_t st) {
+    *p = nullptr;
+    MF_CUDA(cudaMallocAsync((void**)p, (n > 0 ? n : 1) * sizeof(T), st));
+    return MF_OK;
+}
+static inline void tmp_free(void* p, cudaStream_t st) {
+    if (p) cudaFreeAsync(p, st);
+}
+
 static inline uint32_t ceil_div_u32(uint64_t a, uint64_t b) { return (uint32_t)((a + b - 1) / b); }
 
 // exclusive scan of n uint32 values into out[0..n] (out[n] = total); in and out may alias only if

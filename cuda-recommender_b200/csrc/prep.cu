@@ -280,17 +280,17 @@ int side_build_panels(Side& s, int panel_rows, int chunk, int ncta, cudaStream_t
     MF_REQUIRE(Q < (int64_t)1 << 31, "too many (panel, segment) pieces: raise panel_rows");
 
     uint32_t *padded = nullptr, *nitem = nullptr, *seg_items = nullptr, *tmp = nullptr, *cost = nullptr, *cost_prefix = nullptr;
-    MF_TRY(dev_alloc(&padded, (size_t)Q));
-    MF_TRY(dev_alloc(&nitem, (size_t)Q));
+    MF_TRY(tmp_alloc(&padded, (size_t)Q, st));
+    MF_TRY(tmp_alloc(&nitem, (size_t)Q, st));
     MF_TRY(dev_alloc(&s.piece_first, (size_t)Q));
     MF_TRY(dev_alloc(&s.piece_ptr, (size_t)Q + 1));
     MF_TRY(dev_alloc(&s.item_ptr, (size_t)Q + 1));
-    MF_TRY(dev_alloc(&seg_items, (size_t)s.nseg));
+    MF_TRY(tmp_alloc(&seg_items, (size_t)s.nseg, st));
     MF_TRY(dev_alloc(&s.slot_ptr, (size_t)s.nseg + 1));
     MF_TRY(dev_alloc(&s.panel_item_ptr, (size_t)s.npanels + 1));
     MF_TRY(dev_alloc(&s.cta_item_ptr, (size_t)ncta + 1));
     size_t tmp_n = scan_tmp_elems((size_t)(Q > s.nseg ? Q : s.nseg));
-    MF_TRY(dev_alloc(&tmp, tmp_n));
+    MF_TRY(tmp_alloc(&tmp, tmp_n, st));
 
     if (Q > 0)
         k_piece_count<<<grid_for(Q, 256), 256, 0, st>>>(s.nseg, s.npanels, (uint32_t)panel_rows, (uint32_t)chunk, s.ptr,
@@ -317,8 +317,8 @@ int side_build_panels(Side& s, int panel_rows, int chunk, int ncta, cudaStream_t
     MF_TRY(dev_alloc(&s.pval, (size_t)s.npad + 8));
     MF_TRY(dev_alloc(&s.items, (size_t)s.nitems));
     MF_TRY(dev_alloc(&s.partials, (size_t)s.nslots));
-    MF_TRY(dev_alloc(&cost, (size_t)s.nitems));
-    MF_TRY(dev_alloc(&cost_prefix, (size_t)s.nitems + 1));
+    MF_TRY(tmp_alloc(&cost, (size_t)s.nitems, st));
+    MF_TRY(tmp_alloc(&cost_prefix, (size_t)s.nitems + 1, st));
     if (Q > 0) {
         int64_t warps = Q < 148 * 64 * 8 ? Q : 148 * 64 * 8;
         k_fill<<<grid_for(warps * 32, 256), 256, 0, st>>>(s.nseg, s.npanels, (uint32_t)panel_rows, (uint32_t)chunk, s.ptr,
@@ -334,9 +334,9 @@ int side_build_panels(Side& s, int panel_rows, int chunk, int ncta, cudaStream_t
         const size_t nb = (size_t)s.npanels * nbins;
         uint32_t *bin_count = nullptr, *bin_ptr = nullptr, *tmp2 = nullptr;
         WorkItem* sorted = nullptr;
-        MF_TRY(dev_alloc(&bin_count, nb));
-        MF_TRY(dev_alloc(&bin_ptr, nb + 1));
-        MF_TRY(dev_alloc(&tmp2, scan_tmp_elems(nb)));
+        MF_TRY(tmp_alloc(&bin_count, nb, st));
+        MF_TRY(tmp_alloc(&bin_ptr, nb + 1, st));
+        MF_TRY(tmp_alloc(&tmp2, scan_tmp_elems(nb), st));
         MF_TRY(dev_alloc(&sorted, (size_t)s.nitems));
         MF_CUDA(cudaMemsetAsync(bin_count, 0, sizeof(uint32_t) * nb, st));
         k_item_bin_count<<<grid_for(s.nitems, 256), 256, 0, st>>>(s.nitems, s.npanels, nbins, s.panel_item_ptr, s.items, bin_count);
@@ -349,13 +349,13 @@ int side_build_panels(Side& s, int panel_rows, int chunk, int ncta, cudaStream_t
         MF_CUDA(cudaStreamSynchronize(st));
         cudaFree(s.items);
         s.items = sorted;
-        cudaFree(bin_count); cudaFree(bin_ptr); cudaFree(tmp2);
+        tmp_free(bin_count, st); tmp_free(bin_ptr, st); tmp_free(tmp2, st);
     }
     MF_TRY(exclusive_scan_u32(cost, cost_prefix, (size_t)s.nitems, tmp, st));
     k_cta_ranges<<<grid_for(ncta + 1, 128), 128, 0, st>>>(ncta, s.nitems, cost_prefix, s.cta_item_ptr);
     MF_CUDA(cudaGetLastError());
     MF_CUDA(cudaStreamSynchronize(st));
-    cudaFree(padded); cudaFree(nitem); cudaFree(seg_items); cudaFree(tmp); cudaFree(cost); cudaFree(cost_prefix);
+    tmp_free(padded, st); tmp_free(nitem, st); tmp_free(seg_items, st); tmp_free(tmp, st); tmp_free(cost, st); tmp_free(cost_prefix, st);
     return MF_OK;
 }
 

@@ -329,9 +329,14 @@ int create_impl(const mf_ratings* R, const mf_testset* T, const mf_params* param
     int rc = MF_OK;
     auto fail = [&](int code) { mf_session_destroy(s); return code; };
 
-    cudaDeviceProp prop;
-    if (cudaGetDeviceProperties(&prop, s->device) != cudaSuccess) { set_error("cudaGetDeviceProperties failed"); return fail(MF_ERR_CUDA); }
-    s->sm_count = prop.multiProcessorCount;
+    if (cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, s->device) != cudaSuccess) { set_error("cudaDeviceGetAttribute failed"); return fail(MF_ERR_CUDA); }
+    {   // keep freed scratch in the stream-ordered pool instead of returning it to the driver
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, s->device) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
     if (cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking) != cudaSuccess) { set_error("cudaStreamCreate failed"); return fail(MF_ERR_CUDA); }
     cudaEventCreate(&s->ev_a); cudaEventCreate(&s->ev_b); cudaEventCreate(&s->ev_c);
     s->timer.st = s->st;
@@ -360,6 +365,7 @@ int create_impl(const mf_ratings* R, const mf_testset* T, const mf_params* param
             if ((rc = side_check_sorted(s->csr, &ok_r, s->st)) != MF_OK) return fail(rc);
             if ((rc = side_check_sorted(s->csc, &ok_c, s->st)) != MF_OK) return fail(rc);
             if (!ok_r || !ok_c) s->panel = false;  // the panel cut needs ascending indices inside a segment
+            trace.mark("  sortedness check");
         }
         if (s->panel) {
             // shared-memory vectors a sweep may need: CSC side 2 (u_new, u_old); CSR side 3 (v_new, v_add, v_old)
@@ -369,6 +375,7 @@ int create_impl(const mf_ratings* R, const mf_testset* T, const mf_params* param
             const int chunk = params->chunk > 0 ? std::max(8, params->chunk / 8 * 8) : 2048;
             if ((rc = side_build_panels(s->csc, choose_panel_rows(s->csc.gdim, std::max(cap_c, 8)), chunk, s->sm_count, s->st)) != MF_OK) return fail(rc);
             if ((rc = side_build_panels(s->csr, choose_panel_rows(s->csr.gdim, std::max(cap_r, 8)), chunk, s->sm_count, s->st)) != MF_OK) return fail(rc);
+            trace.mark("  build both panel layouts");
             // the caller-order index/value arrays are no longer needed: the residual lives in the panel arrays
             cudaFree(s->csc.idx); s->csc.idx = nullptr; cudaFree(s->csc.val); s->csc.val = nullptr;
             cudaFree(s->csr.idx); s->csr.idx = nullptr; cudaFree(s->csr.val); s->csr.val = nullptr;
