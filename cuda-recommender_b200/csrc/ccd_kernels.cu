@@ -36,6 +36,13 @@ struct Step {
 };
 __device__ __forceinline__ Step load_step(const uint16_t* __restrict__ idx16, const float* __restrict__ val, uint32_t pos) {
     Step e;
+#if defined(MF_EXP_NOLOAD)
+    // timing experiment only (results are meaningless): no global loads, pseudo-random panel indices
+    const uint32_t r0 = (pos * 2654435761u) >> 17, r1 = pos * 40503u + 12345u;
+    e.i = make_uint2((r0 & 0x7ffcu) | ((r1 & 0x7ffcu) << 16), ((r0 >> 3) & 0x7ffcu) | (((r1 * 7u) & 0x7ffcu) << 16));
+    e.v = make_float4(1.f, 2.f, 3.f, 4.f);
+    return e;
+#endif
 #if defined(MF_STREAM_NO_ALLOCATE)
     // streaming loads that do not allocate in L1 (the shared-memory panels leave little L1 behind)
     asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(e.i.x), "=r"(e.i.y) : "l"(idx16 + pos));
@@ -48,19 +55,30 @@ __device__ __forceinline__ Step load_step(const uint16_t* __restrict__ idx16, co
     return e;
 }
 
+// idx16 holds the panel-local index already multiplied by 4 (the byte offset into the shared-memory
+// panel, layout.cuh), so each gather address costs one instruction: mask or shift, then LDS.
+__device__ __forceinline__ float panel_at(const float* __restrict__ sm, uint32_t byte_off) {
+    return *reinterpret_cast<const float*>(reinterpret_cast<const char*>(sm) + byte_off);
+}
+
 template <int MODE>
 __device__ __forceinline__ void calc4(Step& e, const float* __restrict__ sm_new, const float* __restrict__ sm_add,
                                       const float* __restrict__ sm_old, float s_add, float s_old, float& g, float& h) {
     constexpr bool SUB = MODE & kSub, ADD = MODE & kAdd, SOLVE = MODE & kSolve;
     float v[4] = {e.v.x, e.v.y, e.v.z, e.v.w};
+#if defined(MF_EXP_NOGATHER)
+    // timing experiment only: every lane reads the same shared-memory word (broadcast, no bank conflicts)
+    const uint32_t ix[4] = {e.i.x & 4u, (e.i.x >> 16) & 4u, e.i.y & 4u, (e.i.y >> 16) & 4u};
+#else
     const uint32_t ix[4] = {e.i.x & 0xffffu, e.i.x >> 16, e.i.y & 0xffffu, e.i.y >> 16};
+#endif
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         float x = v[j];
-        if (SUB) x = __fsub_rn(x, __fmul_rn(sm_old[ix[j]], s_old));
-        if (ADD) x = __fadd_rn(x, __fmul_rn(sm_add[ix[j]], s_add));
+        if (SUB) x = __fsub_rn(x, __fmul_rn(panel_at(sm_old, ix[j]), s_old));
+        if (ADD) x = __fadd_rn(x, __fmul_rn(panel_at(sm_add, ix[j]), s_add));
         if (SOLVE) {
-            const float un = sm_new[ix[j]];
+            const float un = panel_at(sm_new, ix[j]);
             g = fmaf(un, x, g);
             h = fmaf(un, un, h);
         }
@@ -69,10 +87,59 @@ __device__ __forceinline__ void calc4(Step& e, const float* __restrict__ sm_new,
     if (SUB || ADD) e.v = make_float4(v[0], v[1], v[2], v[3]);
 }
 
+// Streams the (up to four) items of a batch through the 8-lane groups of a warp: a lane owns 4 consecutive
+// entries of its group's 32-entry step.  Four steps are in flight per group (register ring e0..e3): the load
+// of step s+4 is issued right after step s is consumed.  While every group still has 128 entries ahead
+// (o + 128 <= minlen) the steps are consumed without per-lane checks; the ragged end runs predicated.
+template <int MODE>
+__device__ __forceinline__ void stream_batch(const PanelSweepArgs& a, uint32_t pos, uint32_t len, uint32_t minlen,
+                                             uint32_t maxlen, uint32_t lane_off, const float* __restrict__ sm_new,
+                                             const float* __restrict__ sm_add, const float* __restrict__ sm_old, float s_add,
+                                             float s_old, float& g, float& h) {
+    constexpr bool WRITE = (MODE & kSub) || (MODE & kAdd);
+    Step e0, e1, e2, e3;
+#define MF_LOAD(e, o) if ((o) + lane_off < len) e = load_step(a.idx16, a.val, pos + (o))
+#define MF_USE_ALL(e, o)                                                                    \
+    {                                                                                       \
+        calc4<MODE>(e, sm_new, sm_add, sm_old, s_add, s_old, g, h);                         \
+        if (WRITE) __stcs(reinterpret_cast<float4*>(a.val + pos + (o)), e.v);               \
+    }
+#define MF_USE(e, o) if ((o) + lane_off < len) MF_USE_ALL(e, o)
+    MF_LOAD(e0, 0u);
+    MF_LOAD(e1, 32u);
+    MF_LOAD(e2, 64u);
+    MF_LOAD(e3, 96u);
+    uint32_t o = 0;
+#pragma unroll 1
+    for (; o + 128u <= minlen; o += 128u) {
+        MF_USE_ALL(e0, o);
+        MF_LOAD(e0, o + 128u);
+        MF_USE_ALL(e1, o + 32u);
+        MF_LOAD(e1, o + 160u);
+        MF_USE_ALL(e2, o + 64u);
+        MF_LOAD(e2, o + 192u);
+        MF_USE_ALL(e3, o + 96u);
+        MF_LOAD(e3, o + 224u);
+    }
+#pragma unroll 1
+    for (; o < maxlen; o += 128u) {
+        MF_USE(e0, o);
+        MF_LOAD(e0, o + 128u);
+        MF_USE(e1, o + 32u);
+        MF_LOAD(e1, o + 160u);
+        MF_USE(e2, o + 64u);
+        MF_LOAD(e2, o + 192u);
+        MF_USE(e3, o + 96u);
+        MF_LOAD(e3, o + 224u);
+    }
+#undef MF_LOAD
+#undef MF_USE
+#undef MF_USE_ALL
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(1024, 1) k_panel_sweep(PanelSweepArgs a) {
     constexpr bool SUB = MODE & kSub, ADD = MODE & kAdd, SOLVE = MODE & kSolve, ADDSEP = MODE & kAddSep;
-    constexpr bool WRITE = SUB || ADD;
     extern __shared__ __align__(16) float smem[];
     __shared__ unsigned s_ctr;
 
@@ -132,39 +199,15 @@ __global__ void __launch_bounds__(1024, 1) k_panel_sweep(PanelSweepArgs a) {
 
                 const uint32_t len = d.y;
                 const uint32_t lane_off = 4u * (uint32_t)sl;     // this lane's 4 entries inside a 32-entry step
-                const uint32_t pos = d.x + lane_off;
                 float s_add = 0.0f, s_old = 0.0f;
                 if (len != 0u) {
                     if (ADD) s_add = __ldg(a.s_add + a.seg_offset + d.z);
                     if (SUB) s_old = __ldg(a.s_old + a.seg_offset + d.z);
                 }
                 const uint32_t maxlen = __reduce_max_sync(kFull, len);
+                const uint32_t minlen = __reduce_min_sync(kFull, len);
                 float g = 0.0f, h = 0.0f;
-                // four 32-entry steps in flight per group (register ring e0..e3)
-                Step e0, e1, e2, e3;
-#define MF_LOAD(e, o) if ((o) + lane_off < len) e = load_step(a.idx16, a.val, pos + (o))
-#define MF_USE(e, o)                                                                        \
-    if ((o) + lane_off < len) {                                                             \
-        calc4<MODE>(e, sm_new, sm_add, sm_old, s_add, s_old, g, h);                         \
-        if (WRITE) __stcs(reinterpret_cast<float4*>(a.val + pos + (o)), e.v);               \
-    }
-                MF_LOAD(e0, 0u);
-                MF_LOAD(e1, 32u);
-                MF_LOAD(e2, 64u);
-                MF_LOAD(e3, 96u);
-#pragma unroll 1
-                for (uint32_t o = 0; o < maxlen; o += 128u) {
-                    MF_USE(e0, o);
-                    MF_LOAD(e0, o + 128u);
-                    MF_USE(e1, o + 32u);
-                    MF_LOAD(e1, o + 160u);
-                    MF_USE(e2, o + 64u);
-                    MF_LOAD(e2, o + 192u);
-                    MF_USE(e3, o + 96u);
-                    MF_LOAD(e3, o + 224u);
-                }
-#undef MF_LOAD
-#undef MF_USE
+                stream_batch<MODE>(a, d.x + lane_off, len, minlen, maxlen, lane_off, sm_new, sm_add, sm_old, s_add, s_old, g, h);
                 if (SOLVE) {
 #pragma unroll
                     for (int o = 1; o < 8; o <<= 1) {

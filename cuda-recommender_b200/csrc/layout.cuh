@@ -12,9 +12,10 @@
 // `panel_rows` factor entries so that one panel of the factor vector sits in shared memory while
 // the ratings that reference it stream past.  Every segment is cut at the panel boundaries into
 // pieces (panel p, segment s); storage is panel-major, pieces in segment order inside a panel, each
-// piece padded to a multiple of 8 entries (16-byte idx vectors, 32-byte val vectors).  Indices are
-// stored panel-local in 16 bits; padding entries carry idx16 = panel_rows (a zeroed shared-memory
-// slot) and val = 0, so they add nothing to g, h or the residual.
+// piece padded to a multiple of 8 entries.  Indices are stored panel-local in 16 bits, pre-multiplied
+// by 4 (the byte offset of the factor entry inside the staged panel, so panel_rows <= 16376); padding
+// entries carry the offset of a zeroed shared-memory slot (index panel_rows) and val = 0, so they add
+// nothing to g, h or the residual.
 // Pieces are cut into work items of at most `chunk` entries; item j of segment s writes its partial
 // (g, h) to a fixed slot, slots of one segment are contiguous and ordered (panel, chunk), and a
 // finalize pass adds them in that order — the reduction tree of a segment depends only on its own

@@ -77,7 +77,8 @@ __global__ void k_fill(int64_t nseg, int npanels, uint32_t panel_rows, uint32_t 
         uint32_t base = (uint32_t)p * panel_rows;
         for (uint32_t e = lane; e < pd; e += 32) {
             bool real = e < cnt;
-            idx16[dst0 + e] = real ? (uint16_t)(idx[src0 + e] - base) : (uint16_t)panel_rows;
+            // stored pre-multiplied by 4: the byte offset of the factor entry inside the shared-memory panel
+            idx16[dst0 + e] = (uint16_t)((real ? idx[src0 + e] - base : panel_rows) << 2);
             pval[dst0 + e] = real ? val[src0 + e] : 0.0f;
         }
         // slots of segment s are ordered (panel, chunk): count the items of the earlier panels
@@ -268,7 +269,7 @@ int side_check_sorted(const Side& s, bool* sorted, cudaStream_t st) {
 }
 
 int side_build_panels(Side& s, int panel_rows, int chunk, int ncta, cudaStream_t st) {
-    MF_REQUIRE(panel_rows > 0 && panel_rows <= 65528 && panel_rows % 8 == 0, "panel_rows must be a multiple of 8 in (0, 65528]");
+    MF_REQUIRE(panel_rows > 0 && panel_rows <= 16376 && panel_rows % 8 == 0, "panel_rows must be a multiple of 8 in (0, 16376]");
     MF_REQUIRE(chunk >= 8 && chunk % 8 == 0, "chunk must be a positive multiple of 8");
     MF_REQUIRE(ncta > 0, "ncta must be positive");
     s.panel_rows = panel_rows;

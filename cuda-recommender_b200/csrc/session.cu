@@ -368,11 +368,15 @@ int create_impl(const mf_ratings* R, const mf_testset* T, const mf_params* param
             trace.mark("  sortedness check");
         }
         if (s->panel) {
-            // shared-memory vectors a sweep may need: CSC side 2 (u_new, u_old); CSR side 3 (v_new, v_add, v_old)
-            int cap_c = panel_cap(2), cap_r = panel_cap(3);
-            if (params->panel_rows > 0) { cap_c = std::min(cap_c, params->panel_rows / 8 * 8); cap_r = std::min(cap_r, params->panel_rows / 8 * 8); }
-            else cap_c = std::min(cap_c, 24576);
-            const int chunk = params->chunk > 0 ? std::max(8, params->chunk / 8 * 8) : 2048;
+            // Panel size.  Shared memory a sweep needs: CSC side up to 2 vectors (u_new, u_old), CSR side up to 3
+            // (v_new, v_add, v_old).  Measured (profiles/README.md): panels that fill shared memory leave the SM
+            // almost no L1 for the rating streams and the updating sweeps slow down by 30-60 %; 12288 entries
+            // (48 KB per vector) is the sweet spot on B200.  Hard cap 16376: idx16 stores index*4.
+            int cap_c = std::min(panel_cap(2), 16376), cap_r = std::min(panel_cap(3), 16376);
+            const int want = params->panel_rows > 0 ? params->panel_rows / 8 * 8 : 12288;
+            cap_c = std::min(cap_c, want);
+            cap_r = std::min(cap_r, want);
+            const int chunk = params->chunk > 0 ? std::max(8, params->chunk / 8 * 8) : 512;
             if ((rc = side_build_panels(s->csc, choose_panel_rows(s->csc.gdim, std::max(cap_c, 8)), chunk, s->sm_count, s->st)) != MF_OK) return fail(rc);
             if ((rc = side_build_panels(s->csr, choose_panel_rows(s->csr.gdim, std::max(cap_r, 8)), chunk, s->sm_count, s->st)) != MF_OK) return fail(rc);
             trace.mark("  build both panel layouts");

@@ -90,8 +90,8 @@ typedef struct mf_params {
     int32_t schedule;          /* MF_SCHEDULE_* (CCD++) */
     int32_t layout;            /* MF_LAYOUT_*   (CCD++) */
     int32_t quiet;             /* 1: do not print the per-iteration "[-INFO-] iteration num" line */
-    int32_t panel_rows;        /* 0 = default (24576); factor rows per shared-memory panel */
-    int32_t chunk;             /* 0 = default (2048); max rating entries per work item */
+    int32_t panel_rows;        /* 0 = default (12288), max 16376; factor entries per shared-memory panel */
+    int32_t chunk;             /* 0 = default (512); max rating entries per work item */
     int32_t nmf_project;       /* 1: clamp solved coordinates at 0 (extension; the reference never does) */
     int32_t no_launch_timing;  /* 1: skip the per-launch CUDA events (mf_kernel_times stays zero) */
     int32_t reserved[8];

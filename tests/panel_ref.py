@@ -1,6 +1,6 @@
 """numpy restatement of the PANEL layout (cuda-recommender_b200/csrc/layout.cuh, prep.cu) — the
 integer-tier checker for the layout the GPU builds: pieces = (panel, segment) cuts of every segment,
-panel-major storage, 8-entry padding with idx16 = panel_rows / val = 0, work items of <= chunk
+panel-major storage, 8-entry padding with idx16 = 4*panel_rows / val = 0 (indices stored as byte offsets), work items of <= chunk
 entries, slots of a segment ordered (panel, chunk).  Test infrastructure only."""
 import numpy as np
 
@@ -19,12 +19,9 @@ def choose_panel_rows(gdim, cap):
 
 
 def session_panel_rows(gdim, side_is_csr, user_panel_rows=0):
-    cap = panel_cap(3 if side_is_csr else 2)
-    if user_panel_rows > 0:
-        cap = min(cap, user_panel_rows // 8 * 8)
-    elif not side_is_csr:
-        cap = min(cap, 24576)
-    return choose_panel_rows(gdim, max(cap, 8))
+    cap = min(panel_cap(3 if side_is_csr else 2), 16376)
+    want = user_panel_rows // 8 * 8 if user_panel_rows > 0 else 12288
+    return choose_panel_rows(gdim, max(min(cap, want), 8))
 
 
 def panel_layout(ptr, idx, val, gdim, panel_rows, chunk):
@@ -52,7 +49,7 @@ def panel_layout(ptr, idx, val, gdim, panel_rows, chunk):
         if pd == 0:
             continue
         loc = (idx[a:a + cnt].astype(np.int64) - p * panel_rows)
-        idx16.append(np.concatenate([loc, np.full(pd - cnt, panel_rows)]).astype(np.uint16))
+        idx16.append((np.concatenate([loc, np.full(pd - cnt, panel_rows)]) * 4).astype(np.uint16))  # stored as byte offsets
         pval.append(np.concatenate([val[a:a + cnt], np.zeros(pd - cnt, np.float32)]).astype(np.float32))
         for j in range(nit):
             items.append((pos + j * chunk, min(chunk, pd - j * chunk), s, slot_ptr[s] + before[s] + j))
