@@ -64,6 +64,7 @@ def parse_args():
     ap.add_argument("--no-launch-timing", action="store_true")
     ap.add_argument("--panel-rows", type=int, default=0)
     ap.add_argument("--chunk", type=int, default=0)
+    ap.add_argument("--pipeline", default="tma", choices=["tma", "registers"])
     return ap.parse_args()
 
 
@@ -248,7 +249,8 @@ def run_b200_arm(args):
     params = pkg.make_params(pkg.SOLVER_ALS if als else pkg.SOLVER_CCD, k=k, lam=lam, maxiter=args.steps, maxinner=max(T, 1), device=local_rank,
                              schedule=pkg.SCHEDULE_REFERENCE if args.schedule == "reference" else pkg.SCHEDULE_FUSED,
                              layout=pkg.LAYOUT_DIRECT if args.layout == "direct" else pkg.LAYOUT_PANEL,
-                             panel_rows=args.panel_rows, chunk=args.chunk, no_launch_timing=int(args.no_launch_timing))
+                             panel_rows=args.panel_rows, chunk=args.chunk, no_launch_timing=int(args.no_launch_timing),
+                             pipeline=1 if args.pipeline == "registers" else 0)
     nccl_id = None
     if world > 1:
         idt = torch.zeros(128, dtype=torch.uint8, device=dev)
@@ -347,7 +349,7 @@ def run_b200_arm(args):
         Ht = torch.zeros((k, cols), dtype=torch.float32).pin_memory()
         p2 = pkg.make_params(pkg.SOLVER_CCD, k=k, lam=lam, maxiter=E, maxinner=T, device=local_rank,
                              schedule=params.schedule, layout=params.layout, panel_rows=args.panel_rows, chunk=args.chunk,
-                             no_launch_timing=1)
+                             no_launch_timing=1, pipeline=params.pipeline)
         h2d = sum(v.nbytes for kk, v in pinned.items() if isinstance(v, np.ndarray) and not kk.startswith("coo_")) + Wt.numel() * 4
         d2h = (Wt.numel() + Ht.numel()) * 4 + 8 * E
         barrier()

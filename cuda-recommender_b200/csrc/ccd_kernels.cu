@@ -225,6 +225,207 @@ __global__ void __launch_bounds__(1024, 1) k_panel_sweep(PanelSweepArgs a) {
     }
 }
 
+// =============================================================================================
+// TMA pipeline variant of the panel sweep (the default): warp 0 of the CTA is a producer that moves
+// every work item of the CTA's range from HBM into a ring of shared-memory slots with 1-D bulk
+// async copies (cp.async.bulk, completion counted on an mbarrier per slot); warps 1..31 consume the
+// slots.  The HBM stream is thereby decoupled from the arithmetic: ~40-58 items (70-100 KB) are in
+// flight per SM whatever the consumers are doing, and the consumers hold no prefetch registers.
+//   slot      = 64-byte header (the item descriptor) + chunk*2 bytes of indices + chunk*4 bytes of values
+//   full[s]   producer -> consumers: arrive.expect_tx(bytes) by the producer lane + complete_tx by the copies
+//   empty[s]  consumers -> producer: one arrive by the 8-lane group that read the slot
+//   item n of the CTA (n counted from the CTA's first item, across panels) lives in slot n % nslots during
+//   ring round n / nslots; barrier parities follow from n, so no state is reset between panels.
+// Consumers claim batches of four consecutive items from a shared-memory counter exactly as the register
+// ring kernel does, so the reduction tree of an item (lane-serial over its steps, xor-butterfly over the
+// 8 lanes of its group) is identical in both kernels — they give bit-identical results.
+// =============================================================================================
+namespace tma {
+
+constexpr uint32_t kChunkMax = 512;                                  // largest item the slots hold
+constexpr uint32_t kSlotHeader = 64;
+constexpr uint32_t kSlotBytes = kSlotHeader + kChunkMax * 2 + kChunkMax * 4;  // 3136: 784 words = 16 mod 32 banks
+constexpr uint32_t kSpinLimit = 1u << 26;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0u;
+}
+// bounded wait: a protocol bug traps instead of hanging the device
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity))
+        if (++spins > kSpinLimit) __trap();
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
+}  // namespace tma
+
+template <int MODE>
+__global__ void __launch_bounds__(1024, 1) k_panel_sweep_tma(PanelSweepArgs a) {
+    using namespace tma;
+    constexpr bool SUB = MODE & kSub, ADD = MODE & kAdd, SOLVE = MODE & kSolve, ADDSEP = MODE & kAddSep;
+    constexpr bool WRITE = SUB || ADD;
+    extern __shared__ __align__(128) unsigned char smraw[];
+    __shared__ unsigned s_ctr;
+
+    const uint32_t PR = a.panel_rows;
+    const uint32_t stride = PR + 8;  // 8 zeroed floats behind each panel: the padding slot
+    constexpr bool NEEDNEW = SOLVE || (ADD && !ADDSEP);
+    float* smem = reinterpret_cast<float*>(smraw);
+    float* sm_new = smem;
+    float* sm_add = smem;
+    float* sm_old = smem;
+    int nvec = 0;
+    if (NEEDNEW) { sm_new = smem + nvec * stride; ++nvec; }
+    if (ADD) { if (ADDSEP) { sm_add = smem + nvec * stride; ++nvec; } else sm_add = sm_new; }
+    if (SUB) { sm_old = smem + nvec * stride; ++nvec; }
+    const float* g_add = ADDSEP ? a.g_add : a.g_new;
+    const uint32_t vec_bytes = ((uint32_t)nvec * stride * 4u + 127u) & ~127u;
+    const uint32_t NS = a.nslots;
+    unsigned char* slots = smraw + vec_bytes;
+    const uint32_t slots_u32 = smem_u32(slots);
+    const uint32_t full_u32 = slots_u32 + NS * kSlotBytes;   // full[s]  at full_u32 + 8*s
+    const uint32_t empty_u32 = full_u32 + NS * 8u;           // empty[s] at empty_u32 + 8*s
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int grp = lane >> 3, sl = lane & 7;
+    const uint4* __restrict__ items = reinterpret_cast<const uint4*>(a.items);
+
+    if (threadIdx.x == 0) {
+        for (uint32_t s = 0; s < NS; ++s) {
+            mbar_init(full_u32 + 8u * s, 1u);
+            mbar_init(empty_u32 + 8u * s, 1u);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const uint32_t ib0 = a.cta_item_ptr[blockIdx.x];
+    uint32_t ib = ib0;
+    const uint32_t ie = a.cta_item_ptr[blockIdx.x + 1];
+    int p = 0;
+    while (p < a.npanels && a.panel_item_ptr[p + 1] <= ib) ++p;
+
+    while (ib < ie && p < a.npanels) {
+        const uint32_t pend = a.panel_item_ptr[p + 1];
+        const uint32_t pe = ie < pend ? ie : pend;
+        if (pe > ib) {
+            __syncthreads();  // consumers are done with the previous panel's vectors and counter
+            const int64_t base = (int64_t)p * PR;
+            const uint32_t cnt = (uint32_t)((a.gdim - base) < (int64_t)PR ? (a.gdim - base) : (int64_t)PR);
+            for (uint32_t i = threadIdx.x; i < stride; i += blockDim.x) {
+                const bool in = i < cnt;
+                if (NEEDNEW) sm_new[i] = in ? a.g_new[base + i] : 0.0f;
+                if (ADD && ADDSEP) sm_add[i] = in ? g_add[base + i] : 0.0f;
+                if (SUB) sm_old[i] = in ? a.g_old[base + i] : 0.0f;
+            }
+            if (threadIdx.x == 0) s_ctr = ib;
+            __syncthreads();
+
+            if (warp == 0) {
+                // ---------------- producer: every lane moves one item per round ----------------
+                for (uint32_t i = ib + lane; i < pe; i += 32) {
+                    const uint32_t n = i - ib0, slot = n % NS, round = n / NS;
+                    const uint4 d = __ldg(items + i);  // {start, len, seg, slot}
+                    mbar_wait(empty_u32 + 8u * slot, (round & 1u) ^ 1u);  // the slot's previous occupant was read
+                    unsigned char* sb = slots + slot * kSlotBytes;
+                    *reinterpret_cast<uint4*>(sb) = d;
+                    const uint32_t bar = full_u32 + 8u * slot, dst = slots_u32 + slot * kSlotBytes + kSlotHeader;
+                    mbar_expect_tx(bar, d.y * 6u);
+                    bulk_g2s(dst, a.idx16 + d.x, d.y * 2u, bar);
+                    bulk_g2s(dst + kChunkMax * 2u, a.val + d.x, d.y * 4u, bar);
+                }
+            } else {
+                // ---------------- consumers: four items per warp, one per 8-lane group ----------------
+                for (;;) {
+                    uint32_t i0 = 0;
+                    if (lane == 0) i0 = atomicAdd(&s_ctr, 4u);
+                    i0 = __shfl_sync(kFull, i0, 0);
+                    if (i0 >= pe) break;
+                    const uint32_t mine = i0 + grp;
+                    const bool have = mine < pe;
+                    uint4 d = make_uint4(0u, 0u, 0u, 0u);
+                    const unsigned char* sb = slots;
+                    uint32_t slot = 0;
+                    if (have) {
+                        const uint32_t n = mine - ib0;
+                        slot = n % NS;
+                        mbar_wait(full_u32 + 8u * slot, (n / NS) & 1u);  // descriptor + indices + values have landed
+                        sb = slots + slot * kSlotBytes;
+                        d = *reinterpret_cast<const uint4*>(sb);
+                    }
+                    const uint32_t len = d.y;
+                    const uint32_t lane_off = 4u * (uint32_t)sl;
+                    float s_add = 0.0f, s_old = 0.0f;
+                    if (len != 0u) {
+                        if (ADD) s_add = __ldg(a.s_add + a.seg_offset + d.z);
+                        if (SUB) s_old = __ldg(a.s_old + a.seg_offset + d.z);
+                    }
+                    const uint32_t maxlen = __reduce_max_sync(kFull, len);
+                    const uint32_t minlen = __reduce_min_sync(kFull, len);
+                    const uint16_t* sidx = reinterpret_cast<const uint16_t*>(sb + kSlotHeader) + lane_off;
+                    const float* sval = reinterpret_cast<const float*>(sb + kSlotHeader + kChunkMax * 2u) + lane_off;
+                    float* gval = a.val + d.x + lane_off;
+                    float g = 0.0f, h = 0.0f;
+                    uint32_t o = 0;
+#pragma unroll 2
+                    for (; o + 32u <= minlen; o += 32u) {  // every lane of every group has 4 entries here
+                        Step e;
+                        e.i = *reinterpret_cast<const uint2*>(sidx + o);
+                        e.v = *reinterpret_cast<const float4*>(sval + o);
+                        calc4<MODE>(e, sm_new, sm_add, sm_old, s_add, s_old, g, h);
+                        if (WRITE) __stcs(reinterpret_cast<float4*>(gval + o), e.v);
+                    }
+#pragma unroll 1
+                    for (; o < maxlen; o += 32u) {
+                        if (o + lane_off < len) {
+                            Step e;
+                            e.i = *reinterpret_cast<const uint2*>(sidx + o);
+                            e.v = *reinterpret_cast<const float4*>(sval + o);
+                            calc4<MODE>(e, sm_new, sm_add, sm_old, s_add, s_old, g, h);
+                            if (WRITE) __stcs(reinterpret_cast<float4*>(gval + o), e.v);
+                        }
+                    }
+                    if (SOLVE) {
+#pragma unroll
+                        for (int q = 1; q < 8; q <<= 1) {
+                            g += __shfl_xor_sync(kFull, g, q);
+                            h += __shfl_xor_sync(kFull, h, q);
+                        }
+                        if (sl == 0 && len != 0u) a.partials[d.w] = make_float2(g, h);
+                    }
+                    __syncwarp();  // every lane of the group has finished reading the slot
+                    if (have && sl == 0) mbar_arrive(empty_u32 + 8u * slot);
+                }
+            }
+        }
+        ib = pe;
+        ++p;
+    }
+}
+
 // Adds a segment's slots, applies the regulariser, divides: out = g / (lambda*deg + h), with lambda*deg a
 // float*unsigned product as at src/CCD.cpp:112,120; empty segment -> 0 (src/CCD.cpp:8).
 // LANES = 1: one thread per segment (slots added in order); LANES = 32: one warp per segment, lane l adds
@@ -317,6 +518,18 @@ int launch_panel(const PanelSweepArgs& a, int ncta, int threads, size_t smem, cu
 }
 
 template <int MODE>
+int launch_panel_tma(const PanelSweepArgs& a, int ncta, int threads, size_t smem, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        MF_CUDA(cudaFuncSetAttribute(k_panel_sweep_tma<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 64));
+        attr_set = true;
+    }
+    k_panel_sweep_tma<MODE><<<ncta, threads, smem, st>>>(a);
+    MF_CUDA(cudaGetLastError());
+    return MF_OK;
+}
+
+template <int MODE>
 int launch_direct(const DirectSweepArgs& a, int sm_count, cudaStream_t st) {
     int64_t blocks = (a.nseg + 7) / 8;
     int64_t cap = (int64_t)sm_count * 32;
@@ -341,12 +554,36 @@ size_t panel_sweep_smem(int mode, int panel_rows) {
     return (size_t)panel_sweep_vectors(mode) * (size_t)(panel_rows + 8) * sizeof(float);
 }
 
-int panel_sweep(int mode, const PanelSweepArgs& a, int ncta, int threads, cudaStream_t st) {
-    const size_t smem = panel_sweep_smem(mode, (int)a.panel_rows);
-    if (smem > 227 * 1024 - 64) {
-        set_error("panel sweep mode %d needs %zu bytes of shared memory (panel_rows=%u)", mode, smem, a.panel_rows);
+int panel_sweep(int mode, const PanelSweepArgs& a_in, int ncta, int threads, int chunk, bool use_tma, cudaStream_t st) {
+    PanelSweepArgs a = a_in;
+    const size_t vec = panel_sweep_smem(mode, (int)a.panel_rows);
+    const size_t cap = 227 * 1024 - 64;
+    if (vec > cap) {
+        set_error("panel sweep mode %d needs %zu bytes of shared memory (panel_rows=%u)", mode, vec, a.panel_rows);
         return MF_ERR_ARG;
     }
+    if (use_tma && chunk <= (int)tma::kChunkMax) {
+        // slots get whatever shared memory the panel vectors leave (at most 64 slots)
+        const size_t vec_al = (vec + 127) & ~(size_t)127;
+        size_t ns = (cap - vec_al) / (tma::kSlotBytes + 16);
+        if (ns > 64) ns = 64;
+        if (ns >= 32) {  // the producer warp fills 32 slots per round: fewer slots could deadlock it against itself
+            a.nslots = (uint32_t)ns;
+            const size_t smem = vec_al + ns * (tma::kSlotBytes + 16);
+            switch (mode) {
+                case kSolve: return launch_panel_tma<kSolve>(a, ncta, threads, smem, st);
+                case kSub: return launch_panel_tma<kSub>(a, ncta, threads, smem, st);
+                case kAdd: return launch_panel_tma<kAdd>(a, ncta, threads, smem, st);
+                case kSub | kSolve: return launch_panel_tma<kSub | kSolve>(a, ncta, threads, smem, st);
+                case kAdd | kSolve: return launch_panel_tma<kAdd | kSolve>(a, ncta, threads, smem, st);
+                case kSub | kAdd | kSolve: return launch_panel_tma<kSub | kAdd | kSolve>(a, ncta, threads, smem, st);
+                case kAdd | kAddSep | kSolve: return launch_panel_tma<kAdd | kAddSep | kSolve>(a, ncta, threads, smem, st);
+                case kSub | kAdd | kAddSep | kSolve: return launch_panel_tma<kSub | kAdd | kAddSep | kSolve>(a, ncta, threads, smem, st);
+                default: set_error("panel sweep: unsupported mode %d", mode); return MF_ERR_ARG;
+            }
+        }
+    }
+    const size_t smem = vec;
     switch (mode) {
         case kSolve: return launch_panel<kSolve>(a, ncta, threads, smem, st);
         case kSub: return launch_panel<kSub>(a, ncta, threads, smem, st);

@@ -28,6 +28,7 @@ struct PanelSweepArgs {
     const float* s_add;   // per-segment factor for the add-back (full-length vector)
     const float* s_old;   // per-segment factor of the rank being subtracted
     float2* partials;
+    uint32_t nslots;      // TMA pipeline: shared-memory slots of the ring (set by panel_sweep)
 };
 
 struct DirectSweepArgs {
@@ -48,7 +49,7 @@ struct DirectSweepArgs {
 
 int panel_sweep_vectors(int mode);
 size_t panel_sweep_smem(int mode, int panel_rows);
-int panel_sweep(int mode, const PanelSweepArgs& a, int ncta, int threads, cudaStream_t st);
+int panel_sweep(int mode, const PanelSweepArgs& a, int ncta, int threads, int chunk, bool use_tma, cudaStream_t st);
 int panel_finalize(int64_t nseg, int64_t nslots, const uint32_t* slot_ptr, const float2* partials, const uint32_t* seg_ptr,
                    float lambda, int nmf, float* out, cudaStream_t st);
 int direct_sweep(int mode, const DirectSweepArgs& a, int sm_count, cudaStream_t st);

@@ -9,6 +9,9 @@
 
 namespace mf {
 
+// MF_TRACE=1 in the environment: host-side phase timings on stderr (time since the previous mark)
+void trace_mark(const char* what);
+
 // thread-local last-error text behind mf_last_error()
 void set_error(const char* fmt, ...);
 const char* get_error();

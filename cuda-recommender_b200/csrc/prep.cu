@@ -293,6 +293,7 @@ int side_build_panels(Side& s, int panel_rows, int chunk, int ncta, cudaStream_t
     size_t tmp_n = scan_tmp_elems((size_t)(Q > s.nseg ? Q : s.nseg));
     MF_TRY(tmp_alloc(&tmp, tmp_n, st));
 
+    trace_mark("    layout: index allocations");
     if (Q > 0)
         k_piece_count<<<grid_for(Q, 256), 256, 0, st>>>(s.nseg, s.npanels, (uint32_t)panel_rows, (uint32_t)chunk, s.ptr,
                                                         s.idx, s.piece_first, padded, nitem);
@@ -314,12 +315,14 @@ int side_build_panels(Side& s, int panel_rows, int chunk, int ncta, cudaStream_t
     s.nslots = h_nslots;
     MF_REQUIRE(s.nitems == s.nslots, "internal: item/slot count mismatch (%lld vs %lld)", (long long)s.nitems, (long long)s.nslots);
 
+    trace_mark("    layout: count + scans");
     MF_TRY(dev_alloc(&s.idx16, (size_t)s.npad + 8));
     MF_TRY(dev_alloc(&s.pval, (size_t)s.npad + 8));
     MF_TRY(dev_alloc(&s.items, (size_t)s.nitems));
     MF_TRY(dev_alloc(&s.partials, (size_t)s.nslots));
     MF_TRY(tmp_alloc(&cost, (size_t)s.nitems, st));
     MF_TRY(tmp_alloc(&cost_prefix, (size_t)s.nitems + 1, st));
+    trace_mark("    layout: big allocations");
     if (Q > 0) {
         int64_t warps = Q < 148 * 64 * 8 ? Q : 148 * 64 * 8;
         k_fill<<<grid_for(warps * 32, 256), 256, 0, st>>>(s.nseg, s.npanels, (uint32_t)panel_rows, (uint32_t)chunk, s.ptr,
@@ -356,6 +359,7 @@ int side_build_panels(Side& s, int panel_rows, int chunk, int ncta, cudaStream_t
     k_cta_ranges<<<grid_for(ncta + 1, 128), 128, 0, st>>>(ncta, s.nitems, cost_prefix, s.cta_item_ptr);
     MF_CUDA(cudaGetLastError());
     MF_CUDA(cudaStreamSynchronize(st));
+    trace_mark("    layout: fill + order + ranges");
     tmp_free(padded, st); tmp_free(nitem, st); tmp_free(seg_items, st); tmp_free(tmp, st); tmp_free(cost, st); tmp_free(cost_prefix, st);
     return MF_OK;
 }

@@ -2,6 +2,9 @@
 // layout builders: piece offsets, work-item offsets, slot offsets, cost prefix).
 // Three launches: per-tile reduce, single-CTA scan of the tile sums, per-tile scan + offset.
 #include <stdarg.h>
+#include <stdlib.h>
+
+#include <chrono>
 
 #include "common.cuh"
 
@@ -15,6 +18,15 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 const char* get_error() { return g_err; }
+
+void trace_mark(const char* what) {
+    static const bool on = getenv("MF_TRACE") != nullptr;
+    static std::chrono::steady_clock::time_point last = std::chrono::steady_clock::now();
+    if (!on) return;
+    auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[mf trace] %-34s %9.3f ms\n", what, std::chrono::duration<double, std::milli>(now - last).count());
+    last = now;
+}
 
 namespace {
 constexpr int kScanThreads = 1024;

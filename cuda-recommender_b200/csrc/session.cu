@@ -151,7 +151,8 @@ int run_sweep(mf_session* s, Side& sd, int mode, const SweepVectors& v, float* o
         a.partials = sd.partials;
         if (sd.nitems > 0) {
             s->timer.start(family_of(mode));
-            MF_TRY(panel_sweep(mode, a, sd.ncta, kThreads, s->st));
+            a.nslots = 0;
+            MF_TRY(panel_sweep(mode, a, sd.ncta, kThreads, sd.chunk, s->prm.pipeline == MF_PIPELINE_TMA, s->st));
             s->timer.stop();
         }
         if (mode & kSolve) {
@@ -292,22 +293,9 @@ int check_ratings(const mf_ratings* R) {
     return MF_OK;
 }
 
-// MF_TRACE=1 in the environment prints host-side phase timings of session creation to stderr
-struct Trace {
-    bool on;
-    std::chrono::steady_clock::time_point t0;
-    Trace() : on(getenv("MF_TRACE") != nullptr), t0(std::chrono::steady_clock::now()) {}
-    void mark(const char* what) {
-        if (!on) return;
-        auto t1 = std::chrono::steady_clock::now();
-        fprintf(stderr, "[mf trace] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
-        t0 = t1;
-    }
-};
-
 int create_impl(const mf_ratings* R, const mf_testset* T, const mf_params* params, int rank, int nranks,
                 const void* nccl_id, mf_session** out) {
-    Trace trace;
+    trace_mark("(enter session create)");
     MF_REQUIRE(out != nullptr && params != nullptr, "NULL argument");
     *out = nullptr;
     MF_TRY(check_ratings(R));
@@ -342,7 +330,7 @@ int create_impl(const mf_ratings* R, const mf_testset* T, const mf_params* param
     s->timer.st = s->st;
     s->timer.enabled = true;
 
-    trace.mark("device/stream setup");
+    trace_mark("device/stream setup");
     std::vector<uint32_t> rp, cp;
     if ((rc = fetch_ptr(R->csr_row_ptr, R->rows + 1, rp)) != MF_OK) return fail(rc);
     if ((rc = fetch_ptr(R->csc_col_ptr, R->cols + 1, cp)) != MF_OK) return fail(rc);
@@ -356,7 +344,7 @@ int create_impl(const mf_ratings* R, const mf_testset* T, const mf_params* param
     if ((rc = upload_side(s->csr, rp, s->row_bound[rank], s->row_bound[rank + 1], R->csr_col_idx, R->csr_val, R->cols, s->st)) != MF_OK) return fail(rc);
     if ((rc = upload_side(s->csc, cp, s->col_bound[rank], s->col_bound[rank + 1], R->csc_row_idx, R->csc_val, R->rows, s->st)) != MF_OK) return fail(rc);
 
-    trace.mark("upload CSR + CSC");
+    trace_mark("upload CSR + CSC");
     const bool ccd = params->solver_type == MF_SOLVER_CCD;
     if (ccd) {
         s->panel = params->layout == MF_LAYOUT_PANEL;
@@ -365,7 +353,7 @@ int create_impl(const mf_ratings* R, const mf_testset* T, const mf_params* param
             if ((rc = side_check_sorted(s->csr, &ok_r, s->st)) != MF_OK) return fail(rc);
             if ((rc = side_check_sorted(s->csc, &ok_c, s->st)) != MF_OK) return fail(rc);
             if (!ok_r || !ok_c) s->panel = false;  // the panel cut needs ascending indices inside a segment
-            trace.mark("  sortedness check");
+            trace_mark("  sortedness check");
         }
         if (s->panel) {
             // Panel size.  Shared memory a sweep needs: CSC side up to 2 vectors (u_new, u_old), CSR side up to 3
@@ -379,12 +367,12 @@ int create_impl(const mf_ratings* R, const mf_testset* T, const mf_params* param
             const int chunk = params->chunk > 0 ? std::max(8, params->chunk / 8 * 8) : 512;
             if ((rc = side_build_panels(s->csc, choose_panel_rows(s->csc.gdim, std::max(cap_c, 8)), chunk, s->sm_count, s->st)) != MF_OK) return fail(rc);
             if ((rc = side_build_panels(s->csr, choose_panel_rows(s->csr.gdim, std::max(cap_r, 8)), chunk, s->sm_count, s->st)) != MF_OK) return fail(rc);
-            trace.mark("  build both panel layouts");
+            trace_mark("  build both panel layouts");
             // the caller-order index/value arrays are no longer needed: the residual lives in the panel arrays
             cudaFree(s->csc.idx); s->csc.idx = nullptr; cudaFree(s->csc.val); s->csc.val = nullptr;
             cudaFree(s->csr.idx); s->csr.idx = nullptr; cudaFree(s->csr.val); s->csr.val = nullptr;
         }
-        trace.mark("sortedness + panel layout");
+        trace_mark("sortedness + panel layout");
         s->ldm = round_up(s->rows, 32);
         s->ldn = round_up(s->cols, 32);
         if ((rc = dev_alloc(&s->W, (size_t)s->k * s->ldm)) != MF_OK) return fail(rc);
@@ -418,7 +406,7 @@ int create_impl(const mf_ratings* R, const mf_testset* T, const mf_params* param
     }
     cudaError_t e = cudaStreamSynchronize(s->st);
     if (e != cudaSuccess) { set_error("session setup failed: %s", cudaGetErrorString(e)); return fail(MF_ERR_CUDA); }
-    trace.mark("factors + test set + comm");
+    trace_mark("factors + test set + comm");
     *out = s;
     return MF_OK;
 }

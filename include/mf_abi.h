@@ -50,6 +50,7 @@ enum {
 enum { MF_SOLVER_CCD = 0, MF_SOLVER_ALS = 1 };               /* src/pmf.h:6 solvertype */
 enum { MF_SCHEDULE_FUSED = 0, MF_SCHEDULE_REFERENCE = 1 };   /* REFERENCE = CCD_CUDA.cu:339-378 launch order */
 enum { MF_LAYOUT_PANEL = 0, MF_LAYOUT_DIRECT = 1 };          /* HBM layout of the rating copies */
+enum { MF_PIPELINE_TMA = 0, MF_PIPELINE_REGISTERS = 1 };      /* how the panel sweep feeds its warps */
 enum { MF_SIDE_CSC = 0, MF_SIDE_CSR = 1 };                   /* CSC: columns solve v / H;  CSR: rows solve u / W */
 
 /* Paired CSR + CSC of the same ratings — src/pmf_util.h:34-149 (SparseMatrix). */
@@ -94,7 +95,8 @@ typedef struct mf_params {
     int32_t chunk;             /* 0 = default (512); max rating entries per work item */
     int32_t nmf_project;       /* 1: clamp solved coordinates at 0 (extension; the reference never does) */
     int32_t no_launch_timing;  /* 1: skip the per-launch CUDA events (mf_kernel_times stays zero) */
-    int32_t reserved[8];
+    int32_t pipeline;          /* MF_PIPELINE_*: TMA bulk copies into a shared-memory ring (default) or register ring */
+    int32_t reserved[7];
 } mf_params;
 
 /* One line of the reference's per-iteration report (CCD_CUDA.cu:405, ALS_CUDA.cu:360). */
