@@ -509,7 +509,7 @@ template <int MODE>
 int launch_panel(const PanelSweepArgs& a, int ncta, int threads, size_t smem, cudaStream_t st) {
     static bool attr_set = false;  // per template instance
     if (!attr_set) {
-        MF_CUDA(cudaFuncSetAttribute(k_panel_sweep<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 64));
+        MF_CUDA(cudaFuncSetAttribute(k_panel_sweep<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 256));
         attr_set = true;
     }
     k_panel_sweep<MODE><<<ncta, threads, smem, st>>>(a);
@@ -521,7 +521,7 @@ template <int MODE>
 int launch_panel_tma(const PanelSweepArgs& a, int ncta, int threads, size_t smem, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
-        MF_CUDA(cudaFuncSetAttribute(k_panel_sweep_tma<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 64));
+        MF_CUDA(cudaFuncSetAttribute(k_panel_sweep_tma<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 256));
         attr_set = true;
     }
     k_panel_sweep_tma<MODE><<<ncta, threads, smem, st>>>(a);
@@ -557,7 +557,7 @@ size_t panel_sweep_smem(int mode, int panel_rows) {
 int panel_sweep(int mode, const PanelSweepArgs& a_in, int ncta, int threads, int chunk, bool use_tma, cudaStream_t st) {
     PanelSweepArgs a = a_in;
     const size_t vec = panel_sweep_smem(mode, (int)a.panel_rows);
-    const size_t cap = 227 * 1024 - 64;
+    const size_t cap = 227 * 1024 - 256;
     if (vec > cap) {
         set_error("panel sweep mode %d needs %zu bytes of shared memory (panel_rows=%u)", mode, vec, a.panel_rows);
         return MF_ERR_ARG;

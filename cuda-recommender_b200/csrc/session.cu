@@ -62,7 +62,7 @@ void FamilyTimer::destroy() {
 namespace {
 
 constexpr int kThreads = 1024;
-constexpr size_t kSmemMax = 227 * 1024 - 64;
+constexpr size_t kSmemMax = 227 * 1024 - 256;
 
 int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 

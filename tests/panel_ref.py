@@ -4,7 +4,7 @@ panel-major storage, 8-entry padding with idx16 = 4*panel_rows / val = 0 (indice
 entries, slots of a segment ordered (panel, chunk).  Test infrastructure only."""
 import numpy as np
 
-SMEM_MAX = 227 * 1024 - 64
+SMEM_MAX = 227 * 1024 - 256
 
 
 def panel_cap(nvec):
