@@ -289,6 +289,7 @@ __global__ void __launch_bounds__(1024, 1) k_panel_sweep_tma(PanelSweepArgs a) {
     constexpr bool WRITE = SUB || ADD;
     extern __shared__ __align__(128) unsigned char smraw[];
     __shared__ unsigned s_ctr;
+    __shared__ volatile unsigned s_issued;  // items (counted from the CTA's first) the producer has started to fill
 
     const uint32_t PR = a.panel_rows;
     const uint32_t stride = PR + 8;  // 8 zeroed floats behind each panel: the padding slot
@@ -318,6 +319,7 @@ __global__ void __launch_bounds__(1024, 1) k_panel_sweep_tma(PanelSweepArgs a) {
             mbar_init(full_u32 + 8u * s, 1u);
             mbar_init(empty_u32 + 8u * s, 1u);
         }
+        s_issued = 0u;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -346,16 +348,24 @@ __global__ void __launch_bounds__(1024, 1) k_panel_sweep_tma(PanelSweepArgs a) {
 
             if (warp == 0) {
                 // ---------------- producer: every lane moves one item per round ----------------
-                for (uint32_t i = ib + lane; i < pe; i += 32) {
-                    const uint32_t n = i - ib0, slot = n % NS, round = n / NS;
-                    const uint4 d = __ldg(items + i);  // {start, len, seg, slot}
-                    mbar_wait(empty_u32 + 8u * slot, (round & 1u) ^ 1u);  // the slot's previous occupant was read
-                    unsigned char* sb = slots + slot * kSlotBytes;
-                    *reinterpret_cast<uint4*>(sb) = d;
-                    const uint32_t bar = full_u32 + 8u * slot, dst = slots_u32 + slot * kSlotBytes + kSlotHeader;
-                    mbar_expect_tx(bar, d.y * 6u);
-                    bulk_g2s(dst, a.idx16 + d.x, d.y * 2u, bar);
-                    bulk_g2s(dst + kChunkMax * 2u, a.val + d.x, d.y * 4u, bar);
+                for (uint32_t rbase = ib; rbase < pe; rbase += 32) {
+                    const uint32_t i = rbase + lane;
+                    if (i < pe) {
+                        const uint32_t n = i - ib0, slot = n % NS, round = n / NS;
+                        const uint4 d = __ldg(items + i);  // {start, len, seg, slot}
+                        mbar_wait(empty_u32 + 8u * slot, (round & 1u) ^ 1u);  // the slot's previous occupant was read
+                        unsigned char* sb = slots + slot * kSlotBytes;
+                        *reinterpret_cast<uint4*>(sb) = d;
+                        const uint32_t bar = full_u32 + 8u * slot, dst = slots_u32 + slot * kSlotBytes + kSlotHeader;
+                        mbar_expect_tx(bar, d.y * 6u);
+                        bulk_g2s(dst, a.idx16 + d.x, d.y * 2u, bar);
+                        bulk_g2s(dst + kChunkMax * 2u, a.val + d.x, d.y * 4u, bar);
+                    }
+                    // Publish how far the ring has been (re)armed.  A consumer may only wait on full[slot] for
+                    // item n once the producer has armed that slot for n: a parity wait issued earlier would
+                    // alias the slot's previous ring round.
+                    __syncwarp();
+                    if (lane == 0) s_issued = (rbase + 32u < pe ? rbase + 32u : pe) - ib0;
                 }
             } else {
                 // ---------------- consumers: four items per warp, one per 8-lane group ----------------
@@ -372,6 +382,9 @@ __global__ void __launch_bounds__(1024, 1) k_panel_sweep_tma(PanelSweepArgs a) {
                     if (have) {
                         const uint32_t n = mine - ib0;
                         slot = n % NS;
+                        uint32_t spins = 0;
+                        while (s_issued <= n)  // the producer has not armed this slot for item n yet
+                            if (++spins > kSpinLimit) __trap();
                         mbar_wait(full_u32 + 8u * slot, (n / NS) & 1u);  // descriptor + indices + values have landed
                         sb = slots + slot * kSlotBytes;
                         d = *reinterpret_cast<const uint4*>(sb);
