@@ -64,7 +64,7 @@ def parse_args():
     ap.add_argument("--no-launch-timing", action="store_true")
     ap.add_argument("--panel-rows", type=int, default=0)
     ap.add_argument("--chunk", type=int, default=0)
-    ap.add_argument("--pipeline", default="tma", choices=["tma", "registers"])
+    ap.add_argument("--pipeline", default="async", choices=["async", "registers", "tma"])
     return ap.parse_args()
 
 
@@ -250,7 +250,7 @@ def run_b200_arm(args):
                              schedule=pkg.SCHEDULE_REFERENCE if args.schedule == "reference" else pkg.SCHEDULE_FUSED,
                              layout=pkg.LAYOUT_DIRECT if args.layout == "direct" else pkg.LAYOUT_PANEL,
                              panel_rows=args.panel_rows, chunk=args.chunk, no_launch_timing=int(args.no_launch_timing),
-                             pipeline=1 if args.pipeline == "registers" else 0)
+                             pipeline={"async": 0, "registers": 1, "tma": 2}[args.pipeline])
     nccl_id = None
     if world > 1:
         idt = torch.zeros(128, dtype=torch.uint8, device=dev)

@@ -23,7 +23,7 @@ MF_OK = 0
 SOLVER_CCD, SOLVER_ALS = 0, 1
 SCHEDULE_FUSED, SCHEDULE_REFERENCE = 0, 1
 LAYOUT_PANEL, LAYOUT_DIRECT = 0, 1
-PIPELINE_TMA, PIPELINE_REGISTERS = 0, 1
+PIPELINE_ASYNC, PIPELINE_REGISTERS, PIPELINE_TMA_BULK = 0, 1, 2
 SIDE_CSC, SIDE_CSR = 0, 1
 
 

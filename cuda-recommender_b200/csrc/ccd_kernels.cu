@@ -282,11 +282,61 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 
 }  // namespace tma
 
+// One batch out of the shared-memory slot ring: the 8-lane group `sl`-lane belongs to streams the item whose
+// descriptor is `d` and whose indices / values sit in slot `sb` (len 0 = no item for this group).
+template <int MODE>
+__device__ __forceinline__ void consume_slot(const PanelSweepArgs& a, const uint4 d, const unsigned char* sb, int sl,
+                                             const float* __restrict__ sm_new, const float* __restrict__ sm_add,
+                                             const float* __restrict__ sm_old) {
+    using namespace tma;
+    constexpr bool SUB = MODE & kSub, ADD = MODE & kAdd, SOLVE = MODE & kSolve;
+    constexpr bool WRITE = SUB || ADD;
+    const uint32_t len = d.y;
+    const uint32_t lane_off = 4u * (uint32_t)sl;
+    float s_add = 0.0f, s_old = 0.0f;
+    if (len != 0u) {
+        if (ADD) s_add = __ldg(a.s_add + a.seg_offset + d.z);
+        if (SUB) s_old = __ldg(a.s_old + a.seg_offset + d.z);
+    }
+    const uint32_t maxlen = __reduce_max_sync(kFull, len);
+    const uint32_t minlen = __reduce_min_sync(kFull, len);
+    const uint16_t* sidx = reinterpret_cast<const uint16_t*>(sb + kSlotHeader) + lane_off;
+    const float* sval = reinterpret_cast<const float*>(sb + kSlotHeader + kChunkMax * 2u) + lane_off;
+    float* gval = a.val + d.x + lane_off;
+    float g = 0.0f, h = 0.0f;
+    uint32_t o = 0;
+#pragma unroll 2
+    for (; o + 32u <= minlen; o += 32u) {  // every lane of every group has 4 entries here
+        Step e;
+        e.i = *reinterpret_cast<const uint2*>(sidx + o);
+        e.v = *reinterpret_cast<const float4*>(sval + o);
+        calc4<MODE>(e, sm_new, sm_add, sm_old, s_add, s_old, g, h);
+        if (WRITE) __stcs(reinterpret_cast<float4*>(gval + o), e.v);
+    }
+#pragma unroll 1
+    for (; o < maxlen; o += 32u) {
+        if (o + lane_off < len) {
+            Step e;
+            e.i = *reinterpret_cast<const uint2*>(sidx + o);
+            e.v = *reinterpret_cast<const float4*>(sval + o);
+            calc4<MODE>(e, sm_new, sm_add, sm_old, s_add, s_old, g, h);
+            if (WRITE) __stcs(reinterpret_cast<float4*>(gval + o), e.v);
+        }
+    }
+    if (SOLVE) {
+#pragma unroll
+        for (int q = 1; q < 8; q <<= 1) {
+            g += __shfl_xor_sync(kFull, g, q);
+            h += __shfl_xor_sync(kFull, h, q);
+        }
+        if (sl == 0 && len != 0u) a.partials[d.w] = make_float2(g, h);
+    }
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(1024, 1) k_panel_sweep_tma(PanelSweepArgs a) {
     using namespace tma;
     constexpr bool SUB = MODE & kSub, ADD = MODE & kAdd, SOLVE = MODE & kSolve, ADDSEP = MODE & kAddSep;
-    constexpr bool WRITE = SUB || ADD;
     extern __shared__ __align__(128) unsigned char smraw[];
     __shared__ unsigned s_ctr;
     __shared__ volatile unsigned s_issued;  // items (counted from the CTA's first) the producer has started to fill
@@ -389,46 +439,152 @@ __global__ void __launch_bounds__(1024, 1) k_panel_sweep_tma(PanelSweepArgs a) {
                         sb = slots + slot * kSlotBytes;
                         d = *reinterpret_cast<const uint4*>(sb);
                     }
-                    const uint32_t len = d.y;
-                    const uint32_t lane_off = 4u * (uint32_t)sl;
-                    float s_add = 0.0f, s_old = 0.0f;
-                    if (len != 0u) {
-                        if (ADD) s_add = __ldg(a.s_add + a.seg_offset + d.z);
-                        if (SUB) s_old = __ldg(a.s_old + a.seg_offset + d.z);
-                    }
-                    const uint32_t maxlen = __reduce_max_sync(kFull, len);
-                    const uint32_t minlen = __reduce_min_sync(kFull, len);
-                    const uint16_t* sidx = reinterpret_cast<const uint16_t*>(sb + kSlotHeader) + lane_off;
-                    const float* sval = reinterpret_cast<const float*>(sb + kSlotHeader + kChunkMax * 2u) + lane_off;
-                    float* gval = a.val + d.x + lane_off;
-                    float g = 0.0f, h = 0.0f;
-                    uint32_t o = 0;
-#pragma unroll 2
-                    for (; o + 32u <= minlen; o += 32u) {  // every lane of every group has 4 entries here
-                        Step e;
-                        e.i = *reinterpret_cast<const uint2*>(sidx + o);
-                        e.v = *reinterpret_cast<const float4*>(sval + o);
-                        calc4<MODE>(e, sm_new, sm_add, sm_old, s_add, s_old, g, h);
-                        if (WRITE) __stcs(reinterpret_cast<float4*>(gval + o), e.v);
-                    }
-#pragma unroll 1
-                    for (; o < maxlen; o += 32u) {
-                        if (o + lane_off < len) {
-                            Step e;
-                            e.i = *reinterpret_cast<const uint2*>(sidx + o);
-                            e.v = *reinterpret_cast<const float4*>(sval + o);
-                            calc4<MODE>(e, sm_new, sm_add, sm_old, s_add, s_old, g, h);
-                            if (WRITE) __stcs(reinterpret_cast<float4*>(gval + o), e.v);
+                    consume_slot<MODE>(a, d, sb, sl, sm_new, sm_add, sm_old);
+                    __syncwarp();  // every lane of the group has finished reading the slot
+                    if (have && sl == 0) mbar_arrive(empty_u32 + 8u * slot);
+                }
+            }
+        }
+        ib = pe;
+        ++p;
+    }
+}
+
+// =============================================================================================
+// cp.async pipeline variant (the default): same slot ring and the same consumers as the bulk-copy
+// kernel above, but the ring is fed by kProducerWarps producer WARPS using 16-byte cp.async.cg copies
+// (LDGSTS, L1-bypassing) — one warp-wide instruction moves 32 x 16 bytes from arbitrary addresses, which
+// suits work items of a few hundred entries far better than one bulk-copy descriptor per item (measured:
+// profiles/README.md).  A producer warp handles a batch of four items at a time, one per 8-lane group,
+// exactly like the consumers; each lane signals the slot's `full` mbarrier when its own copies have landed
+// (cp.async.mbarrier.arrive.noinc), so the barrier expects 8 arrivals.
+//   slot_round[s]  ring round (+1) the slot is currently armed for, written by the producer after it has
+//                  waited for the slot's previous occupant to be consumed; a consumer waits for its round to
+//                  show up there before it issues the parity wait (which would otherwise alias the previous
+//                  round of the slot).
+// =============================================================================================
+namespace tma {
+constexpr int kProducerWarps = 4;
+__device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+}  // namespace tma
+
+template <int MODE>
+__global__ void __launch_bounds__(1024, 1) k_panel_sweep_async(PanelSweepArgs a) {
+    using namespace tma;
+    constexpr bool SUB = MODE & kSub, ADD = MODE & kAdd, SOLVE = MODE & kSolve, ADDSEP = MODE & kAddSep;
+    extern __shared__ __align__(128) unsigned char smraw[];
+    __shared__ unsigned s_ctr;
+
+    const uint32_t PR = a.panel_rows;
+    const uint32_t stride = PR + 8;  // 8 zeroed floats behind each panel: the padding slot
+    constexpr bool NEEDNEW = SOLVE || (ADD && !ADDSEP);
+    float* smem = reinterpret_cast<float*>(smraw);
+    float* sm_new = smem;
+    float* sm_add = smem;
+    float* sm_old = smem;
+    int nvec = 0;
+    if (NEEDNEW) { sm_new = smem + nvec * stride; ++nvec; }
+    if (ADD) { if (ADDSEP) { sm_add = smem + nvec * stride; ++nvec; } else sm_add = sm_new; }
+    if (SUB) { sm_old = smem + nvec * stride; ++nvec; }
+    const float* g_add = ADDSEP ? a.g_add : a.g_new;
+    const uint32_t vec_bytes = ((uint32_t)nvec * stride * 4u + 127u) & ~127u;
+    const uint32_t NS = a.nslots;
+    unsigned char* slots = smraw + vec_bytes;
+    const uint32_t slots_u32 = smem_u32(slots);
+    const uint32_t full_u32 = slots_u32 + NS * kSlotBytes;   // full[s]  at full_u32 + 8*s
+    const uint32_t empty_u32 = full_u32 + NS * 8u;           // empty[s] at empty_u32 + 8*s
+    volatile uint32_t* slot_round = reinterpret_cast<volatile uint32_t*>(slots + NS * (kSlotBytes + 16u));
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int grp = lane >> 3, sl = lane & 7;
+    const uint4* __restrict__ items = reinterpret_cast<const uint4*>(a.items);
+
+    if (threadIdx.x < NS) {
+        mbar_init(full_u32 + 8u * threadIdx.x, 8u);   // the 8 lanes of the producing group
+        mbar_init(empty_u32 + 8u * threadIdx.x, 1u);  // lane 0 of the consuming group
+        slot_round[threadIdx.x] = 0u;
+    }
+    if (threadIdx.x == 0) asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+
+    const uint32_t ib0 = a.cta_item_ptr[blockIdx.x];
+    uint32_t ib = ib0;
+    const uint32_t ie = a.cta_item_ptr[blockIdx.x + 1];
+    int p = 0;
+    while (p < a.npanels && a.panel_item_ptr[p + 1] <= ib) ++p;
+
+    while (ib < ie && p < a.npanels) {
+        const uint32_t pend = a.panel_item_ptr[p + 1];
+        const uint32_t pe = ie < pend ? ie : pend;
+        if (pe > ib) {
+            __syncthreads();  // consumers are done with the previous panel's vectors and counter
+            const int64_t base = (int64_t)p * PR;
+            const uint32_t cnt = (uint32_t)((a.gdim - base) < (int64_t)PR ? (a.gdim - base) : (int64_t)PR);
+            for (uint32_t i = threadIdx.x; i < stride; i += blockDim.x) {
+                const bool in = i < cnt;
+                if (NEEDNEW) sm_new[i] = in ? a.g_new[base + i] : 0.0f;
+                if (ADD && ADDSEP) sm_add[i] = in ? g_add[base + i] : 0.0f;
+                if (SUB) sm_old[i] = in ? a.g_old[base + i] : 0.0f;
+            }
+            if (threadIdx.x == 0) s_ctr = ib;
+            __syncthreads();
+
+            if (warp < kProducerWarps) {
+                // ---------------- producers: warp w feeds batches w, w+P, w+2P, ... of this panel range ----------------
+                uint32_t i0 = ib + 4u * (uint32_t)warp;
+                uint4 d = make_uint4(0u, 0u, 0u, 0u);
+                if (i0 + grp < pe) d = __ldg(items + i0 + grp);
+                while (i0 < pe) {
+                    const uint32_t i0n = i0 + 4u * kProducerWarps;
+                    uint4 dn = make_uint4(0u, 0u, 0u, 0u);
+                    if (i0n + grp < pe) dn = __ldg(items + i0n + grp);  // next batch's descriptors, one batch ahead
+                    if (d.y != 0u) {
+                        const uint32_t n = i0 + grp - ib0, slot = n % NS, round = n / NS;
+                        mbar_wait(empty_u32 + 8u * slot, (round & 1u) ^ 1u);  // the slot's previous occupant was read
+                        const uint32_t sbase = slots_u32 + slot * kSlotBytes;
+                        if (sl == 0) {
+                            *reinterpret_cast<uint4*>(slots + slot * kSlotBytes) = d;
+                            slot_round[slot] = round + 1u;  // armed: consumers of this round may now wait on full[slot]
                         }
+                        const unsigned char* gi = reinterpret_cast<const unsigned char*>(a.idx16 + d.x);
+                        const unsigned char* gv = reinterpret_cast<const unsigned char*>(a.val + d.x);
+                        const uint32_t nbi = d.y * 2u, nbv = d.y * 4u;  // bytes, multiples of 16
+                        for (uint32_t c = 16u * (uint32_t)sl; c < nbi; c += 128u) cp_async_16(sbase + kSlotHeader + c, gi + c);
+                        for (uint32_t c = 16u * (uint32_t)sl; c < nbv; c += 128u)
+                            cp_async_16(sbase + kSlotHeader + kChunkMax * 2u + c, gv + c);
+                        cp_async_arrive_noinc(full_u32 + 8u * slot);  // fires when this lane's copies have landed
                     }
-                    if (SOLVE) {
-#pragma unroll
-                        for (int q = 1; q < 8; q <<= 1) {
-                            g += __shfl_xor_sync(kFull, g, q);
-                            h += __shfl_xor_sync(kFull, h, q);
-                        }
-                        if (sl == 0 && len != 0u) a.partials[d.w] = make_float2(g, h);
+                    i0 = i0n;
+                    d = dn;
+                }
+            } else {
+                // ---------------- consumers: four items per warp, one per 8-lane group ----------------
+                for (;;) {
+                    uint32_t i0 = 0;
+                    if (lane == 0) i0 = atomicAdd(&s_ctr, 4u);
+                    i0 = __shfl_sync(kFull, i0, 0);
+                    if (i0 >= pe) break;
+                    const uint32_t mine = i0 + grp;
+                    const bool have = mine < pe;
+                    uint4 d = make_uint4(0u, 0u, 0u, 0u);
+                    const unsigned char* sb = slots;
+                    uint32_t slot = 0;
+                    if (have) {
+                        const uint32_t n = mine - ib0, round = n / NS;
+                        slot = n % NS;
+                        uint32_t spins = 0;
+                        while (slot_round[slot] != round + 1u)  // not armed for this round yet
+                            if (++spins > kSpinLimit) __trap();
+                        mbar_wait(full_u32 + 8u * slot, round & 1u);  // descriptor + indices + values have landed
+                        sb = slots + slot * kSlotBytes;
+                        d = *reinterpret_cast<const uint4*>(sb);
                     }
+                    consume_slot<MODE>(a, d, sb, sl, sm_new, sm_add, sm_old);
                     __syncwarp();  // every lane of the group has finished reading the slot
                     if (have && sl == 0) mbar_arrive(empty_u32 + 8u * slot);
                 }
@@ -543,6 +699,18 @@ int launch_panel_tma(const PanelSweepArgs& a, int ncta, int threads, size_t smem
 }
 
 template <int MODE>
+int launch_panel_async(const PanelSweepArgs& a, int ncta, int threads, size_t smem, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        MF_CUDA(cudaFuncSetAttribute(k_panel_sweep_async<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 256));
+        attr_set = true;
+    }
+    k_panel_sweep_async<MODE><<<ncta, threads, smem, st>>>(a);
+    MF_CUDA(cudaGetLastError());
+    return MF_OK;
+}
+
+template <int MODE>
 int launch_direct(const DirectSweepArgs& a, int sm_count, cudaStream_t st) {
     int64_t blocks = (a.nseg + 7) / 8;
     int64_t cap = (int64_t)sm_count * 32;
@@ -567,7 +735,7 @@ size_t panel_sweep_smem(int mode, int panel_rows) {
     return (size_t)panel_sweep_vectors(mode) * (size_t)(panel_rows + 8) * sizeof(float);
 }
 
-int panel_sweep(int mode, const PanelSweepArgs& a_in, int ncta, int threads, int chunk, bool use_tma, cudaStream_t st) {
+int panel_sweep(int mode, const PanelSweepArgs& a_in, int ncta, int threads, int chunk, int pipeline, cudaStream_t st) {
     PanelSweepArgs a = a_in;
     const size_t vec = panel_sweep_smem(mode, (int)a.panel_rows);
     const size_t cap = 227 * 1024 - 256;
@@ -575,25 +743,31 @@ int panel_sweep(int mode, const PanelSweepArgs& a_in, int ncta, int threads, int
         set_error("panel sweep mode %d needs %zu bytes of shared memory (panel_rows=%u)", mode, vec, a.panel_rows);
         return MF_ERR_ARG;
     }
-    if (use_tma && chunk <= (int)tma::kChunkMax) {
-        // slots get whatever shared memory the panel vectors leave (at most 64 slots)
+    if (pipeline != MF_PIPELINE_REGISTERS && chunk <= (int)tma::kChunkMax) {
+        // the slot ring gets whatever shared memory the panel vectors leave (at most 64 slots); per slot: data, two
+        // mbarriers, one round word
         const size_t vec_al = (vec + 127) & ~(size_t)127;
-        size_t ns = (cap - vec_al) / (tma::kSlotBytes + 16);
+        const size_t per_slot = tma::kSlotBytes + 16 + 4;
+        size_t ns = (cap - vec_al) / per_slot;
         if (ns > 64) ns = 64;
-        if (ns >= 32) {  // the producer warp fills 32 slots per round: fewer slots could deadlock it against itself
+        if (ns >= 32) {  // the bulk-copy producer arms 32 slots per round: fewer slots could deadlock it against itself
             a.nslots = (uint32_t)ns;
-            const size_t smem = vec_al + ns * (tma::kSlotBytes + 16);
-            switch (mode) {
-                case kSolve: return launch_panel_tma<kSolve>(a, ncta, threads, smem, st);
-                case kSub: return launch_panel_tma<kSub>(a, ncta, threads, smem, st);
-                case kAdd: return launch_panel_tma<kAdd>(a, ncta, threads, smem, st);
-                case kSub | kSolve: return launch_panel_tma<kSub | kSolve>(a, ncta, threads, smem, st);
-                case kAdd | kSolve: return launch_panel_tma<kAdd | kSolve>(a, ncta, threads, smem, st);
-                case kSub | kAdd | kSolve: return launch_panel_tma<kSub | kAdd | kSolve>(a, ncta, threads, smem, st);
-                case kAdd | kAddSep | kSolve: return launch_panel_tma<kAdd | kAddSep | kSolve>(a, ncta, threads, smem, st);
-                case kSub | kAdd | kAddSep | kSolve: return launch_panel_tma<kSub | kAdd | kAddSep | kSolve>(a, ncta, threads, smem, st);
-                default: set_error("panel sweep: unsupported mode %d", mode); return MF_ERR_ARG;
-            }
+            const size_t smem = vec_al + ns * per_slot;
+#define MF_DISPATCH(LAUNCH)                                                                                         \
+    switch (mode) {                                                                                                 \
+        case kSolve: return LAUNCH<kSolve>(a, ncta, threads, smem, st);                                             \
+        case kSub: return LAUNCH<kSub>(a, ncta, threads, smem, st);                                                 \
+        case kAdd: return LAUNCH<kAdd>(a, ncta, threads, smem, st);                                                 \
+        case kSub | kSolve: return LAUNCH<kSub | kSolve>(a, ncta, threads, smem, st);                               \
+        case kAdd | kSolve: return LAUNCH<kAdd | kSolve>(a, ncta, threads, smem, st);                               \
+        case kSub | kAdd | kSolve: return LAUNCH<kSub | kAdd | kSolve>(a, ncta, threads, smem, st);                 \
+        case kAdd | kAddSep | kSolve: return LAUNCH<kAdd | kAddSep | kSolve>(a, ncta, threads, smem, st);           \
+        case kSub | kAdd | kAddSep | kSolve: return LAUNCH<kSub | kAdd | kAddSep | kSolve>(a, ncta, threads, smem, st); \
+        default: set_error("panel sweep: unsupported mode %d", mode); return MF_ERR_ARG;                            \
+    }
+            if (pipeline == MF_PIPELINE_TMA_BULK) { MF_DISPATCH(launch_panel_tma) }
+            MF_DISPATCH(launch_panel_async)
+#undef MF_DISPATCH
         }
     }
     const size_t smem = vec;

@@ -49,7 +49,7 @@ struct DirectSweepArgs {
 
 int panel_sweep_vectors(int mode);
 size_t panel_sweep_smem(int mode, int panel_rows);
-int panel_sweep(int mode, const PanelSweepArgs& a, int ncta, int threads, int chunk, bool use_tma, cudaStream_t st);
+int panel_sweep(int mode, const PanelSweepArgs& a, int ncta, int threads, int chunk, int pipeline, cudaStream_t st);
 int panel_finalize(int64_t nseg, int64_t nslots, const uint32_t* slot_ptr, const float2* partials, const uint32_t* seg_ptr,
                    float lambda, int nmf, float* out, cudaStream_t st);
 int direct_sweep(int mode, const DirectSweepArgs& a, int sm_count, cudaStream_t st);

@@ -152,7 +152,7 @@ int run_sweep(mf_session* s, Side& sd, int mode, const SweepVectors& v, float* o
         if (sd.nitems > 0) {
             s->timer.start(family_of(mode));
             a.nslots = 0;
-            MF_TRY(panel_sweep(mode, a, sd.ncta, kThreads, sd.chunk, s->prm.pipeline == MF_PIPELINE_TMA, s->st));
+            MF_TRY(panel_sweep(mode, a, sd.ncta, kThreads, sd.chunk, s->prm.pipeline, s->st));
             s->timer.stop();
         }
         if (mode & kSolve) {

@@ -50,7 +50,9 @@ enum {
 enum { MF_SOLVER_CCD = 0, MF_SOLVER_ALS = 1 };               /* src/pmf.h:6 solvertype */
 enum { MF_SCHEDULE_FUSED = 0, MF_SCHEDULE_REFERENCE = 1 };   /* REFERENCE = CCD_CUDA.cu:339-378 launch order */
 enum { MF_LAYOUT_PANEL = 0, MF_LAYOUT_DIRECT = 1 };          /* HBM layout of the rating copies */
-enum { MF_PIPELINE_TMA = 0, MF_PIPELINE_REGISTERS = 1 };      /* how the panel sweep feeds its warps */
+/* how the panel sweep feeds its warps: producer warps with cp.async into a shared-memory slot ring
+ * (default), a per-lane register ring, or one bulk-copy (TMA) descriptor per work item into the same slot ring */
+enum { MF_PIPELINE_ASYNC = 0, MF_PIPELINE_REGISTERS = 1, MF_PIPELINE_TMA_BULK = 2 };
 enum { MF_SIDE_CSC = 0, MF_SIDE_CSR = 1 };                   /* CSC: columns solve v / H;  CSR: rows solve u / W */
 
 /* Paired CSR + CSC of the same ratings — src/pmf_util.h:34-149 (SparseMatrix). */
@@ -95,7 +97,7 @@ typedef struct mf_params {
     int32_t chunk;             /* 0 = default (512); max rating entries per work item */
     int32_t nmf_project;       /* 1: clamp solved coordinates at 0 (extension; the reference never does) */
     int32_t no_launch_timing;  /* 1: skip the per-launch CUDA events (mf_kernel_times stays zero) */
-    int32_t pipeline;          /* MF_PIPELINE_*: TMA bulk copies into a shared-memory ring (default) or register ring */
+    int32_t pipeline;          /* MF_PIPELINE_* */
     int32_t reserved[7];
 } mf_params;
 

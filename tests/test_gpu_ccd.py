@@ -111,21 +111,23 @@ def test_fused_schedule_equals_reference_schedule_bitwise(gpu, port, data_factor
         assert np.array_equal(a, b)
 
 
-def test_tma_pipeline_equals_register_pipeline_bitwise(gpu, port, data_factory):
-    """The two ways of feeding the sweep (bulk async copies into a shared-memory ring vs. a register ring)
-    use the same reduction tree: identical factors and residual, for several panel / chunk geometries."""
+def test_all_pipelines_bitwise_equal(gpu, port, data_factory):
+    """The three ways of feeding the sweep (cp.async producer warps or one bulk-copy descriptor per item into a
+    shared-memory slot ring, or a register ring) use the same reduction tree: identical factors and residual,
+    for several panel / chunk geometries."""
     for shape, kw in (("ml100k", dict()), ("ml100k", dict(panel_rows=256, chunk=64)), ("small", dict(panel_rows=64, chunk=16))):
         d = data_factory(shape)
         k = 5
         W0 = port.initial_col(k, d["rows"])
         outs = []
-        for pipeline in (0, 1):
+        for pipeline in (0, 1, 2):
             with gpu.Session(d, gpu.make_params(k=k, lam=0.05, maxinner=2, pipeline=pipeline, **kw)) as s:
                 s.set_factors(W0)
                 s.iterate(3)
                 outs.append(s.get_factors() + s.get_values())
-        for a, b in zip(*outs):
-            assert np.array_equal(a, b)
+        for other in outs[1:]:
+            for a, b in zip(outs[0], other):
+                assert np.array_equal(a, b)
 
 
 def test_panel_geometry_does_not_change_residual_and_barely_factors(gpu, port, data_factory):
