@@ -245,7 +245,17 @@ namespace tma {
 constexpr uint32_t kChunkMax = 512;                                  // largest item the slots hold
 constexpr uint32_t kSlotHeader = 64;
 constexpr uint32_t kSlotBytes = kSlotHeader + kChunkMax * 2 + kChunkMax * 4;  // 3136: 784 words = 16 mod 32 banks
-constexpr uint32_t kSpinLimit = 1u << 26;
+constexpr uint32_t kSpinLimit = 1u << 24;
+
+// First protocol timeout of a launch is recorded here (code, block, warp, lane, item n, slot, round, observed)
+// and the thread leaves the kernel: results are then wrong, but nothing hangs and the host can report it.
+__device__ unsigned int g_timeout[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+__device__ __forceinline__ void report_timeout(unsigned code, unsigned n, unsigned slot, unsigned round, unsigned seen) {
+    if (atomicCAS(&g_timeout[0], 0u, code) == 0u) {
+        g_timeout[1] = blockIdx.x; g_timeout[2] = threadIdx.x >> 5; g_timeout[3] = threadIdx.x & 31;
+        g_timeout[4] = n; g_timeout[5] = slot; g_timeout[6] = round; g_timeout[7] = seen;
+    }
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -273,6 +283,14 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity))
         if (++spins > kSpinLimit) __trap();
+}
+// bounded wait that reports and returns false instead of trapping (cp.async pipeline)
+__device__ __forceinline__ bool mbar_wait_report(uint32_t bar, uint32_t parity, unsigned code, unsigned n, unsigned slot,
+                                                 unsigned round) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity))
+        if (++spins > kSpinLimit) { report_timeout(code, n, slot, round, 0u); return false; }
+    return true;
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
@@ -456,8 +474,8 @@ __global__ void __launch_bounds__(1024, 1) k_panel_sweep_tma(PanelSweepArgs a) {
 // (LDGSTS, L1-bypassing) — one warp-wide instruction moves 32 x 16 bytes from arbitrary addresses, which
 // suits work items of a few hundred entries far better than one bulk-copy descriptor per item (measured:
 // profiles/README.md).  A producer warp handles a batch of four items at a time, one per 8-lane group,
-// exactly like the consumers; each lane signals the slot's `full` mbarrier when its own copies have landed
-// (cp.async.mbarrier.arrive.noinc), so the barrier expects 8 arrivals.
+// exactly like the consumers; each lane arrives on the slot's `full` mbarrier once its own copies have landed
+// (cp.async groups + wait_group), so the barrier expects 8 arrivals.
 //   slot_round[s]  ring round (+1) the slot is currently armed for, written by the producer after it has
 //                  waited for the slot's previous occupant to be consumed; a consumer waits for its round to
 //                  show up there before it issues the parity wait (which would otherwise alias the previous
@@ -467,9 +485,6 @@ namespace tma {
 constexpr int kProducerWarps = 4;
 __device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
-    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
 }  // namespace tma
 
@@ -536,16 +551,22 @@ __global__ void __launch_bounds__(1024, 1) k_panel_sweep_async(PanelSweepArgs a)
 
             if (warp < kProducerWarps) {
                 // ---------------- producers: warp w feeds batches w, w+P, w+2P, ... of this panel range ----------------
+                // Each lane commits its copies of a batch as one cp.async group and signals the slot's `full`
+                // barrier two batches later, after cp.async.wait_group has retired that group: up to three
+                // batches per lane group are in flight.  (cp.async.mbarrier.arrive.noinc was measured to fire
+                // early when a lane has tens of copies outstanding; the explicit wait is exact.)
                 uint32_t i0 = ib + 4u * (uint32_t)warp;
                 uint4 d = make_uint4(0u, 0u, 0u, 0u);
                 if (i0 + grp < pe) d = __ldg(items + i0 + grp);
+                uint32_t pb0 = 0u, pb1 = 0u;  // `full` barriers of this lane's previous two batches (0 = none)
                 while (i0 < pe) {
                     const uint32_t i0n = i0 + 4u * kProducerWarps;
                     uint4 dn = make_uint4(0u, 0u, 0u, 0u);
                     if (i0n + grp < pe) dn = __ldg(items + i0n + grp);  // next batch's descriptors, one batch ahead
+                    uint32_t cur = 0u;
                     if (d.y != 0u) {
                         const uint32_t n = i0 + grp - ib0, slot = n % NS, round = n / NS;
-                        mbar_wait(empty_u32 + 8u * slot, (round & 1u) ^ 1u);  // the slot's previous occupant was read
+                        if (!mbar_wait_report(empty_u32 + 8u * slot, (round & 1u) ^ 1u, 1u, n, slot, round)) return;  // previous occupant read
                         const uint32_t sbase = slots_u32 + slot * kSlotBytes;
                         if (sl == 0) {
                             *reinterpret_cast<uint4*>(slots + slot * kSlotBytes) = d;
@@ -557,11 +578,18 @@ __global__ void __launch_bounds__(1024, 1) k_panel_sweep_async(PanelSweepArgs a)
                         for (uint32_t c = 16u * (uint32_t)sl; c < nbi; c += 128u) cp_async_16(sbase + kSlotHeader + c, gi + c);
                         for (uint32_t c = 16u * (uint32_t)sl; c < nbv; c += 128u)
                             cp_async_16(sbase + kSlotHeader + kChunkMax * 2u + c, gv + c);
-                        cp_async_arrive_noinc(full_u32 + 8u * slot);  // fires when this lane's copies have landed
+                        cur = full_u32 + 8u * slot;
                     }
+                    asm volatile("cp.async.commit_group;" ::: "memory");
+                    asm volatile("cp.async.wait_group 2;" ::: "memory");  // the batch committed two rounds ago has landed
+                    if (pb1 != 0u) mbar_arrive(pb1);
+                    pb1 = pb0; pb0 = cur;
                     i0 = i0n;
                     d = dn;
                 }
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+                if (pb1 != 0u) mbar_arrive(pb1);
+                if (pb0 != 0u) mbar_arrive(pb0);
             } else {
                 // ---------------- consumers: four items per warp, one per 8-lane group ----------------
                 for (;;) {
@@ -579,11 +607,17 @@ __global__ void __launch_bounds__(1024, 1) k_panel_sweep_async(PanelSweepArgs a)
                         slot = n % NS;
                         uint32_t spins = 0;
                         while (slot_round[slot] != round + 1u)  // not armed for this round yet
-                            if (++spins > kSpinLimit) __trap();
-                        mbar_wait(full_u32 + 8u * slot, round & 1u);  // descriptor + indices + values have landed
+                            if (++spins > kSpinLimit) { report_timeout(2u, n, slot, round, slot_round[slot]); return; }
+                        if (!mbar_wait_report(full_u32 + 8u * slot, round & 1u, 3u, n, slot, round)) return;  // data has landed
                         sb = slots + slot * kSlotBytes;
                         d = *reinterpret_cast<const uint4*>(sb);
                     }
+#ifdef MF_DEBUG_ASSERT
+                    if (have && ((d.x & 7u) || d.y > kChunkMax || (d.y & 7u) || d.y == 0u || ((uintptr_t)sb & 15u))) {
+                        report_timeout(12u, d.x, d.y, mine, slot);
+                        return;
+                    }
+#endif
                     consume_slot<MODE>(a, d, sb, sl, sm_new, sm_add, sm_old);
                     __syncwarp();  // every lane of the group has finished reading the slot
                     if (have && sl == 0) mbar_arrive(empty_u32 + 8u * slot);
@@ -722,6 +756,17 @@ int launch_direct(const DirectSweepArgs& a, int sm_count, cudaStream_t st) {
 }
 
 }  // namespace
+
+int panel_timeout_report(char* buf, size_t n) {
+    unsigned int h[8] = {0};
+    if (cudaMemcpyFromSymbol(h, tma::g_timeout, sizeof(h)) != cudaSuccess) return 0;
+    if (h[0] == 0) return 0;
+    snprintf(buf, n, "pipeline timeout: code %u (1 producer/empty, 2 consumer/armed, 3 consumer/full) block %u warp %u lane %u item %u slot %u round %u seen %u",
+             h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7]);
+    unsigned int z[8] = {0};
+    cudaMemcpyToSymbol(tma::g_timeout, z, sizeof(z));
+    return 1;
+}
 
 int panel_sweep_vectors(int mode) {
     int n = 0;

@@ -47,6 +47,7 @@ struct DirectSweepArgs {
     float* out;  // already offset to this shard's first segment
 };
 
+int panel_timeout_report(char* buf, size_t n);  // 1 + message when a pipeline wait timed out since the last call
 int panel_sweep_vectors(int mode);
 size_t panel_sweep_smem(int mode, int panel_rows);
 int panel_sweep(int mode, const PanelSweepArgs& a, int ncta, int threads, int chunk, int pipeline, cudaStream_t st);

@@ -580,6 +580,10 @@ int mf_session_ccdpp_iterate(mf_session* s, int n_outer, mf_iter_stats* stats) {
         total = ms * 1e-3;
         s->timer.collect(s->fam_seconds, s->fam_launches);
         s->last_seconds = total;
+        {
+            char msg[256];
+            if (s->panel && panel_timeout_report(msg, sizeof(msg))) { set_error("%s", msg); return MF_ERR_STATE; }
+        }
         return MF_OK;
     }
     for (int it = 0; it < n_outer; ++it) {
