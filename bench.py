@@ -64,7 +64,8 @@ def parse_args():
     ap.add_argument("--no-launch-timing", action="store_true")
     ap.add_argument("--panel-rows", type=int, default=0)
     ap.add_argument("--chunk", type=int, default=0)
-    ap.add_argument("--pipeline", default="async", choices=["async", "registers", "tma"])
+    ap.add_argument("--pipeline", default="registers", choices=["registers", "async", "tma"])
+    ap.add_argument("--timing-stride", type=int, default=8, help="per-launch CUDA events on every n-th rank only")
     return ap.parse_args()
 
 
@@ -90,7 +91,10 @@ def config_dict(args, extra=None):
 # clocks
 # ---------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi sampling in the background (100 ms period).  It is started before the warm-up so that it is
+    already running when the (short) timed region begins; only samples whose timestamp falls inside the timed
+    region are used."""
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self):
@@ -105,34 +109,42 @@ class ClockSampler:
         self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
                                      stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
 
-    def stop(self, gpu_indices):
+    def stop(self, gpu_indices, t_begin, t_end):
+        import datetime
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.25)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        sm, sm_all, mx, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        lo = datetime.datetime.fromtimestamp(t_begin - 0.11)
+        hi = datetime.datetime.fromtimestamp(t_end + 0.11)
         for line in open(self.path):
             f = [x.strip() for x in line.split(",")]
-            if len(f) < 9:
+            if len(f) < 10:
                 continue
             try:
-                if int(f[0]) not in gpu_indices:
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f")
+                if int(f[1]) not in gpu_indices:
                     continue
-                sm.append(float(f[1])); mx.append(float(f[2]))
+                clk, cmax = float(f[2]), float(f[3])
             except ValueError:
                 continue
-            for name, v in zip(names, f[5:9]):
+            sm_all.append(clk)
+            if not (lo <= ts <= hi):
+                continue
+            sm.append(clk); mx.append(cmax)
+            for name, v in zip(names, f[6:10]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         os.unlink(self.path)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "samples_whole_run": len(sm_all), "reasons": sorted(reasons)}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -250,7 +262,7 @@ def run_b200_arm(args):
                              schedule=pkg.SCHEDULE_REFERENCE if args.schedule == "reference" else pkg.SCHEDULE_FUSED,
                              layout=pkg.LAYOUT_DIRECT if args.layout == "direct" else pkg.LAYOUT_PANEL,
                              panel_rows=args.panel_rows, chunk=args.chunk, no_launch_timing=int(args.no_launch_timing),
-                             pipeline={"async": 0, "registers": 1, "tma": 2}[args.pipeline])
+                             pipeline={"registers": 0, "async": 1, "tma": 2}[args.pipeline], timing_stride=args.timing_stride)
     nccl_id = None
     if world > 1:
         idt = torch.zeros(128, dtype=torch.uint8, device=dev)
@@ -277,24 +289,26 @@ def run_b200_arm(args):
     torch.cuda.empty_cache()
 
     # ---- warm-up, then K timed steps bracketed by barrier + synchronize
-    if args.warmup > 0:
-        sess.iterate(args.warmup, want_stats=False)
     sampler = ClockSampler()
-    barrier()
     if rank == 0:
         sampler.start()
+    if args.warmup > 0:
+        sess.iterate(args.warmup, want_stats=False)
+    barrier()
+    t_begin = time.time()
     t0 = time.perf_counter()
     sess.iterate(args.steps, want_stats=False)
     barrier()
     wall = time.perf_counter() - t0
-    clocks = sampler.stop(set(range(world))) if rank == 0 else None
+    t_end = time.time()
+    clocks = sampler.stop(set(range(world)), t_begin, t_end) if rank == 0 else None
     dev_s = max_over_ranks(sess.last_seconds())
     wall = max_over_ranks(wall)
     kt = sess.kernel_times()
     rmse = sess.rmse()
     sec_per_iter = dev_s / args.steps
 
-    launches = int(sum(kt[n] for n in kt if n.endswith("_launches") and not n.startswith("collective")))
+    launches = int(kt["total_launches"])  # every kernel the library launched in the timed region (sweeps + finalize)
     fam = {}
     if als and kt["als_launches"]:
         # Gram + RHS flops of one iteration (symmetric count): 2*nnz*k*(k+1) + 4*nnz*k, both half-steps
@@ -305,6 +319,12 @@ def run_b200_arm(args):
     for name in ("solve", "fused", "update"):
         if kt[name + "_launches"]:
             fam[name] = (kt[name + "_s"], kt[name + "_launches"], kt[name + "_bytes"])
+    # launches of each family in one outer iteration of the schedule that ran
+    if args.schedule == "fused":
+        per_step = {"solve": 2 * k * (T - 1), "fused": 2 * k, "update": 0, "finalize": 2 * k * T}
+    else:
+        per_step = {"solve": 2 * k * T, "fused": 0, "update": 4 * k, "finalize": 2 * k * T}
+    per_step["collective"] = 2 * k * T if world > 1 else 0
     roofline = None
     if fam:
         top = max(fam, key=lambda n: fam[n][0])
@@ -326,11 +346,12 @@ def run_b200_arm(args):
         roofline = {"bound": "hbm", "kernel": f"ccd {top} sweep ({args.layout} layout)", "achieved": achieved, "peak": peak,
                     "unit": "GB/s", "frac": achieved / peak, "peak_source": "measured" if peaks else "fallback",
                     "traffic": traffic, "bytes_per_launch": nbytes, "avg_launch_ms": avg * 1e3, "launches": n,
-                    "share_of_step": secs / dev_s if dev_s > 0 else None,
+                    "share_of_step": (avg * per_step[top]) / sec_per_iter if sec_per_iter > 0 else None,
+                    "timing": f"CUDA events around the launches of every {max(args.timing_stride, 1)}-th rank in the timed region",
                     "achieved_at_survey_bytes": survey_bytes / avg / 1e9,
-                    "families_ms_per_step": {f: fam[f][0] / args.steps * 1e3 for f in fam} |
-                                            {"finalize": kt["finalize_s"] / args.steps * 1e3,
-                                             "collective": kt["collective_s"] / args.steps * 1e3}}
+                    "families_ms_per_step": {f: fam[f][0] / fam[f][1] * per_step[f] * 1e3 for f in fam} |
+                                            {"finalize": kt["finalize_s"] / max(kt["finalize_launches"], 1) * per_step["finalize"] * 1e3,
+                                             "collective": kt["collective_s"] / max(kt["collective_launches"], 1) * per_step["collective"] * 1e3}}
 
     # ---- end to end through the public drop-in call, host buffers, every copy inside the timed region
     e2e = None

@@ -788,14 +788,14 @@ int panel_sweep(int mode, const PanelSweepArgs& a_in, int ncta, int threads, int
         set_error("panel sweep mode %d needs %zu bytes of shared memory (panel_rows=%u)", mode, vec, a.panel_rows);
         return MF_ERR_ARG;
     }
-    if (pipeline != MF_PIPELINE_REGISTERS && chunk <= (int)tma::kChunkMax) {
+    if (pipeline != MF_PIPELINE_REGISTERS && chunk <= (int)tma::kChunkMax) {  // experimental slot-ring pipelines
         // the slot ring gets whatever shared memory the panel vectors leave (at most 64 slots); per slot: data, two
         // mbarriers, one round word
         const size_t vec_al = (vec + 127) & ~(size_t)127;
         const size_t per_slot = tma::kSlotBytes + 16 + 4;
         size_t ns = (cap - vec_al) / per_slot;
         if (ns > 64) ns = 64;
-        if (ns >= 32) {  // the bulk-copy producer arms 32 slots per round: fewer slots could deadlock it against itself
+        if (ns >= 40) {  // fewer slots could deadlock the producers against their own un-signalled batches
             a.nslots = (uint32_t)ns;
             const size_t smem = vec_al + ns * per_slot;
 #define MF_DISPATCH(LAUNCH)                                                                                         \

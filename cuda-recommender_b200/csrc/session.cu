@@ -29,6 +29,7 @@ cudaEvent_t FamilyTimer::take() {
     return pool[used++];
 }
 void FamilyTimer::start(int fam) {
+    if (fam != F_COLLECTIVE) ++launched;
     if (!enabled) return;
     open_fam = fam;
     open_ev = take();
@@ -559,8 +560,11 @@ int mf_session_ccdpp_iterate(mf_session* s, int n_outer, mf_iter_stats* stats) {
     MF_REQUIRE(s && n_outer >= 0, "bad argument");
     if (s->prm.solver_type != MF_SOLVER_CCD) { set_error("not a CCD++ session"); return MF_ERR_STATE; }
     MF_CUDA(cudaSetDevice(s->device));
-    s->timer.enabled = s->prm.no_launch_timing == 0;
+    const bool timing_on = s->prm.no_launch_timing == 0;
+    const int tstride = s->prm.timing_stride > 1 ? s->prm.timing_stride : 1;
+    s->timer.enabled = timing_on;
     for (int f = 0; f < F_COUNT; ++f) { s->fam_seconds[f] = 0; s->fam_launches[f] = 0; }
+    s->timer.launched = 0;
     double total = 0.0;
     if (!stats) {
         // no per-iteration report wanted: one event pair around all n_outer iterations, one sync
@@ -568,6 +572,7 @@ int mf_session_ccdpp_iterate(mf_session* s, int n_outer, mf_iter_stats* stats) {
         for (int it = 0; it < n_outer; ++it) {
             const bool add = s->outer_done > 0;
             for (int t = 0; t < s->k; ++t) {
+                s->timer.enabled = timing_on && (t % tstride == 0);
                 if (s->prm.schedule == MF_SCHEDULE_REFERENCE) MF_TRY(ccd_rank_reference(s, t, add));
                 else MF_TRY(ccd_rank_fused(s, t, add));
             }
@@ -592,9 +597,11 @@ int mf_session_ccdpp_iterate(mf_session* s, int n_outer, mf_iter_stats* stats) {
         memcpy(before, s->fam_seconds, sizeof(before));
         MF_CUDA(cudaEventRecord(s->ev_a, s->st));
         for (int t = 0; t < s->k; ++t) {
+            s->timer.enabled = timing_on && (t % tstride == 0);
             if (s->prm.schedule == MF_SCHEDULE_REFERENCE) MF_TRY(ccd_rank_reference(s, t, add));
             else MF_TRY(ccd_rank_fused(s, t, add));
         }
+        s->timer.enabled = timing_on;
         MF_CUDA(cudaEventRecord(s->ev_b, s->st));
         MF_CUDA(cudaStreamSynchronize(s->st));
         float ms = 0.f;
@@ -702,6 +709,7 @@ int mf_session_kernel_times(mf_session* s, mf_kernel_times* out) {
         out->fused_bytes = (sweep_bytes(s, s->csc, kSolve | kSub | kAdd) + sweep_bytes(s, s->csr, kSolve | kSub | kAdd | kAddSep)) / 2;
         out->update_bytes = (sweep_bytes(s, s->csc, kSub) + sweep_bytes(s, s->csr, kSub)) / 2;
     }
+    out->total_launches = s->timer.launched;
     return MF_OK;
 }
 

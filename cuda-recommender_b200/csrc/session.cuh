@@ -17,6 +17,7 @@ struct FamilyTimer {
     size_t used = 0;
     std::vector<Span> spans;
     bool enabled = true;
+    int64_t launched = 0;  // every start() call, timed or not
     cudaStream_t st = nullptr;
     int open_fam = -1;
     cudaEvent_t open_ev = nullptr;

@@ -50,9 +50,10 @@ enum {
 enum { MF_SOLVER_CCD = 0, MF_SOLVER_ALS = 1 };               /* src/pmf.h:6 solvertype */
 enum { MF_SCHEDULE_FUSED = 0, MF_SCHEDULE_REFERENCE = 1 };   /* REFERENCE = CCD_CUDA.cu:339-378 launch order */
 enum { MF_LAYOUT_PANEL = 0, MF_LAYOUT_DIRECT = 1 };          /* HBM layout of the rating copies */
-/* how the panel sweep feeds its warps: producer warps with cp.async into a shared-memory slot ring
- * (default), a per-lane register ring, or one bulk-copy (TMA) descriptor per work item into the same slot ring */
-enum { MF_PIPELINE_ASYNC = 0, MF_PIPELINE_REGISTERS = 1, MF_PIPELINE_TMA_BULK = 2 };
+/* how the panel sweep feeds its warps: a per-lane register ring (default, fastest measured), or —
+ * kept for comparison — producer warps with cp.async / one bulk-copy (TMA) descriptor per work item into a
+ * shared-memory slot ring guarded by mbarriers */
+enum { MF_PIPELINE_REGISTERS = 0, MF_PIPELINE_ASYNC = 1, MF_PIPELINE_TMA_BULK = 2 };
 enum { MF_SIDE_CSC = 0, MF_SIDE_CSR = 1 };                   /* CSC: columns solve v / H;  CSR: rows solve u / W */
 
 /* Paired CSR + CSC of the same ratings — src/pmf_util.h:34-149 (SparseMatrix). */
@@ -98,7 +99,8 @@ typedef struct mf_params {
     int32_t nmf_project;       /* 1: clamp solved coordinates at 0 (extension; the reference never does) */
     int32_t no_launch_timing;  /* 1: skip the per-launch CUDA events (mf_kernel_times stays zero) */
     int32_t pipeline;          /* MF_PIPELINE_* */
-    int32_t reserved[7];
+    int32_t timing_stride;     /* CCD++: per-launch events only on every timing_stride-th rank (0/1 = every rank) */
+    int32_t reserved[6];
 } mf_params;
 
 /* One line of the reference's per-iteration report (CCD_CUDA.cu:405, ALS_CUDA.cu:360). */
@@ -109,8 +111,9 @@ typedef struct mf_iter_stats {
     double rmse_time;   /* seconds                                                      */
 } mf_iter_stats;
 
-/* Per-kernel-family device times accumulated by the last iterate call (CUDA events on the
- * session stream around every launch of that family). */
+/* Per-kernel-family device times accumulated by the last iterate call (CUDA events on the session stream
+ * around the launches of that family; with timing_stride > 1 only the launches of every n-th rank are timed,
+ * *_launches counts the timed ones). */
 typedef struct mf_kernel_times {
     double solve_s;        int64_t solve_launches;        /* read-only solve sweeps               */
     double fused_s;        int64_t fused_launches;        /* update(s)+solve sweeps               */
@@ -120,6 +123,7 @@ typedef struct mf_kernel_times {
     double rmse_s;         int64_t rmse_launches;
     double collective_s;   int64_t collective_launches;   /* NCCL all-gathers (multi-GPU)         */
     int64_t solve_bytes, fused_bytes, update_bytes;       /* HBM bytes one launch of the family must move */
+    int64_t total_launches;  /* every kernel launched by the last iterate call, timed or not (sweeps, finalize, ALS, RMSE) */
 } mf_kernel_times;
 
 typedef struct mf_session mf_session;
