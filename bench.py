@@ -64,6 +64,7 @@ def parse_args():
     ap.add_argument("--no-launch-timing", action="store_true")
     ap.add_argument("--panel-rows", type=int, default=0)
     ap.add_argument("--chunk", type=int, default=0)
+    ap.add_argument("--pad", type=int, default=0)
     ap.add_argument("--pipeline", default="registers", choices=["registers", "async", "tma"])
     ap.add_argument("--timing-stride", type=int, default=8, help="per-launch CUDA events on every n-th rank only")
     return ap.parse_args()
@@ -262,7 +263,7 @@ def run_b200_arm(args):
                              schedule=pkg.SCHEDULE_REFERENCE if args.schedule == "reference" else pkg.SCHEDULE_FUSED,
                              layout=pkg.LAYOUT_DIRECT if args.layout == "direct" else pkg.LAYOUT_PANEL,
                              panel_rows=args.panel_rows, chunk=args.chunk, no_launch_timing=int(args.no_launch_timing),
-                             pipeline={"registers": 0, "async": 1, "tma": 2}[args.pipeline], timing_stride=args.timing_stride)
+                             pipeline={"registers": 0, "async": 1, "tma": 2}[args.pipeline], timing_stride=args.timing_stride, pad_entries=args.pad)
     nccl_id = None
     if world > 1:
         idt = torch.zeros(128, dtype=torch.uint8, device=dev)
@@ -370,7 +371,7 @@ def run_b200_arm(args):
         Ht = torch.zeros((k, cols), dtype=torch.float32).pin_memory()
         p2 = pkg.make_params(pkg.SOLVER_CCD, k=k, lam=lam, maxiter=E, maxinner=T, device=local_rank,
                              schedule=params.schedule, layout=params.layout, panel_rows=args.panel_rows, chunk=args.chunk,
-                             no_launch_timing=1, pipeline=params.pipeline)
+                             no_launch_timing=1, pipeline=params.pipeline, pad_entries=args.pad)
         h2d = sum(v.nbytes for kk, v in pinned.items() if isinstance(v, np.ndarray) and not kk.startswith("coo_")) + Wt.numel() * 4
         d2h = (Wt.numel() + Ht.numel()) * 4 + 8 * E
         barrier()

@@ -47,7 +47,7 @@ class mf_params(C.Structure):
                 ("verbose", C.c_int32), ("do_nmf", C.c_int32), ("nBlocks", C.c_uint32), ("nThreadsPerBlock", C.c_uint32),
                 ("device", C.c_int32), ("schedule", C.c_int32), ("layout", C.c_int32), ("quiet", C.c_int32),
                 ("panel_rows", C.c_int32), ("chunk", C.c_int32), ("nmf_project", C.c_int32),
-                ("no_launch_timing", C.c_int32), ("pipeline", C.c_int32), ("timing_stride", C.c_int32), ("reserved", C.c_int32 * 6)]
+                ("no_launch_timing", C.c_int32), ("pipeline", C.c_int32), ("timing_stride", C.c_int32), ("pad_entries", C.c_int32), ("reserved", C.c_int32 * 5)]
 
 
 class mf_iter_stats(C.Structure):
@@ -182,13 +182,13 @@ class Ratings:
 
 
 def make_params(solver=SOLVER_CCD, k=10, lam=0.1, maxiter=5, maxinner=1, device=0, schedule=SCHEDULE_FUSED,
-                layout=LAYOUT_PANEL, quiet=True, panel_rows=0, chunk=0, nmf_project=0, no_launch_timing=0, pipeline=0, timing_stride=0):
+                layout=LAYOUT_PANEL, quiet=True, panel_rows=0, chunk=0, nmf_project=0, no_launch_timing=0, pipeline=0, timing_stride=0, pad_entries=0):
     p = mf_params()
     lib().mf_params_default(C.byref(p))
     p.solver_type, p.k, p.lambda_, p.maxiter, p.maxinneriter = solver, k, lam, maxiter, maxinner
     p.device, p.schedule, p.layout, p.quiet = device, schedule, layout, int(quiet)
     p.panel_rows, p.chunk, p.nmf_project, p.no_launch_timing = panel_rows, chunk, nmf_project, no_launch_timing
-    p.pipeline, p.timing_stride = pipeline, timing_stride
+    p.pipeline, p.timing_stride, p.pad_entries = pipeline, timing_stride, pad_entries
     return p
 
 

@@ -226,7 +226,8 @@ __global__ void __launch_bounds__(1024, 1) k_panel_sweep(PanelSweepArgs a) {
 }
 
 // =============================================================================================
-// TMA pipeline variant of the panel sweep (the default): warp 0 of the CTA is a producer that moves
+// TMA bulk-copy variant of the panel sweep (MF_PIPELINE_TMA_BULK; measured alternative, not the default —
+// DESIGN.md §4): warp 0 of the CTA is a producer that moves
 // every work item of the CTA's range from HBM into a ring of shared-memory slots with 1-D bulk
 // async copies (cp.async.bulk, completion counted on an mbarrier per slot); warps 1..31 consume the
 // slots.  The HBM stream is thereby decoupled from the arithmetic: ~40-58 items (70-100 KB) are in
@@ -469,11 +470,10 @@ __global__ void __launch_bounds__(1024, 1) k_panel_sweep_tma(PanelSweepArgs a) {
 }
 
 // =============================================================================================
-// cp.async pipeline variant (the default): same slot ring and the same consumers as the bulk-copy
+// cp.async pipeline variant (MF_PIPELINE_ASYNC; measured alternative, not the default): same slot ring and the
+// same consumers as the bulk-copy
 // kernel above, but the ring is fed by kProducerWarps producer WARPS using 16-byte cp.async.cg copies
-// (LDGSTS, L1-bypassing) — one warp-wide instruction moves 32 x 16 bytes from arbitrary addresses, which
-// suits work items of a few hundred entries far better than one bulk-copy descriptor per item (measured:
-// profiles/README.md).  A producer warp handles a batch of four items at a time, one per 8-lane group,
+// (LDGSTS, L1-bypassing) — one warp-wide instruction moves 32 x 16 bytes from arbitrary addresses.  A producer warp handles a batch of four items at a time, one per 8-lane group,
 // exactly like the consumers; each lane arrives on the slot's `full` mbarrier once its own copies have landed
 // (cp.async groups + wait_group), so the barrier expects 8 arrivals.
 //   slot_round[s]  ring round (+1) the slot is currently armed for, written by the producer after it has

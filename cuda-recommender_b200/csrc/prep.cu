@@ -8,7 +8,7 @@
 namespace mf {
 namespace {
 
-constexpr int kPad = 8;        // piece padding granule (entries)
+constexpr int kPad = 8;        // unit of lengths in the bins / cost model; every padded length is a multiple of it
 constexpr uint32_t kCost0 = 8; // per-item fixed cost in units of 8 entries (descriptor, reduce, store)
 
 __device__ __forceinline__ uint32_t lower_bound_u32(const uint32_t* __restrict__ a, uint32_t lo, uint32_t hi,
@@ -21,7 +21,7 @@ __device__ __forceinline__ uint32_t lower_bound_u32(const uint32_t* __restrict__
 }
 
 // one thread per piece q = p*nseg + s
-__global__ void k_piece_count(int64_t nseg, int npanels, uint32_t panel_rows, uint32_t chunk,
+__global__ void k_piece_count(int64_t nseg, int npanels, uint32_t panel_rows, uint32_t chunk, uint32_t pad,
                               const uint32_t* __restrict__ ptr, const uint32_t* __restrict__ idx,
                               uint32_t* __restrict__ piece_first, uint32_t* __restrict__ padded,
                               uint32_t* __restrict__ nitem) {
@@ -35,7 +35,7 @@ __global__ void k_piece_count(int64_t nseg, int npanels, uint32_t panel_rows, ui
     uint32_t first = lower_bound_u32(idx, lo, hi, (uint32_t)k0);
     uint32_t last = k1 > 0xffffffffull ? hi : lower_bound_u32(idx, first, hi, (uint32_t)k1);
     uint32_t cnt = last - first;
-    uint32_t pd = (cnt + kPad - 1) / kPad * kPad;
+    uint32_t pd = (cnt + pad - 1) / pad * pad;
     piece_first[q] = first;
     padded[q] = pd;
     nitem[q] = (pd + chunk - 1) / chunk;
@@ -271,6 +271,7 @@ int side_check_sorted(const Side& s, bool* sorted, cudaStream_t st) {
 int side_build_panels(Side& s, int panel_rows, int chunk, int ncta, cudaStream_t st) {
     MF_REQUIRE(panel_rows > 0 && panel_rows <= 16376 && panel_rows % 8 == 0, "panel_rows must be a multiple of 8 in (0, 16376]");
     MF_REQUIRE(chunk >= 8 && chunk % 8 == 0, "chunk must be a positive multiple of 8");
+    if (s.pad < kPad || s.pad % kPad != 0 || chunk % s.pad != 0) s.pad = kPad;
     MF_REQUIRE(ncta > 0, "ncta must be positive");
     s.panel_rows = panel_rows;
     s.chunk = chunk;
@@ -295,7 +296,7 @@ int side_build_panels(Side& s, int panel_rows, int chunk, int ncta, cudaStream_t
 
     trace_mark("    layout: index allocations");
     if (Q > 0)
-        k_piece_count<<<grid_for(Q, 256), 256, 0, st>>>(s.nseg, s.npanels, (uint32_t)panel_rows, (uint32_t)chunk, s.ptr,
+        k_piece_count<<<grid_for(Q, 256), 256, 0, st>>>(s.nseg, s.npanels, (uint32_t)panel_rows, (uint32_t)chunk, (uint32_t)s.pad, s.ptr,
                                                         s.idx, s.piece_first, padded, nitem);
     MF_CUDA(cudaGetLastError());
     MF_TRY(exclusive_scan_u32(padded, s.piece_ptr, (size_t)Q, tmp, st));

@@ -359,13 +359,14 @@ int create_impl(const mf_ratings* R, const mf_testset* T, const mf_params* param
         if (s->panel) {
             // Panel size.  Shared memory a sweep needs: CSC side up to 2 vectors (u_new, u_old), CSR side up to 3
             // (v_new, v_add, v_old).  Measured (profiles/README.md): panels that fill shared memory leave the SM
-            // almost no L1 for the rating streams and the updating sweeps slow down by 30-60 %; 12288 entries
-            // (48 KB per vector) is the sweet spot on B200.  Hard cap 16376: idx16 stores index*4.
+            // almost no L1 for the rating streams and the updating sweeps slow down by 30-60 %; 12-16 K entries
+            // (48-64 KB per vector) is the sweet spot on B200.  Hard cap 16376: idx16 stores index*4.
             int cap_c = std::min(panel_cap(2), 16376), cap_r = std::min(panel_cap(3), 16376);
-            const int want = params->panel_rows > 0 ? params->panel_rows / 8 * 8 : 12288;
+            const int want = params->panel_rows > 0 ? params->panel_rows / 8 * 8 : 16376;
             cap_c = std::min(cap_c, want);
             cap_r = std::min(cap_r, want);
             const int chunk = params->chunk > 0 ? std::max(8, params->chunk / 8 * 8) : 512;
+            s->csc.pad = s->csr.pad = params->pad_entries > 0 ? params->pad_entries : 32;
             if ((rc = side_build_panels(s->csc, choose_panel_rows(s->csc.gdim, std::max(cap_c, 8)), chunk, s->sm_count, s->st)) != MF_OK) return fail(rc);
             if ((rc = side_build_panels(s->csr, choose_panel_rows(s->csr.gdim, std::max(cap_r, 8)), chunk, s->sm_count, s->st)) != MF_OK) return fail(rc);
             trace_mark("  build both panel layouts");

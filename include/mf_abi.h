@@ -94,13 +94,14 @@ typedef struct mf_params {
     int32_t schedule;          /* MF_SCHEDULE_* (CCD++) */
     int32_t layout;            /* MF_LAYOUT_*   (CCD++) */
     int32_t quiet;             /* 1: do not print the per-iteration "[-INFO-] iteration num" line */
-    int32_t panel_rows;        /* 0 = default (12288), max 16376; factor entries per shared-memory panel */
+    int32_t panel_rows;        /* 0 = default and max (16376); factor entries per shared-memory panel */
     int32_t chunk;             /* 0 = default (512); max rating entries per work item */
     int32_t nmf_project;       /* 1: clamp solved coordinates at 0 (extension; the reference never does) */
     int32_t no_launch_timing;  /* 1: skip the per-launch CUDA events (mf_kernel_times stays zero) */
     int32_t pipeline;          /* MF_PIPELINE_* */
     int32_t timing_stride;     /* CCD++: per-launch events only on every timing_stride-th rank (0/1 = every rank) */
-    int32_t reserved[6];
+    int32_t pad_entries;       /* 0 = default (32): pieces are padded to a multiple of this many entries (8, 16, 32, 64) */
+    int32_t reserved[5];
 } mf_params;
 
 /* One line of the reference's per-iteration report (CCD_CUDA.cu:405, ALS_CUDA.cu:360). */

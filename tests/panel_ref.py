@@ -1,6 +1,6 @@
 """numpy restatement of the PANEL layout (cuda-recommender_b200/csrc/layout.cuh, prep.cu) — the
 integer-tier checker for the layout the GPU builds: pieces = (panel, segment) cuts of every segment,
-panel-major storage, 8-entry padding with idx16 = 4*panel_rows / val = 0 (indices stored as byte offsets), work items of <= chunk
+panel-major storage, pieces padded to `pad` entries with idx16 = 4*panel_rows / val = 0 (indices stored as byte offsets), work items of <= chunk
 entries, slots of a segment ordered (panel, chunk).  Test infrastructure only."""
 import numpy as np
 
@@ -20,11 +20,13 @@ def choose_panel_rows(gdim, cap):
 
 def session_panel_rows(gdim, side_is_csr, user_panel_rows=0):
     cap = min(panel_cap(3 if side_is_csr else 2), 16376)
-    want = user_panel_rows // 8 * 8 if user_panel_rows > 0 else 12288
+    want = user_panel_rows // 8 * 8 if user_panel_rows > 0 else 16376
     return choose_panel_rows(gdim, max(min(cap, want), 8))
 
 
-def panel_layout(ptr, idx, val, gdim, panel_rows, chunk):
+def panel_layout(ptr, idx, val, gdim, panel_rows, chunk, pad=32):
+    if pad < 8 or pad % 8 or chunk % pad:
+        pad = 8
     ptr = ptr.astype(np.int64)
     nseg = len(ptr) - 1
     P = max(1, -(-gdim // panel_rows))
@@ -38,7 +40,7 @@ def panel_layout(ptr, idx, val, gdim, panel_rows, chunk):
             a = ptr[s] + np.searchsorted(seg, lo_key, "left")
             b = ptr[s] + np.searchsorted(seg, hi_key, "left")
             cnt = b - a
-            pd = -(-cnt // 8) * 8
+            pd = -(-cnt // pad) * pad
             nit = -(-pd // chunk)
             pieces.append((p, s, a, cnt, pd, nit))
             seg_items[s] += nit
