@@ -633,38 +633,88 @@ __global__ void __launch_bounds__(1024, 1) k_panel_sweep_async(PanelSweepArgs a)
 // float*unsigned product as at src/CCD.cpp:112,120; empty segment -> 0 (src/CCD.cpp:8).
 // LANES = 1: one thread per segment (slots added in order); LANES = 32: one warp per segment, lane l adds
 // slots l, l+32, ... in order and the lanes are combined by an xor-butterfly — both are fixed trees.
+// Multi-GPU epilogue of the finalize kernel (fused solve -> exchange): the freshly solved coordinates are also
+// stored straight into every peer's copy of the factor vector over NVLink (CUDA IPC mappings, dist.cu), and
+// the last CTA to finish publishes this rank's epoch in every peer's flag word with a system-scope release.
+// The receiving side waits in k_exchange_wait.  No double buffering is needed: a rank can only produce the
+// next generation of a vector after it has received everybody's blocks of the other vector, and everybody
+// sends those only after their last sweep that read the old generation (sweeps alternate u / v).
+struct PushArgs {
+    float* const* peer_vec;      // [nranks] base of the same factor matrix (W or H) on every rank; nullptr = no push
+    unsigned* const* peer_flags; // [nranks] flag words of every rank
+    unsigned* ticket;            // local CTA counter (zero between launches)
+    int64_t row_off;             // element offset of out[0] inside the factor matrix
+    int rank, nranks;
+    unsigned epoch;
+};
+
 template <int LANES>
 __global__ void __launch_bounds__(256) k_finalize(int64_t nseg, const uint32_t* __restrict__ slot_ptr,
                                                   const float2* __restrict__ partials, const uint32_t* __restrict__ seg_ptr,
-                                                  float lambda, int nmf, float* __restrict__ out) {
+                                                  float lambda, int nmf, float* __restrict__ out, PushArgs push) {
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t s = tid / LANES;
     const int l = (int)(tid % LANES);
-    if (s >= nseg) return;
-    const uint32_t deg = seg_ptr[s + 1] - seg_ptr[s];
-    float g = 0.0f, h = 0.0f;
-    if (deg != 0u) {
-        const uint32_t hi = slot_ptr[s + 1];
-        for (uint32_t q = slot_ptr[s] + l; q < hi; q += LANES) {
-            const float2 pr = partials[q];
-            g += pr.x;
-            h += pr.y;
-        }
-    }
-    if (LANES > 1) {
-#pragma unroll
-        for (int o = 1; o < LANES; o <<= 1) {
-            g += __shfl_xor_sync(0xffffffffu, g, o);
-            h += __shfl_xor_sync(0xffffffffu, h, o);
-        }
-    }
-    if (l == 0) {
-        float r = 0.0f;
+    if (s < nseg) {
+        const uint32_t deg = seg_ptr[s + 1] - seg_ptr[s];
+        float g = 0.0f, h = 0.0f;
         if (deg != 0u) {
-            r = g / (lambda * deg + h);
-            if (nmf) r = fmaxf(r, 0.0f);
+            const uint32_t hi = slot_ptr[s + 1];
+            for (uint32_t q = slot_ptr[s] + l; q < hi; q += LANES) {
+                const float2 pr = partials[q];
+                g += pr.x;
+                h += pr.y;
+            }
         }
-        out[s] = r;
+        if (LANES > 1) {
+#pragma unroll
+            for (int o = 1; o < LANES; o <<= 1) {
+                g += __shfl_xor_sync(0xffffffffu, g, o);
+                h += __shfl_xor_sync(0xffffffffu, h, o);
+            }
+        }
+        if (l == 0) {
+            float r = 0.0f;
+            if (deg != 0u) {
+                r = g / (lambda * deg + h);
+                if (nmf) r = fmaxf(r, 0.0f);
+            }
+            out[s] = r;
+            if (push.peer_vec != nullptr) {
+                for (int p = 0; p < push.nranks; ++p)
+                    if (p != push.rank) push.peer_vec[p][push.row_off + s] = r;
+            }
+        }
+    }
+    if (push.peer_vec != nullptr) {
+        // every CTA: make its remote stores visible system-wide, then take a ticket; the last one signals the peers
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned t = atomicAdd(push.ticket, 1u);
+            if (t == gridDim.x - 1) {
+                *push.ticket = 0u;
+                __threadfence_system();
+                for (int p = 0; p < push.nranks; ++p)
+                    if (p != push.rank) {
+                        unsigned* f = push.peer_flags[p] + push.rank;
+                        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(push.epoch) : "memory");
+                    }
+            }
+        }
+    }
+}
+
+// waits until every peer has published `epoch` (or later) in this rank's flag words
+__global__ void k_exchange_wait(const unsigned* flags, int rank, int nranks, unsigned epoch) {
+    const int p = threadIdx.x;
+    if (p < nranks && p != rank) {
+        unsigned spins = 0, v = 0;
+        for (;;) {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + p) : "memory");
+            if ((int)(v - epoch) >= 0) break;
+            if (++spins > (1u << 27)) __trap();
+        }
     }
 }
 
@@ -830,12 +880,26 @@ int panel_sweep(int mode, const PanelSweepArgs& a_in, int ncta, int threads, int
 }
 
 int panel_finalize(int64_t nseg, int64_t nslots, const uint32_t* slot_ptr, const float2* partials, const uint32_t* seg_ptr,
-                   float lambda, int nmf, float* out, cudaStream_t st) {
-    if (nseg <= 0) return MF_OK;
+                   float lambda, int nmf, float* out, const FinalizePush* fp, cudaStream_t st) {
+    PushArgs push;
+    push.peer_vec = nullptr; push.peer_flags = nullptr; push.ticket = nullptr; push.row_off = 0; push.rank = 0; push.nranks = 1; push.epoch = 0;
+    if (fp && fp->peer_vec) {
+        push.peer_vec = fp->peer_vec; push.peer_flags = fp->peer_flags; push.ticket = fp->ticket; push.row_off = fp->row_off;
+        push.rank = fp->rank; push.nranks = fp->nranks; push.epoch = fp->epoch;
+    }
+    int64_t nthreads = nslots > 4 * nseg ? nseg * 32 : nseg;
+    if (nthreads < 1) nthreads = 1;  // a push launch must run even for an empty block: its peers wait for the flag
+    if (nseg <= 0 && !push.peer_vec) return MF_OK;
     if (nslots > 4 * nseg)  // many slots per segment (long columns cut by panels and chunks): a warp per segment
-        k_finalize<32><<<(unsigned)((nseg * 32 + 255) / 256), 256, 0, st>>>(nseg, slot_ptr, partials, seg_ptr, lambda, nmf, out);
+        k_finalize<32><<<(unsigned)((nthreads + 255) / 256), 256, 0, st>>>(nseg, slot_ptr, partials, seg_ptr, lambda, nmf, out, push);
     else
-        k_finalize<1><<<(unsigned)((nseg + 255) / 256), 256, 0, st>>>(nseg, slot_ptr, partials, seg_ptr, lambda, nmf, out);
+        k_finalize<1><<<(unsigned)((nthreads + 255) / 256), 256, 0, st>>>(nseg, slot_ptr, partials, seg_ptr, lambda, nmf, out, push);
+    MF_CUDA(cudaGetLastError());
+    return MF_OK;
+}
+
+int exchange_wait(const unsigned* flags, int rank, int nranks, unsigned epoch, cudaStream_t st) {
+    k_exchange_wait<<<1, 32 * ((nranks + 31) / 32), 0, st>>>(flags, rank, nranks, epoch);
     MF_CUDA(cudaGetLastError());
     return MF_OK;
 }

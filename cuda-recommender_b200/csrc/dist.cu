@@ -9,6 +9,7 @@
 // NCCL is bound at run time (dlopen of libnccl.so.2) so the library loads, and single-GPU sessions
 // run, on a box without NCCL, and so that inside a torch process the already-loaded NCCL is shared.
 #include <dlfcn.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "session.cuh"
@@ -19,7 +20,7 @@ namespace {
 typedef struct ncclComm* ncclComm_t;
 typedef struct { char internal[128]; } ncclUniqueId;
 enum { ncclSuccess = 0 };
-enum { ncclFloat32 = 7 };  // ncclDataType_t (nccl.h): int8 0, uint8 1, int32 2, uint32 3, int64 4, uint64 5, half 6, float 7
+enum { ncclInt8 = 0, ncclFloat32 = 7 };  // ncclDataType_t (nccl.h): int8 0, uint8 1, int32 2, uint32 3, int64 4, uint64 5, half 6, float 7
 
 struct Api {
     void* handle = nullptr;
@@ -29,6 +30,7 @@ struct Api {
     int (*GroupStart)() = nullptr;
     int (*GroupEnd)() = nullptr;
     int (*Broadcast)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
 };
 
@@ -57,6 +59,7 @@ int load_api() {
     MF_SYM(GroupStart, "ncclGroupStart")
     MF_SYM(GroupEnd, "ncclGroupEnd")
     MF_SYM(Broadcast, "ncclBroadcast")
+    MF_SYM(AllGather, "ncclAllGather")
     MF_SYM(GetErrorString, "ncclGetErrorString")
 #undef MF_SYM
     g_api = a;
@@ -77,6 +80,14 @@ int load_api() {
 struct Dist {
     ncclComm_t comm = nullptr;
     int rank = 0, nranks = 1;
+    // peer-to-peer exchange over NVLink (CUDA IPC mappings of every peer's factor buffers and flag words)
+    bool p2p = false;
+    std::vector<void*> opened;      // mappings to close
+    float** d_peerW = nullptr;      // [nranks] device array: W of every rank (own entry = own pointer)
+    float** d_peerH = nullptr;
+    unsigned** d_peerFlags = nullptr;  // [nranks] device array: flag words of every rank
+    unsigned* flags = nullptr;      // [nranks + 1] own flag words (flags[r] written by rank r) + block ticket
+    unsigned epoch = 0;             // exchanges issued so far
 };
 
 int dist_unique_id(void* id128) {
@@ -108,10 +119,77 @@ int dist_create(Dist** out, int rank, int nranks, const void* id128, int device)
 
 int dist_destroy(Dist* d) {
     if (!d) return MF_OK;
+    for (void* p : d->opened) cudaIpcCloseMemHandle(p);
+    if (d->d_peerW) cudaFree(d->d_peerW);
+    if (d->d_peerH) cudaFree(d->d_peerH);
+    if (d->d_peerFlags) cudaFree(d->d_peerFlags);
+    if (d->flags) cudaFree(d->flags);
     if (d->comm) g_api.CommDestroy(d->comm);
     delete d;
     return MF_OK;
 }
+
+// Maps every peer's W, H and flag words into this process (CUDA IPC over NVLink / NVSwitch) so that the finalize
+// kernel can store a freshly solved block straight into the peers' factor buffers (ccd_kernels.cu: k_finalize
+// push epilogue + k_exchange_wait).  The 64-byte IPC handles travel through one ncclAllGather.  Any failure
+// leaves p2p off and the NCCL broadcast path in use.
+int dist_setup_p2p(Dist* d, float* W, float* H, cudaStream_t st) {
+    if (!d || d->nranks <= 1) return MF_OK;
+    if (getenv("MF_NO_P2P")) return MF_OK;
+    const int P = d->nranks;
+    struct Handles { cudaIpcMemHandle_t w, h, f; };
+    static_assert(sizeof(Handles) == 192, "three 64-byte handles");
+    MF_TRY(dev_alloc(&d->flags, (size_t)P + 1));
+    MF_CUDA(cudaMemsetAsync(d->flags, 0, sizeof(unsigned) * ((size_t)P + 1), st));
+    Handles mine;
+    if (cudaIpcGetMemHandle(&mine.w, W) != cudaSuccess || cudaIpcGetMemHandle(&mine.h, H) != cudaSuccess ||
+        cudaIpcGetMemHandle(&mine.f, d->flags) != cudaSuccess) {
+        cudaGetLastError();
+        return MF_OK;  // no IPC on this system: stay on NCCL
+    }
+    Handles* d_all = nullptr;
+    MF_TRY(dev_alloc(&d_all, (size_t)P));
+    MF_CUDA(cudaMemcpyAsync(d_all + d->rank, &mine, sizeof(Handles), cudaMemcpyHostToDevice, st));
+    MF_NCCL(g_api.AllGather(d_all + d->rank, d_all, sizeof(Handles), ncclInt8, d->comm, st));
+    std::vector<Handles> all((size_t)P);
+    MF_CUDA(cudaMemcpyAsync(all.data(), d_all, sizeof(Handles) * (size_t)P, cudaMemcpyDeviceToHost, st));
+    MF_CUDA(cudaStreamSynchronize(st));
+    cudaFree(d_all);
+    std::vector<float*> pw((size_t)P), ph((size_t)P);
+    std::vector<unsigned*> pf((size_t)P);
+    bool ok = true;
+    for (int r = 0; r < P && ok; ++r) {
+        if (r == d->rank) { pw[r] = W; ph[r] = H; pf[r] = d->flags; continue; }
+        void *a = nullptr, *b = nullptr, *c = nullptr;
+        ok = cudaIpcOpenMemHandle(&a, all[r].w, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+        if (ok) { d->opened.push_back(a); ok = cudaIpcOpenMemHandle(&b, all[r].h, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess; }
+        if (ok) { d->opened.push_back(b); ok = cudaIpcOpenMemHandle(&c, all[r].f, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess; }
+        if (ok) d->opened.push_back(c);
+        pw[r] = (float*)a; ph[r] = (float*)b; pf[r] = (unsigned*)c;
+    }
+    if (!ok) {
+        cudaGetLastError();
+        for (void* p : d->opened) cudaIpcCloseMemHandle(p);
+        d->opened.clear();
+        return MF_OK;  // peers not reachable: stay on NCCL
+    }
+    MF_TRY(dev_alloc(&d->d_peerW, (size_t)P));
+    MF_TRY(dev_alloc(&d->d_peerH, (size_t)P));
+    MF_TRY(dev_alloc(&d->d_peerFlags, (size_t)P));
+    MF_CUDA(cudaMemcpy(d->d_peerW, pw.data(), sizeof(float*) * (size_t)P, cudaMemcpyHostToDevice));
+    MF_CUDA(cudaMemcpy(d->d_peerH, ph.data(), sizeof(float*) * (size_t)P, cudaMemcpyHostToDevice));
+    MF_CUDA(cudaMemcpy(d->d_peerFlags, pf.data(), sizeof(unsigned*) * (size_t)P, cudaMemcpyHostToDevice));
+    d->p2p = true;
+    return MF_OK;
+}
+
+bool dist_p2p(const Dist* d) { return d && d->p2p; }
+int dist_rank(const Dist* d) { return d ? d->rank : 0; }
+float* const* dist_peer_W(const Dist* d) { return d->d_peerW; }
+float* const* dist_peer_H(const Dist* d) { return d->d_peerH; }
+unsigned* const* dist_peer_flags(const Dist* d) { return d->d_peerFlags; }
+unsigned* dist_flags(const Dist* d) { return d->flags; }
+unsigned dist_next_epoch(Dist* d) { return ++d->epoch; }
 
 int dist_allgather_blocks(Dist* d, float* vec, const std::vector<int64_t>& bound, int64_t unit, cudaStream_t st) {
     if (!d || d->nranks <= 1) return MF_OK;

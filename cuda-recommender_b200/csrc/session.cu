@@ -139,7 +139,7 @@ int family_of(int mode) {
 }
 
 // one sweep of `mode` over side sd; when it solves, `out` (full-length vector) receives this shard's block
-int run_sweep(mf_session* s, Side& sd, int mode, const SweepVectors& v, float* out) {
+int run_sweep(mf_session* s, Side& sd, int mode, const SweepVectors& v, float* out, bool push = false) {
     if (sd.nnz == 0 && !(mode & kSolve)) return MF_OK;
     const int nmf = s->prm.nmf_project;
     if (s->panel) {
@@ -157,9 +157,25 @@ int run_sweep(mf_session* s, Side& sd, int mode, const SweepVectors& v, float* o
             s->timer.stop();
         }
         if (mode & kSolve) {
+            FinalizePush fp;
+            fp.peer_vec = nullptr;
+            if (push) {  // fused solve -> exchange: the finalize kernel stores the block into every peer's factor matrix
+                const bool is_h = out >= s->H && out < s->H + (int64_t)s->k * s->ldn;
+                fp.peer_vec = is_h ? dist_peer_H(s->dist) : dist_peer_W(s->dist);
+                fp.peer_flags = dist_peer_flags(s->dist);
+                fp.ticket = dist_flags(s->dist) + s->nranks;
+                fp.row_off = (out - (is_h ? s->H : s->W)) + sd.seg_offset;
+                fp.rank = s->rank; fp.nranks = s->nranks; fp.epoch = dist_next_epoch(s->dist);
+            }
             s->timer.start(F_FINALIZE);
-            MF_TRY(panel_finalize(sd.nseg, sd.nslots, sd.slot_ptr, sd.partials, sd.ptr, s->prm.lambda, nmf, out + sd.seg_offset, s->st));
+            MF_TRY(panel_finalize(sd.nseg, sd.nslots, sd.slot_ptr, sd.partials, sd.ptr, s->prm.lambda, nmf, out + sd.seg_offset,
+                                  push ? &fp : nullptr, s->st));
             s->timer.stop();
+            if (push) {
+                s->timer.start(F_COLLECTIVE);
+                MF_TRY(exchange_wait(dist_flags(s->dist), s->rank, s->nranks, fp.epoch, s->st));
+                s->timer.stop();
+            }
         }
     } else {
         DirectSweepArgs a;
@@ -181,16 +197,35 @@ int gather_blocks(mf_session* s, float* vec, const std::vector<int64_t>& bound, 
     return MF_OK;
 }
 
+// multi-GPU with peer mappings and the panel layout: the exchange is fused into the finalize kernel
+bool fused_exchange(const mf_session* s) { return s->nranks > 1 && s->panel && dist_p2p(s->dist); }
+
 // v = H[t] from the CSC copy and u = W[t]
 int solve_v(mf_session* s, int t, int mode, const SweepVectors& v) {
     float* out = s->H + (int64_t)t * s->ldn;
+    if (fused_exchange(s)) return run_sweep(s, s->csc, mode, v, out, true);
     MF_TRY(run_sweep(s, s->csc, mode, v, out));
     return gather_blocks(s, out, s->col_bound, 1);
 }
 int solve_u(mf_session* s, int t, int mode, const SweepVectors& v) {
     float* out = s->W + (int64_t)t * s->ldm;
+    if (fused_exchange(s)) return run_sweep(s, s->csr, mode, v, out, true);
     MF_TRY(run_sweep(s, s->csr, mode, v, out));
     return gather_blocks(s, out, s->row_bound, 1);
+}
+
+// all ranks have finished everything they enqueued before this point (peer-to-peer path only): keeps a fast
+// rank's next pushes from landing in a factor row a slower peer is still reading (RMSE, downloads)
+int exchange_barrier(mf_session* s) {
+    if (!fused_exchange(s)) return MF_OK;
+    FinalizePush fp;
+    fp.peer_vec = dist_peer_W(s->dist); fp.peer_flags = dist_peer_flags(s->dist); fp.ticket = dist_flags(s->dist) + s->nranks;
+    fp.row_off = 0; fp.rank = s->rank; fp.nranks = s->nranks; fp.epoch = dist_next_epoch(s->dist);
+    s->timer.start(F_COLLECTIVE);
+    MF_TRY(panel_finalize(0, 0, nullptr, nullptr, nullptr, 0.f, 0, nullptr, &fp, s->st));
+    MF_TRY(exchange_wait(dist_flags(s->dist), s->rank, s->nranks, fp.epoch, s->st));
+    s->timer.stop();
+    return MF_OK;
 }
 
 // residual (+|-)= u_t v_t^T on both copies — UpdateRating on R then Rt, src/CCD.cpp:100-103 / :133-134
@@ -222,7 +257,7 @@ int ccd_rank_fused(mf_session* s, int t, bool add) {
     const int sub = s->pending;
     const float* u_sub = sub >= 0 ? s->W + (int64_t)sub * s->ldm : nullptr;
     const float* v_sub = sub >= 0 ? s->H + (int64_t)sub * s->ldn : nullptr;
-    if (add) MF_CUDA(cudaMemcpyAsync(s->v_old, v, sizeof(float) * (size_t)s->ldn, cudaMemcpyDeviceToDevice, s->st));
+    const float* v_prev_iter = s->v_old + (int64_t)t * s->ldn;  // v_t as the previous outer iteration left it
     {   // CSC: [subtract `sub`] [add back t with the old (u_t, v_t)] solve v_t against u_t
         SweepVectors a;
         a.g_new = u; a.g_old = u_sub; a.s_add = v; a.s_old = v_sub;
@@ -230,8 +265,8 @@ int ccd_rank_fused(mf_session* s, int t, bool add) {
     }
     {   // CSR: [subtract `sub`] [add back t with the old v_t (saved) and old u_t] solve u_t against the new v_t
         SweepVectors a;
-        a.g_new = v; a.g_add = s->v_old; a.s_add = u; a.s_old = u_sub;
-        a.g_old = (sub == t) ? s->v_old : v_sub;  // k == 1: the subtracted rank's v was just overwritten
+        a.g_new = v; a.g_add = v_prev_iter; a.s_add = u; a.s_old = u_sub;
+        a.g_old = (sub == t) ? v_prev_iter : v_sub;  // k == 1: the subtracted rank's v was just overwritten
         MF_TRY(solve_u(s, t, kSolve | (sub >= 0 ? kSub : 0) | (add ? (kAdd | kAddSep) : 0), a));
     }
     for (int it = 1; it < T; ++it) {
@@ -241,6 +276,9 @@ int ccd_rank_fused(mf_session* s, int t, bool add) {
         b.g_new = v;
         MF_TRY(solve_u(s, t, kSolve, b));
     }
+    // keep v_t for the next outer iteration's add-back on the CSR copy (taken now: no rank writes H[t] again
+    // before that, so the copy can never race with a peer's push)
+    MF_CUDA(cudaMemcpyAsync(s->v_old + (int64_t)t * s->ldn, v, sizeof(float) * (size_t)s->ldn, cudaMemcpyDeviceToDevice, s->st));
     s->pending = t;
     return MF_OK;
 }
@@ -379,10 +417,10 @@ int create_impl(const mf_ratings* R, const mf_testset* T, const mf_params* param
         s->ldn = round_up(s->cols, 32);
         if ((rc = dev_alloc(&s->W, (size_t)s->k * s->ldm)) != MF_OK) return fail(rc);
         if ((rc = dev_alloc(&s->H, (size_t)s->k * s->ldn)) != MF_OK) return fail(rc);
-        if ((rc = dev_alloc(&s->v_old, (size_t)s->ldn)) != MF_OK) return fail(rc);
+        if ((rc = dev_alloc(&s->v_old, (size_t)s->k * s->ldn)) != MF_OK) return fail(rc);
         cudaMemsetAsync(s->W, 0, sizeof(float) * (size_t)s->k * s->ldm, s->st);
         cudaMemsetAsync(s->H, 0, sizeof(float) * (size_t)s->k * s->ldn, s->st);
-        cudaMemsetAsync(s->v_old, 0, sizeof(float) * (size_t)s->ldn, s->st);
+        cudaMemsetAsync(s->v_old, 0, sizeof(float) * (size_t)s->k * s->ldn, s->st);
     } else {
         s->ldm = s->k; s->ldn = s->k;
         if ((rc = dev_alloc(&s->W, (size_t)s->rows * s->k)) != MF_OK) return fail(rc);
@@ -405,6 +443,7 @@ int create_impl(const mf_ratings* R, const mf_testset* T, const mf_params* param
     if (nranks > 1) {
         if (!nccl_id) { set_error("multi-GPU session needs the shared ncclUniqueId"); return fail(MF_ERR_ARG); }
         if ((rc = dist_create(&s->dist, rank, nranks, nccl_id, s->device)) != MF_OK) return fail(rc);
+        if (ccd && s->panel && (rc = dist_setup_p2p(s->dist, s->W, s->H, s->st)) != MF_OK) return fail(rc);
     }
     cudaError_t e = cudaStreamSynchronize(s->st);
     if (e != cudaSuccess) { set_error("session setup failed: %s", cudaGetErrorString(e)); return fail(MF_ERR_CUDA); }
@@ -413,11 +452,14 @@ int create_impl(const mf_ratings* R, const mf_testset* T, const mf_params* param
     return MF_OK;
 }
 
-// HBM bytes one sweep launch of a family has to move on this session (compulsory traffic of the layout)
+// Algorithmic HBM bytes of one sweep launch on this session: per rating entry 2 B of index + 4 B of value
+// (+ 4 B written back by an updating sweep) in the panel layout — padding entries are NOT counted, they are
+// overhead of the layout — plus the work-item descriptors, the partial-sum slots, the segment pointers and the
+// staged factor vectors.  DIRECT layout: 4 B indices.
 int64_t sweep_bytes(const mf_session* s, const Side& sd, int mode) {
     const bool write = mode & (kSub | kAdd);
     if (s->panel) {
-        int64_t b = sd.npad * (2 + 4 + (write ? 4 : 0)) + sd.nitems * 16;
+        int64_t b = sd.nnz * (2 + 4 + (write ? 4 : 0)) + sd.nitems * 16;
         if (mode & kSolve) b += sd.nslots * 8 * 2 + sd.nseg * (4 + 4 + 4);
         return b + (int64_t)panel_sweep_vectors(mode) * sd.gdim * 4;
     }
@@ -501,6 +543,7 @@ int mf_session_set_factors(mf_session* s, const float* W, const float* H) {
         MF_CUDA(cudaMemcpy2DAsync(s->W, sizeof(float) * s->ldm, W, sizeof(float) * s->rows, sizeof(float) * s->rows, s->k, cudaMemcpyDefault, s->st));
         if (H) MF_CUDA(cudaMemcpy2DAsync(s->H, sizeof(float) * s->ldn, H, sizeof(float) * s->cols, sizeof(float) * s->cols, s->k, cudaMemcpyDefault, s->st));
         else MF_CUDA(cudaMemsetAsync(s->H, 0, sizeof(float) * (size_t)s->k * s->ldn, s->st));  // CCD_CUDA.cu:287
+        MF_CUDA(cudaMemcpyAsync(s->v_old, s->H, sizeof(float) * (size_t)s->k * s->ldn, cudaMemcpyDeviceToDevice, s->st));
     } else {
         MF_REQUIRE(H != nullptr, "ALS needs initial H (ALS_CUDA.cu:237-243)");
         MF_CUDA(cudaMemcpyAsync(s->W, W, sizeof(float) * (size_t)s->rows * s->k, cudaMemcpyDefault, s->st));
@@ -572,6 +615,7 @@ int mf_session_ccdpp_iterate(mf_session* s, int n_outer, mf_iter_stats* stats) {
         MF_CUDA(cudaEventRecord(s->ev_a, s->st));
         for (int it = 0; it < n_outer; ++it) {
             const bool add = s->outer_done > 0;
+            MF_TRY(exchange_barrier(s));
             for (int t = 0; t < s->k; ++t) {
                 s->timer.enabled = timing_on && (t % tstride == 0);
                 if (s->prm.schedule == MF_SCHEDULE_REFERENCE) MF_TRY(ccd_rank_reference(s, t, add));
@@ -597,6 +641,7 @@ int mf_session_ccdpp_iterate(mf_session* s, int n_outer, mf_iter_stats* stats) {
         double before[F_COUNT];
         memcpy(before, s->fam_seconds, sizeof(before));
         MF_CUDA(cudaEventRecord(s->ev_a, s->st));
+        MF_TRY(exchange_barrier(s));
         for (int t = 0; t < s->k; ++t) {
             s->timer.enabled = timing_on && (t % tstride == 0);
             if (s->prm.schedule == MF_SCHEDULE_REFERENCE) MF_TRY(ccd_rank_reference(s, t, add));

@@ -44,7 +44,8 @@ struct mf_session {
     bool panel = false;
     int k = 0;
     int64_t ldm = 0, ldn = 0;  // CCD++: leading dimensions of W[k][ldm], H[k][ldn]
-    float *W = nullptr, *H = nullptr, *v_old = nullptr;
+    float *W = nullptr, *H = nullptr;
+    float* v_old = nullptr;  // CCD++: H as the previous outer iteration left it, [k][ldn] (add-back of the CSR copy)
     int64_t nt = 0;
     uint32_t *trow = nullptr, *tcol = nullptr;
     float* tval = nullptr;
@@ -64,6 +65,15 @@ namespace mf {
 int dist_unique_id(void* id128);
 int dist_create(Dist** out, int rank, int nranks, const void* id128, int device);
 int dist_destroy(Dist* d);
+// optional NVLink peer-to-peer exchange (CUDA IPC); falls back to NCCL silently when unavailable
+int dist_setup_p2p(Dist* d, float* W, float* H, cudaStream_t st);
+bool dist_p2p(const Dist* d);
+int dist_rank(const Dist* d);
+float* const* dist_peer_W(const Dist* d);
+float* const* dist_peer_H(const Dist* d);
+unsigned* const* dist_peer_flags(const Dist* d);
+unsigned* dist_flags(const Dist* d);
+unsigned dist_next_epoch(Dist* d);
 // in-place all-gather of a full-length vector whose block r = [bound[r], bound[r+1]) was produced by rank r
 int dist_allgather_blocks(Dist* d, float* vec, const std::vector<int64_t>& bound, int64_t elems_per_unit, cudaStream_t st);
 int dist_allreduce_sum_double(Dist* d, double* dev_value, cudaStream_t st);
