@@ -652,10 +652,10 @@ template <int LANES>
 __global__ void __launch_bounds__(256) k_finalize(int64_t nseg, const uint32_t* __restrict__ slot_ptr,
                                                   const float2* __restrict__ partials, const uint32_t* __restrict__ seg_ptr,
                                                   float lambda, int nmf, float* __restrict__ out, PushArgs push) {
-    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t s = tid / LANES;
-    const int l = (int)(tid % LANES);
-    if (s < nseg) {
+    // grid-stride over segments (a push launch uses few, large CTAs so that few system-scope fences are needed)
+    for (int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; tid < nseg * LANES; tid += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t s = tid / LANES;
+        const int l = (int)(tid % LANES);
         const uint32_t deg = seg_ptr[s + 1] - seg_ptr[s];
         float g = 0.0f, h = 0.0f;
         if (deg != 0u) {
@@ -890,10 +890,12 @@ int panel_finalize(int64_t nseg, int64_t nslots, const uint32_t* slot_ptr, const
     int64_t nthreads = nslots > 4 * nseg ? nseg * 32 : nseg;
     if (nthreads < 1) nthreads = 1;  // a push launch must run even for an empty block: its peers wait for the flag
     if (nseg <= 0 && !push.peer_vec) return MF_OK;
+    int64_t blocks = (nthreads + 255) / 256;
+    if (push.peer_vec && blocks > 296) blocks = 296;  // fewer CTAs -> fewer system-scope fences before the flag
     if (nslots > 4 * nseg)  // many slots per segment (long columns cut by panels and chunks): a warp per segment
-        k_finalize<32><<<(unsigned)((nthreads + 255) / 256), 256, 0, st>>>(nseg, slot_ptr, partials, seg_ptr, lambda, nmf, out, push);
+        k_finalize<32><<<(unsigned)blocks, 256, 0, st>>>(nseg, slot_ptr, partials, seg_ptr, lambda, nmf, out, push);
     else
-        k_finalize<1><<<(unsigned)((nthreads + 255) / 256), 256, 0, st>>>(nseg, slot_ptr, partials, seg_ptr, lambda, nmf, out, push);
+        k_finalize<1><<<(unsigned)blocks, 256, 0, st>>>(nseg, slot_ptr, partials, seg_ptr, lambda, nmf, out, push);
     MF_CUDA(cudaGetLastError());
     return MF_OK;
 }
