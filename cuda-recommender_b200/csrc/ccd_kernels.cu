@@ -633,15 +633,12 @@ __global__ void __launch_bounds__(1024, 1) k_panel_sweep_async(PanelSweepArgs a)
 // float*unsigned product as at src/CCD.cpp:112,120; empty segment -> 0 (src/CCD.cpp:8).
 // LANES = 1: one thread per segment (slots added in order); LANES = 32: one warp per segment, lane l adds
 // slots l, l+32, ... in order and the lanes are combined by an xor-butterfly — both are fixed trees.
-// Multi-GPU epilogue of the finalize kernel (fused solve -> exchange, NVLink peer-to-peer through CUDA IPC
-// mappings, dist.cu): once a CTA has written its share of the freshly solved block it makes the writes visible
-// system-wide and takes a ticket; the last CTA publishes this rank's epoch in every peer's flag word with a
-// system-scope release store.  The receiving side (k_exchange_pull) waits for a peer's flag and then copies that
-// peer's block out of the peer's memory with coalesced 16-byte loads.  (Pushing the values from the finalize
-// kernel instead was measured slower: the system-scope fence then has to wait for every remote store.)
-// No double buffering is needed: a rank can only produce the next generation of a vector after it has received
-// everybody's blocks of the other vector, and everybody publishes those only after their last sweep that read
-// the old generation (sweeps alternate u / v).
+// Multi-GPU epilogue of the finalize kernel (fused solve -> exchange): the freshly solved coordinates are also
+// stored straight into every peer's copy of the factor vector over NVLink (CUDA IPC mappings, dist.cu), and
+// the last CTA to finish publishes this rank's epoch in every peer's flag word with a system-scope release.
+// The receiving side waits in k_exchange_wait.  No double buffering is needed: a rank can only produce the
+// next generation of a vector after it has received everybody's blocks of the other vector, and everybody
+// sends those only after their last sweep that read the old generation (sweeps alternate u / v).
 struct PushArgs {
     float* const* peer_vec;      // [nranks] base of the same factor matrix (W or H) on every rank; nullptr = no push
     unsigned* const* peer_flags; // [nranks] flag words of every rank
@@ -683,6 +680,10 @@ __global__ void __launch_bounds__(256) k_finalize(int64_t nseg, const uint32_t* 
                 if (nmf) r = fmaxf(r, 0.0f);
             }
             out[s] = r;
+            if (push.peer_vec != nullptr) {
+                for (int p = 0; p < push.nranks; ++p)
+                    if (p != push.rank) push.peer_vec[p][push.row_off + s] = r;
+            }
         }
     }
     if (push.peer_vec != nullptr) {
@@ -704,16 +705,10 @@ __global__ void __launch_bounds__(256) k_finalize(int64_t nseg, const uint32_t* 
     }
 }
 
-// waits until peer p has published `epoch` (or later) in this rank's flag words, then copies p's block of the factor
-// vector from p's memory into the local copy.  grid = (nranks-1) * kPullCtas CTAs; CTA b serves peer b / kPullCtas.
-constexpr int kPullCtas = 8;
-__global__ void __launch_bounds__(512) k_exchange_pull(float* const* peer_vec, float* local_base, int64_t row_base,
-                                                       const long long* bound, const unsigned* flags, int rank, int nranks,
-                                                       unsigned epoch) {
-    int p = blockIdx.x / kPullCtas;
-    if (p >= rank) ++p;  // skip self
-    const int part = blockIdx.x % kPullCtas;
-    if (threadIdx.x == 0) {
+// waits until every peer has published `epoch` (or later) in this rank's flag words
+__global__ void k_exchange_wait(const unsigned* flags, int rank, int nranks, unsigned epoch) {
+    const int p = threadIdx.x;
+    if (p < nranks && p != rank) {
         unsigned spins = 0, v = 0;
         for (;;) {
             asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + p) : "memory");
@@ -721,18 +716,6 @@ __global__ void __launch_bounds__(512) k_exchange_pull(float* const* peer_vec, f
             if (++spins > (1u << 27)) __trap();
         }
     }
-    __syncthreads();
-    const int64_t lo = bound[p], hi = bound[p + 1];
-    const float* src = peer_vec[p] + row_base;
-    float* dst = local_base + row_base;
-    // 16-byte main part on the aligned interior, scalar edges
-    int64_t a = (lo + 3) & ~(int64_t)3, b = hi & ~(int64_t)3;
-    if (a > b) { a = hi; b = hi; }
-    const int64_t nthreads = (int64_t)kPullCtas * blockDim.x, me = (int64_t)part * blockDim.x + threadIdx.x;
-    for (int64_t i = lo + me; i < (a < hi ? a : hi); i += nthreads) dst[i] = src[i];
-    for (int64_t i = a + 4 * me; i < b; i += 4 * nthreads)
-        *reinterpret_cast<float4*>(dst + i) = *reinterpret_cast<const float4*>(src + i);
-    for (int64_t i = b + me; i < hi; i += nthreads) dst[i] = src[i];
 }
 
 // DIRECT layout: one warp per segment on the caller's arrays (uint32 indices, gathers through L1/L2).
@@ -917,10 +900,8 @@ int panel_finalize(int64_t nseg, int64_t nslots, const uint32_t* slot_ptr, const
     return MF_OK;
 }
 
-int exchange_pull(float* const* peer_vec, float* local_base, int64_t row_base, const long long* bound, const unsigned* flags,
-                  int rank, int nranks, unsigned epoch, cudaStream_t st) {
-    if (nranks <= 1) return MF_OK;
-    k_exchange_pull<<<(nranks - 1) * kPullCtas, 512, 0, st>>>(peer_vec, local_base, row_base, bound, flags, rank, nranks, epoch);
+int exchange_wait(const unsigned* flags, int rank, int nranks, unsigned epoch, cudaStream_t st) {
+    k_exchange_wait<<<1, 32 * ((nranks + 31) / 32), 0, st>>>(flags, rank, nranks, epoch);
     MF_CUDA(cudaGetLastError());
     return MF_OK;
 }

@@ -53,7 +53,7 @@ size_t panel_sweep_smem(int mode, int panel_rows);
 int panel_sweep(int mode, const PanelSweepArgs& a, int ncta, int threads, int chunk, int pipeline, cudaStream_t st);
 // multi-GPU: where the finalize kernel also stores the solved block (every peer's copy of the factor matrix)
 struct FinalizePush {
-    float* const* peer_vec;       // non-null = publish the epoch to the peers when the block is written (device array, unused otherwise)
+    float* const* peer_vec;       // [nranks] W or H base of every rank (device array), nullptr = single GPU / NCCL path
     unsigned* const* peer_flags;  // [nranks] flag words of every rank (device array)
     unsigned* ticket;             // local CTA ticket counter
     int64_t row_off;              // element offset of out[0] inside the factor matrix
@@ -62,10 +62,7 @@ struct FinalizePush {
 };
 int panel_finalize(int64_t nseg, int64_t nslots, const uint32_t* slot_ptr, const float2* partials, const uint32_t* seg_ptr,
                    float lambda, int nmf, float* out, const FinalizePush* push, cudaStream_t st);
-// waits for every peer's flag, then copies that peer's block [bound[p], bound[p+1]) of the vector starting at
-// row_base (elements) out of the peer's factor matrix into the local one
-int exchange_pull(float* const* peer_vec, float* local_base, int64_t row_base, const long long* bound, const unsigned* flags,
-                  int rank, int nranks, unsigned epoch, cudaStream_t st);
+int exchange_wait(const unsigned* flags, int rank, int nranks, unsigned epoch, cudaStream_t st);
 int direct_sweep(int mode, const DirectSweepArgs& a, int sm_count, cudaStream_t st);
 
 }  // namespace mf

@@ -172,10 +172,8 @@ int run_sweep(mf_session* s, Side& sd, int mode, const SweepVectors& v, float* o
                                   push ? &fp : nullptr, s->st));
             s->timer.stop();
             if (push) {
-                const bool is_h = out >= s->H && out < s->H + (int64_t)s->k * s->ldn;
                 s->timer.start(F_COLLECTIVE);
-                MF_TRY(exchange_pull(is_h ? dist_peer_H(s->dist) : dist_peer_W(s->dist), is_h ? s->H : s->W, out - (is_h ? s->H : s->W),
-                                     is_h ? s->d_col_bound : s->d_row_bound, dist_flags(s->dist), s->rank, s->nranks, fp.epoch, s->st));
+                MF_TRY(exchange_wait(dist_flags(s->dist), s->rank, s->nranks, fp.epoch, s->st));
                 s->timer.stop();
             }
         }
@@ -225,7 +223,7 @@ int exchange_barrier(mf_session* s) {
     fp.row_off = 0; fp.rank = s->rank; fp.nranks = s->nranks; fp.epoch = dist_next_epoch(s->dist);
     s->timer.start(F_COLLECTIVE);
     MF_TRY(panel_finalize(0, 0, nullptr, nullptr, nullptr, 0.f, 0, nullptr, &fp, s->st));
-    MF_TRY(exchange_pull(dist_peer_W(s->dist), s->W, 0, s->d_zero_bound, dist_flags(s->dist), s->rank, s->nranks, fp.epoch, s->st));
+    MF_TRY(exchange_wait(dist_flags(s->dist), s->rank, s->nranks, fp.epoch, s->st));
     s->timer.stop();
     return MF_OK;
 }
@@ -446,15 +444,6 @@ int create_impl(const mf_ratings* R, const mf_testset* T, const mf_params* param
         if (!nccl_id) { set_error("multi-GPU session needs the shared ncclUniqueId"); return fail(MF_ERR_ARG); }
         if ((rc = dist_create(&s->dist, rank, nranks, nccl_id, s->device)) != MF_OK) return fail(rc);
         if (ccd && s->panel && (rc = dist_setup_p2p(s->dist, s->W, s->H, s->st)) != MF_OK) return fail(rc);
-        {   // block bounds on the device for the pull kernel (and an all-zero one: a barrier pulls nothing)
-            std::vector<long long> rb(s->row_bound.begin(), s->row_bound.end()), cb(s->col_bound.begin(), s->col_bound.end()), zb((size_t)nranks + 1, 0);
-            if ((rc = dev_alloc(&s->d_row_bound, rb.size())) != MF_OK) return fail(rc);
-            if ((rc = dev_alloc(&s->d_col_bound, cb.size())) != MF_OK) return fail(rc);
-            if ((rc = dev_alloc(&s->d_zero_bound, zb.size())) != MF_OK) return fail(rc);
-            cudaMemcpy(s->d_row_bound, rb.data(), sizeof(long long) * rb.size(), cudaMemcpyHostToDevice);
-            cudaMemcpy(s->d_col_bound, cb.data(), sizeof(long long) * cb.size(), cudaMemcpyHostToDevice);
-            cudaMemcpy(s->d_zero_bound, zb.data(), sizeof(long long) * zb.size(), cudaMemcpyHostToDevice);
-        }
     }
     cudaError_t e = cudaStreamSynchronize(s->st);
     if (e != cudaSuccess) { set_error("session setup failed: %s", cudaGetErrorString(e)); return fail(MF_ERR_CUDA); }
@@ -535,7 +524,7 @@ int mf_session_destroy(mf_session* s) {
     if (s->dist) dist_destroy(s->dist);
     side_free(s->csc);
     side_free(s->csr);
-    void* ptrs[] = {s->W, s->H, s->v_old, s->trow, s->tcol, s->tval, s->d_acc, s->d_row_bound, s->d_col_bound, s->d_zero_bound};
+    void* ptrs[] = {s->W, s->H, s->v_old, s->trow, s->tcol, s->tval, s->d_acc};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     s->timer.destroy();

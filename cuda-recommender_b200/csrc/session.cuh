@@ -58,7 +58,6 @@ struct mf_session {
     double last_seconds = 0.0;
     cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr;
     mf::Dist* dist = nullptr;
-    long long *d_row_bound = nullptr, *d_col_bound = nullptr, *d_zero_bound = nullptr;  // [nranks+1] on the device (pull kernel)
 };
 
 namespace mf {
