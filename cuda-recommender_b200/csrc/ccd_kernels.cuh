@@ -51,18 +51,23 @@ int panel_timeout_report(char* buf, size_t n);  // 1 + message when a pipeline w
 int panel_sweep_vectors(int mode);
 size_t panel_sweep_smem(int mode, int panel_rows);
 int panel_sweep(int mode, const PanelSweepArgs& a, int ncta, int threads, int chunk, int pipeline, cudaStream_t st);
-// multi-GPU: where the finalize kernel also stores the solved block (every peer's copy of the factor matrix)
+// multi-GPU: the finalize kernel also sends the solved block to every peer (LL protocol) or, as a barrier, only
+// publishes the epoch in the peers' flag words
 struct FinalizePush {
-    float* const* peer_vec;       // [nranks] W or H base of every rank (device array), nullptr = single GPU / NCCL path
-    unsigned* const* peer_flags;  // [nranks] flag words of every rank (device array)
-    unsigned* ticket;             // local CTA ticket counter
-    int64_t row_off;              // element offset of out[0] inside the factor matrix
+    unsigned long long* const* peer_ll;  // [nranks] LL receive buffer of every rank for this factor matrix (device array)
+    unsigned* const* peer_flags;         // [nranks] flag words of every rank (device array)
+    unsigned* ticket;                    // local CTA ticket counter
+    int64_t vec_off;                     // index of out[0] inside the factor vector
     int rank, nranks;
     unsigned epoch;
+    int barrier;                         // 1 = send no values, publish the epoch (exchange_wait on the other side)
 };
 int panel_finalize(int64_t nseg, int64_t nslots, const uint32_t* slot_ptr, const float2* partials, const uint32_t* seg_ptr,
                    float lambda, int nmf, float* out, const FinalizePush* push, cudaStream_t st);
 int exchange_wait(const unsigned* flags, int rank, int nranks, unsigned epoch, cudaStream_t st);
+// polls the LL receive buffer for the entries of `vec` owned by peers (everything outside [own_lo, own_hi)) and stores them
+int exchange_unpack(const unsigned long long* ll, float* vec, int64_t dim, int64_t own_lo, int64_t own_hi, unsigned epoch,
+                    cudaStream_t st);
 int direct_sweep(int mode, const DirectSweepArgs& a, int sm_count, cudaStream_t st);
 
 }  // namespace mf

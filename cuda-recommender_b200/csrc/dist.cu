@@ -87,6 +87,10 @@ struct Dist {
     float** d_peerH = nullptr;
     unsigned** d_peerFlags = nullptr;  // [nranks] device array: flag words of every rank
     unsigned* flags = nullptr;      // [nranks + 1] own flag words (flags[r] written by rank r) + block ticket
+    unsigned long long* llW = nullptr;  // own low-latency receive buffers: one (value, epoch) word per factor entry
+    unsigned long long* llH = nullptr;
+    unsigned long long** d_peerLLW = nullptr;  // [nranks] device arrays of every rank's receive buffers
+    unsigned long long** d_peerLLH = nullptr;
     unsigned epoch = 0;             // exchanges issued so far
 };
 
@@ -124,6 +128,10 @@ int dist_destroy(Dist* d) {
     if (d->d_peerH) cudaFree(d->d_peerH);
     if (d->d_peerFlags) cudaFree(d->d_peerFlags);
     if (d->flags) cudaFree(d->flags);
+    if (d->llW) cudaFree(d->llW);
+    if (d->llH) cudaFree(d->llH);
+    if (d->d_peerLLW) cudaFree(d->d_peerLLW);
+    if (d->d_peerLLH) cudaFree(d->d_peerLLH);
     if (d->comm) g_api.CommDestroy(d->comm);
     delete d;
     return MF_OK;
@@ -133,17 +141,22 @@ int dist_destroy(Dist* d) {
 // kernel can store a freshly solved block straight into the peers' factor buffers (ccd_kernels.cu: k_finalize
 // push epilogue + k_exchange_wait).  The 64-byte IPC handles travel through one ncclAllGather.  Any failure
 // leaves p2p off and the NCCL broadcast path in use.
-int dist_setup_p2p(Dist* d, float* W, float* H, cudaStream_t st) {
+int dist_setup_p2p(Dist* d, float* W, float* H, int64_t ldm, int64_t ldn, cudaStream_t st) {
     if (!d || d->nranks <= 1) return MF_OK;
     if (getenv("MF_NO_P2P")) return MF_OK;
     const int P = d->nranks;
-    struct Handles { cudaIpcMemHandle_t w, h, f; };
-    static_assert(sizeof(Handles) == 192, "three 64-byte handles");
+    struct Handles { cudaIpcMemHandle_t w, h, f, lw, lh; };
+    static_assert(sizeof(Handles) == 320, "five 64-byte handles");
     MF_TRY(dev_alloc(&d->flags, (size_t)P + 1));
     MF_CUDA(cudaMemsetAsync(d->flags, 0, sizeof(unsigned) * ((size_t)P + 1), st));
+    MF_TRY(dev_alloc(&d->llW, (size_t)ldm));
+    MF_TRY(dev_alloc(&d->llH, (size_t)ldn));
+    MF_CUDA(cudaMemsetAsync(d->llW, 0, sizeof(unsigned long long) * (size_t)ldm, st));
+    MF_CUDA(cudaMemsetAsync(d->llH, 0, sizeof(unsigned long long) * (size_t)ldn, st));
     Handles mine;
     if (cudaIpcGetMemHandle(&mine.w, W) != cudaSuccess || cudaIpcGetMemHandle(&mine.h, H) != cudaSuccess ||
-        cudaIpcGetMemHandle(&mine.f, d->flags) != cudaSuccess) {
+        cudaIpcGetMemHandle(&mine.f, d->flags) != cudaSuccess || cudaIpcGetMemHandle(&mine.lw, d->llW) != cudaSuccess ||
+        cudaIpcGetMemHandle(&mine.lh, d->llH) != cudaSuccess) {
         cudaGetLastError();
         return MF_OK;  // no IPC on this system: stay on NCCL
     }
@@ -157,15 +170,18 @@ int dist_setup_p2p(Dist* d, float* W, float* H, cudaStream_t st) {
     cudaFree(d_all);
     std::vector<float*> pw((size_t)P), ph((size_t)P);
     std::vector<unsigned*> pf((size_t)P);
+    std::vector<unsigned long long*> plw((size_t)P), plh((size_t)P);
     bool ok = true;
     for (int r = 0; r < P && ok; ++r) {
-        if (r == d->rank) { pw[r] = W; ph[r] = H; pf[r] = d->flags; continue; }
-        void *a = nullptr, *b = nullptr, *c = nullptr;
-        ok = cudaIpcOpenMemHandle(&a, all[r].w, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
-        if (ok) { d->opened.push_back(a); ok = cudaIpcOpenMemHandle(&b, all[r].h, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess; }
-        if (ok) { d->opened.push_back(b); ok = cudaIpcOpenMemHandle(&c, all[r].f, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess; }
-        if (ok) d->opened.push_back(c);
-        pw[r] = (float*)a; ph[r] = (float*)b; pf[r] = (unsigned*)c;
+        if (r == d->rank) { pw[r] = W; ph[r] = H; pf[r] = d->flags; plw[r] = d->llW; plh[r] = d->llH; continue; }
+        const cudaIpcMemHandle_t* hs[5] = {&all[r].w, &all[r].h, &all[r].f, &all[r].lw, &all[r].lh};
+        void* m[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+        for (int q = 0; q < 5 && ok; ++q) {
+            ok = cudaIpcOpenMemHandle(&m[q], *hs[q], cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+            if (ok) d->opened.push_back(m[q]);
+        }
+        pw[r] = (float*)m[0]; ph[r] = (float*)m[1]; pf[r] = (unsigned*)m[2];
+        plw[r] = (unsigned long long*)m[3]; plh[r] = (unsigned long long*)m[4];
     }
     if (!ok) {
         cudaGetLastError();
@@ -179,6 +195,10 @@ int dist_setup_p2p(Dist* d, float* W, float* H, cudaStream_t st) {
     MF_CUDA(cudaMemcpy(d->d_peerW, pw.data(), sizeof(float*) * (size_t)P, cudaMemcpyHostToDevice));
     MF_CUDA(cudaMemcpy(d->d_peerH, ph.data(), sizeof(float*) * (size_t)P, cudaMemcpyHostToDevice));
     MF_CUDA(cudaMemcpy(d->d_peerFlags, pf.data(), sizeof(unsigned*) * (size_t)P, cudaMemcpyHostToDevice));
+    MF_TRY(dev_alloc(&d->d_peerLLW, (size_t)P));
+    MF_TRY(dev_alloc(&d->d_peerLLH, (size_t)P));
+    MF_CUDA(cudaMemcpy(d->d_peerLLW, plw.data(), sizeof(void*) * (size_t)P, cudaMemcpyHostToDevice));
+    MF_CUDA(cudaMemcpy(d->d_peerLLH, plh.data(), sizeof(void*) * (size_t)P, cudaMemcpyHostToDevice));
     d->p2p = true;
     return MF_OK;
 }
@@ -190,6 +210,8 @@ float* const* dist_peer_H(const Dist* d) { return d->d_peerH; }
 unsigned* const* dist_peer_flags(const Dist* d) { return d->d_peerFlags; }
 unsigned* dist_flags(const Dist* d) { return d->flags; }
 unsigned dist_next_epoch(Dist* d) { return ++d->epoch; }
+unsigned long long* const* dist_peer_ll(const Dist* d, bool h) { return h ? d->d_peerLLH : d->d_peerLLW; }
+unsigned long long* dist_ll(const Dist* d, bool h) { return h ? d->llH : d->llW; }
 
 int dist_allgather_blocks(Dist* d, float* vec, const std::vector<int64_t>& bound, int64_t unit, cudaStream_t st) {
     if (!d || d->nranks <= 1) return MF_OK;

@@ -158,14 +158,13 @@ int run_sweep(mf_session* s, Side& sd, int mode, const SweepVectors& v, float* o
         }
         if (mode & kSolve) {
             FinalizePush fp;
-            fp.peer_vec = nullptr;
-            if (push) {  // fused solve -> exchange: the finalize kernel stores the block into every peer's factor matrix
-                const bool is_h = out >= s->H && out < s->H + (int64_t)s->k * s->ldn;
-                fp.peer_vec = is_h ? dist_peer_H(s->dist) : dist_peer_W(s->dist);
+            const bool is_h = push && out >= s->H && out < s->H + (int64_t)s->k * s->ldn;
+            if (push) {  // fused solve -> exchange: the finalize kernel sends the block to every peer (LL words over NVLink)
+                fp.peer_ll = dist_peer_ll(s->dist, is_h);
                 fp.peer_flags = dist_peer_flags(s->dist);
                 fp.ticket = dist_flags(s->dist) + s->nranks;
-                fp.row_off = (out - (is_h ? s->H : s->W)) + sd.seg_offset;
-                fp.rank = s->rank; fp.nranks = s->nranks; fp.epoch = dist_next_epoch(s->dist);
+                fp.vec_off = sd.seg_offset;
+                fp.rank = s->rank; fp.nranks = s->nranks; fp.epoch = dist_next_epoch(s->dist); fp.barrier = 0;
             }
             s->timer.start(F_FINALIZE);
             MF_TRY(panel_finalize(sd.nseg, sd.nslots, sd.slot_ptr, sd.partials, sd.ptr, s->prm.lambda, nmf, out + sd.seg_offset,
@@ -173,7 +172,8 @@ int run_sweep(mf_session* s, Side& sd, int mode, const SweepVectors& v, float* o
             s->timer.stop();
             if (push) {
                 s->timer.start(F_COLLECTIVE);
-                MF_TRY(exchange_wait(dist_flags(s->dist), s->rank, s->nranks, fp.epoch, s->st));
+                MF_TRY(exchange_unpack(dist_ll(s->dist, is_h), out, is_h ? s->cols : s->rows, sd.seg_offset, sd.seg_offset + sd.nseg,
+                                       fp.epoch, s->st));
                 s->timer.stop();
             }
         }
@@ -219,8 +219,8 @@ int solve_u(mf_session* s, int t, int mode, const SweepVectors& v) {
 int exchange_barrier(mf_session* s) {
     if (!fused_exchange(s)) return MF_OK;
     FinalizePush fp;
-    fp.peer_vec = dist_peer_W(s->dist); fp.peer_flags = dist_peer_flags(s->dist); fp.ticket = dist_flags(s->dist) + s->nranks;
-    fp.row_off = 0; fp.rank = s->rank; fp.nranks = s->nranks; fp.epoch = dist_next_epoch(s->dist);
+    fp.peer_ll = nullptr; fp.peer_flags = dist_peer_flags(s->dist); fp.ticket = dist_flags(s->dist) + s->nranks;
+    fp.vec_off = 0; fp.rank = s->rank; fp.nranks = s->nranks; fp.epoch = dist_next_epoch(s->dist); fp.barrier = 1;
     s->timer.start(F_COLLECTIVE);
     MF_TRY(panel_finalize(0, 0, nullptr, nullptr, nullptr, 0.f, 0, nullptr, &fp, s->st));
     MF_TRY(exchange_wait(dist_flags(s->dist), s->rank, s->nranks, fp.epoch, s->st));
@@ -443,7 +443,7 @@ int create_impl(const mf_ratings* R, const mf_testset* T, const mf_params* param
     if (nranks > 1) {
         if (!nccl_id) { set_error("multi-GPU session needs the shared ncclUniqueId"); return fail(MF_ERR_ARG); }
         if ((rc = dist_create(&s->dist, rank, nranks, nccl_id, s->device)) != MF_OK) return fail(rc);
-        if (ccd && s->panel && (rc = dist_setup_p2p(s->dist, s->W, s->H, s->st)) != MF_OK) return fail(rc);
+        if (ccd && s->panel && (rc = dist_setup_p2p(s->dist, s->W, s->H, s->ldm, s->ldn, s->st)) != MF_OK) return fail(rc);
     }
     cudaError_t e = cudaStreamSynchronize(s->st);
     if (e != cudaSuccess) { set_error("session setup failed: %s", cudaGetErrorString(e)); return fail(MF_ERR_CUDA); }
