@@ -7,7 +7,9 @@
 //
 // Here one CTA owns a segment (a user row or an item column) at a time:
 //   * segments are visited longest-first (degree-binned order) through an atomic queue;
-//   * the segment's factor rows Y[idx] are staged through shared memory in batches of 32 rows;
+//   * the segment's factor rows Y[idx] are staged through shared memory in batches of 32 rows with asynchronous
+//     copies (cp.async, double-buffered: batch b+1 is in flight while batch b is accumulated; the row ids of
+//     batch b+2 travel in registers);
 //   * A = Y_O^T Y_O is accumulated in registers as 4x4 tiles of the lower triangle (each thread owns
 //     up to MAXT tiles for the whole segment), b = Y_O^T r alongside;
 //   * A + lambda*I (lambda NOT scaled by |O|, src/ALS.cpp:120-122) is factored in shared memory
@@ -42,16 +44,28 @@ __global__ void k_bin_scan(unsigned* __restrict__ count, unsigned* __restrict__ 
     }
 }
 
-template <int TPS, int MAXT>
+// 4/8/16-byte asynchronous global->shared copies (LDGSTS): the factor-row gather of the next batch runs while the
+// current batch is being accumulated
+template <int BYTES>
+__device__ __forceinline__ void cp_async(void* smem_dst, const void* gsrc) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    if (BYTES == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+    else if (BYTES == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+    else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
+}
+
+// VW = floats per copy (4 when k % 4 == 0, 2 when k is even, else 1): every factor row starts VW-aligned
+template <int TPS, int MAXT, int VW>
 __global__ void __launch_bounds__(TPS) k_als_half(int64_t nseg, const uint32_t* __restrict__ order, unsigned* __restrict__ queue,
                                                   const uint32_t* __restrict__ ptr, const uint32_t* __restrict__ idx,
                                                   const float* __restrict__ val, const float* __restrict__ Y,
                                                   float* __restrict__ X, int k, int kp, float lambda) {
     extern __shared__ __align__(16) float sm[];
-    float* A = sm;                      // [kp*kp]  lower triangle used
-    float* bvec = A + kp * kp;          // [kp]
-    float* Ys = bvec + kp;              // [kBatch*kp]
-    float* rs = Ys + kBatch * kp;       // [kBatch]
+    float* A = sm;                           // [kp*kp]  lower triangle used
+    float* bvec = A + kp * kp;               // [kp]
+    float* Ys = bvec + kp;                   // [2][kBatch*kp]  double-buffered staged factor rows
+    float* rs = Ys + 2 * kBatch * kp;        // [2][kBatch]     ratings of the staged rows
+    uint32_t* sidx = reinterpret_cast<uint32_t*>(rs + 2 * kBatch);  // [2][kBatch] row ids of the batch to be fetched next
     __shared__ unsigned s_next;
 
     const int tid = threadIdx.x;
@@ -72,6 +86,9 @@ __global__ void __launch_bounds__(TPS) k_als_half(int64_t nseg, const uint32_t* 
             tj[m] = 0;
         }
     }
+    // the pad columns k..kp-1 of both staging buffers stay zero for the whole kernel (the copies never touch them)
+    for (int e = tid; e < 2 * kBatch * kp; e += TPS) Ys[e] = 0.0f;
+    const int vec_per_row = k / VW;
 
     for (;;) {
         __syncthreads();
@@ -93,36 +110,64 @@ __global__ void __launch_bounds__(TPS) k_als_half(int64_t nseg, const uint32_t* 
             for (int e = 0; e < 16; ++e) acc[m][e] = 0.0f;
         float bacc = 0.0f;
 
-        for (uint32_t base = lo; base < hi; base += kBatch) {
-            const int nrow = (int)min((uint32_t)kBatch, hi - base);
-            __syncthreads();  // previous batch fully consumed
-            for (int e = tid; e < nrow * kp; e += TPS) {
-                const int r = e / kp, c = e - r * kp;
-                Ys[e] = c < k ? __ldg(Y + (size_t)__ldg(idx + base + r) * k + c) : 0.0f;
+        const int nbatch = (int)((hi - lo + kBatch - 1) / kBatch);
+        // issue the asynchronous gather of batch `b` into buffer b&1, row ids taken from sidx[b&1]
+        auto issue_rows = [&](int b) {
+            const int nrow = (int)min((uint32_t)kBatch, hi - (lo + (uint32_t)b * kBatch));
+            float* dst = Ys + (b & 1) * kBatch * kp;
+            const uint32_t* ids = sidx + (b & 1) * kBatch;
+            for (int e = tid; e < nrow * vec_per_row; e += TPS) {
+                const int r = e / vec_per_row, c = (e - r * vec_per_row) * VW;
+                cp_async<VW * 4>(dst + r * kp + c, Y + (size_t)ids[r] * k + c);
             }
-            if (tid < nrow) rs[tid] = __ldg(val + base + tid);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        // prologue: ids + ratings of batches 0 and 1, rows of batch 0
+        if (tid < kBatch) {
+            const uint32_t e0 = lo + tid, e1 = lo + kBatch + tid;
+            if (e0 < hi) { sidx[tid] = __ldg(idx + e0); rs[tid] = __ldg(val + e0); }
+            if (e1 < hi) { sidx[kBatch + tid] = __ldg(idx + e1); rs[kBatch + tid] = __ldg(val + e1); }
+        }
+        __syncthreads();
+        issue_rows(0);
+
+        for (int b = 0; b < nbatch; ++b) {
+            const int nrow = (int)min((uint32_t)kBatch, hi - (lo + (uint32_t)b * kBatch));
+            if (b + 1 < nbatch) issue_rows(b + 1); else asm volatile("cp.async.commit_group;" ::: "memory");
+            // ids + ratings of batch b+2 travel in registers while batch b is accumulated
+            uint32_t nid = 0; float nr = 0.0f;
+            const uint32_t e2 = lo + (uint32_t)(b + 2) * kBatch + tid;
+            const bool has2 = tid < kBatch && b + 2 < nbatch && e2 < hi;
+            if (has2) { nid = __ldg(idx + e2); nr = __ldg(val + e2); }
+            asm volatile("cp.async.wait_group 1;" ::: "memory");  // batch b has landed (batch b+1 may be in flight)
             __syncthreads();
+            const float* Yb = Ys + (b & 1) * kBatch * kp;
+            const float* rb = rs + (b & 1) * kBatch;
 #pragma unroll
             for (int m = 0; m < MAXT; ++m) {
                 if (ti[m] < 0) continue;
-                const float* yi = Ys + 4 * ti[m];
-                const float* yj = Ys + 4 * tj[m];
+                const float* yi = Yb + 4 * ti[m];
+                const float* yj = Yb + 4 * tj[m];
                 for (int r = 0; r < nrow; ++r) {
                     const float4 a = *reinterpret_cast<const float4*>(yi + r * kp);
-                    const float4 b = *reinterpret_cast<const float4*>(yj + r * kp);
-                    acc[m][0] = fmaf(a.x, b.x, acc[m][0]);   acc[m][1] = fmaf(a.x, b.y, acc[m][1]);
-                    acc[m][2] = fmaf(a.x, b.z, acc[m][2]);   acc[m][3] = fmaf(a.x, b.w, acc[m][3]);
-                    acc[m][4] = fmaf(a.y, b.x, acc[m][4]);   acc[m][5] = fmaf(a.y, b.y, acc[m][5]);
-                    acc[m][6] = fmaf(a.y, b.z, acc[m][6]);   acc[m][7] = fmaf(a.y, b.w, acc[m][7]);
-                    acc[m][8] = fmaf(a.z, b.x, acc[m][8]);   acc[m][9] = fmaf(a.z, b.y, acc[m][9]);
-                    acc[m][10] = fmaf(a.z, b.z, acc[m][10]); acc[m][11] = fmaf(a.z, b.w, acc[m][11]);
-                    acc[m][12] = fmaf(a.w, b.x, acc[m][12]); acc[m][13] = fmaf(a.w, b.y, acc[m][13]);
-                    acc[m][14] = fmaf(a.w, b.z, acc[m][14]); acc[m][15] = fmaf(a.w, b.w, acc[m][15]);
+                    const float4 c = *reinterpret_cast<const float4*>(yj + r * kp);
+                    acc[m][0] = fmaf(a.x, c.x, acc[m][0]);   acc[m][1] = fmaf(a.x, c.y, acc[m][1]);
+                    acc[m][2] = fmaf(a.x, c.z, acc[m][2]);   acc[m][3] = fmaf(a.x, c.w, acc[m][3]);
+                    acc[m][4] = fmaf(a.y, c.x, acc[m][4]);   acc[m][5] = fmaf(a.y, c.y, acc[m][5]);
+                    acc[m][6] = fmaf(a.y, c.z, acc[m][6]);   acc[m][7] = fmaf(a.y, c.w, acc[m][7]);
+                    acc[m][8] = fmaf(a.z, c.x, acc[m][8]);   acc[m][9] = fmaf(a.z, c.y, acc[m][9]);
+                    acc[m][10] = fmaf(a.z, c.z, acc[m][10]); acc[m][11] = fmaf(a.z, c.w, acc[m][11]);
+                    acc[m][12] = fmaf(a.w, c.x, acc[m][12]); acc[m][13] = fmaf(a.w, c.y, acc[m][13]);
+                    acc[m][14] = fmaf(a.w, c.z, acc[m][14]); acc[m][15] = fmaf(a.w, c.w, acc[m][15]);
                 }
             }
             if (tid < k)
-                for (int r = 0; r < nrow; ++r) bacc = fmaf(rs[r], Ys[r * kp + tid], bacc);
+                for (int r = 0; r < nrow; ++r) bacc = fmaf(rb[r], Yb[r * kp + tid], bacc);
+            __syncthreads();  // everyone is done with buffer b&1 and its ratings / ids
+            if (has2) { sidx[(b & 1) * kBatch + tid] = nid; rs[(b & 1) * kBatch + tid] = nr; }
+            __syncthreads();  // ids of batch b+2 are in place before the next iteration issues its rows
         }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
         // tiles -> A (lower triangle incl. the whole diagonal tiles), + lambda on the diagonal
 #pragma unroll
         for (int m = 0; m < MAXT; ++m) {
@@ -176,23 +221,31 @@ __global__ void __launch_bounds__(TPS) k_als_half(int64_t nseg, const uint32_t* 
     }
 }
 
-template <int TPS, int MAXT>
-int launch_als(int64_t nseg, const uint32_t* order, unsigned* queue, const Side& s, const float* Y, float* X, int k,
-               int kp, float lambda, int sm_count, cudaStream_t st) {
-    const size_t smem = sizeof(float) * ((size_t)kp * kp + kp + (size_t)kBatch * kp + kBatch);
+template <int TPS, int MAXT, int VW>
+int launch_als_vw(int64_t nseg, const uint32_t* order, unsigned* queue, const Side& s, const float* Y, float* X, int k,
+                  int kp, float lambda, int sm_count, cudaStream_t st) {
+    const size_t smem = sizeof(float) * ((size_t)kp * kp + kp + 2 * (size_t)kBatch * kp + 2 * kBatch) + sizeof(uint32_t) * 2 * kBatch;
     static size_t attr = 0;
     if (smem > 48 * 1024 && smem > attr) {
-        MF_CUDA(cudaFuncSetAttribute(k_als_half<TPS, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        MF_CUDA(cudaFuncSetAttribute(k_als_half<TPS, MAXT, VW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr = smem;
     }
     int per_sm = 1;
-    MF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_als_half<TPS, MAXT>, TPS, smem));
+    MF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_als_half<TPS, MAXT, VW>, TPS, smem));
     if (per_sm < 1) per_sm = 1;
     int64_t grid = (int64_t)sm_count * per_sm;
     if (grid > nseg) grid = nseg;
-    k_als_half<TPS, MAXT><<<(unsigned)grid, TPS, smem, st>>>(nseg, order, queue, s.ptr, s.idx, s.val, Y, X, k, kp, lambda);
+    k_als_half<TPS, MAXT, VW><<<(unsigned)grid, TPS, smem, st>>>(nseg, order, queue, s.ptr, s.idx, s.val, Y, X, k, kp, lambda);
     MF_CUDA(cudaGetLastError());
     return MF_OK;
+}
+
+template <int TPS, int MAXT>
+int launch_als(int64_t nseg, const uint32_t* order, unsigned* queue, const Side& s, const float* Y, float* X, int k,
+               int kp, float lambda, int sm_count, cudaStream_t st) {
+    if (k % 4 == 0) return launch_als_vw<TPS, MAXT, 4>(nseg, order, queue, s, Y, X, k, kp, lambda, sm_count, st);
+    if (k % 2 == 0) return launch_als_vw<TPS, MAXT, 2>(nseg, order, queue, s, Y, X, k, kp, lambda, sm_count, st);
+    return launch_als_vw<TPS, MAXT, 1>(nseg, order, queue, s, Y, X, k, kp, lambda, sm_count, st);
 }
 
 }  // namespace
