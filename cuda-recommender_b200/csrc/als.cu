@@ -5,16 +5,25 @@
 // updateH_overW_kernel (cuda_src/ALS_CUDA.cu:81-181), which give every row to ONE thread and
 // malloc() k*k floats per thread on the device heap.
 //
-// Here one CTA owns a segment (a user row or an item column) at a time:
-//   * segments are visited longest-first (degree-binned order) through an atomic queue;
+// Here one CTA owns a segment (a user row or an item column) at a time; segments are visited longest-first
+// (degree-binned order) through an atomic queue.  Everything about a segment is one register-tiled computation on
+// the augmented matrix  M = [Y_O | r]^T [Y_O | r]  (+ lambda on the first k diagonal entries, lambda NOT scaled by
+// |O|, src/ALS.cpp:120-122):
 //   * the segment's factor rows Y[idx] are staged through shared memory in batches of 32 rows with asynchronous
-//     copies (cp.async, double-buffered: batch b+1 is in flight while batch b is accumulated; the row ids of
-//     batch b+2 travel in registers);
-//   * A = Y_O^T Y_O is accumulated in registers as 4x4 tiles of the lower triangle (each thread owns
-//     up to MAXT tiles for the whole segment), b = Y_O^T r alongside;
-//   * A + lambda*I (lambda NOT scaled by |O|, src/ALS.cpp:120-122) is factored in shared memory
-//     (in-place lower Cholesky) and x is obtained by two triangular solves — no explicit inverse;
+//     copies (cp.async, double-buffered), the rating r is stored as one more column behind the k factor columns;
+//   * M is accumulated in registers as TS x TS tiles of the lower triangle (TS = 8, or 4 for small k), one tile per
+//     thread, the rows of a batch dealt to `ks` thread groups (split-K) whose partial tiles are added in a fixed
+//     order through shared memory: the Gram matrix A = M[0:k,0:k] and the right-hand side b = M[k,0:k] come out of
+//     the same loop;
+//   * the tiles never leave the registers for the factorisation: blocked right-looking Cholesky (diagonal tile
+//     factored by its owner, panel tiles solved against it, trailing tiles updated by the same rank-1 code as the
+//     Gram loop).  Row k of the factor of M is y = L^-1 b, so the forward substitution costs nothing;
+//   * L^T x = y is solved block by block by one warp — no explicit inverse;
 //   * an empty segment writes zeros (src/ALS.cpp:151-157).
+// Shared-memory layout of a staged row / of a column of L: 4-float chunks; with TS = 8 the two chunks of tile t
+// sit at chunk positions t and nb + t, so that consecutive tiles read consecutive 16-byte words (no bank conflicts).
+#include <algorithm>
+
 #include "session.cuh"
 
 namespace mf {
@@ -44,8 +53,7 @@ __global__ void k_bin_scan(unsigned* __restrict__ count, unsigned* __restrict__ 
     }
 }
 
-// 4/8/16-byte asynchronous global->shared copies (LDGSTS): the factor-row gather of the next batch runs while the
-// current batch is being accumulated
+// 4/8/16-byte asynchronous global->shared copies (LDGSTS)
 template <int BYTES>
 __device__ __forceinline__ void cp_async(void* smem_dst, const void* gsrc) {
     const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
@@ -54,41 +62,69 @@ __device__ __forceinline__ void cp_async(void* smem_dst, const void* gsrc) {
     else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
 }
 
-// VW = floats per copy (4 when k % 4 == 0, 2 when k is even, else 1): every factor row starts VW-aligned
-template <int TPS, int MAXT, int VW>
-__global__ void __launch_bounds__(TPS) k_als_half(int64_t nseg, const uint32_t* __restrict__ order, unsigned* __restrict__ queue,
-                                                  const uint32_t* __restrict__ ptr, const uint32_t* __restrict__ idx,
-                                                  const float* __restrict__ val, const float* __restrict__ Y,
-                                                  float* __restrict__ X, int k, int kp, float lambda) {
+// position (in floats) of matrix index i inside a staged row / a column of L
+template <int TS>
+__device__ __forceinline__ int pos_of(int i, int nb) {
+    const int ch = i >> 2;
+    return 4 * (TS == 8 ? (ch >> 1) + (ch & 1) * nb : ch) + (i & 3);
+}
+
+// the TS entries of tile t out of one staged row / one column of L
+template <int TS>
+__device__ __forceinline__ void load_tile_vec(const float* __restrict__ row, int t, int nb, float (&v)[TS]) {
+    const float4 lo = *reinterpret_cast<const float4*>(row + 4 * t);
+    v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w;
+    if (TS == 8) {
+        const float4 hi = *reinterpret_cast<const float4*>(row + 4 * (nb + t));
+        v[TS - 4] = hi.x; v[TS - 3] = hi.y; v[TS - 2] = hi.z; v[TS - 1] = hi.w;
+    }
+}
+
+// acc += sign * a b^T
+template <int TS, bool NEG>
+__device__ __forceinline__ void rank1(float (&acc)[TS][TS], const float (&a)[TS], const float (&b)[TS]) {
+#pragma unroll
+    for (int i = 0; i < TS; ++i)
+#pragma unroll
+        for (int j = 0; j < TS; ++j) acc[i][j] = fmaf(NEG ? -a[i] : a[i], b[j], acc[i][j]);
+}
+
+// TS = tile edge; VW = floats per copy (4 when k % 4 == 0, 2 when k is even, else 1): every factor row starts VW-aligned.
+// nb = tiles per matrix edge (nb * TS >= k + 1); ks = split-K groups; threads 0 .. ks*ntiles-1 work on the Gram matrix.
+template <int TS, int VW>
+__global__ void __launch_bounds__(TS == 8 ? 384 : 128)
+k_als_tile(int64_t nseg, const uint32_t* __restrict__ order, unsigned* __restrict__ queue, const uint32_t* __restrict__ ptr,
+           const uint32_t* __restrict__ idx, const float* __restrict__ val, const float* __restrict__ Y, float* __restrict__ X,
+           int k, int nb, int ks, float lambda) {
     extern __shared__ __align__(16) float sm[];
-    float* A = sm;                           // [kp*kp]  lower triangle used
-    float* bvec = A + kp * kp;               // [kp]
-    float* Ys = bvec + kp;                   // [2][kBatch*kp]  double-buffered staged factor rows
-    float* rs = Ys + 2 * kBatch * kp;        // [2][kBatch]     ratings of the staged rows
-    uint32_t* sidx = reinterpret_cast<uint32_t*>(rs + 2 * kBatch);  // [2][kBatch] row ids of the batch to be fetched next
+    const int kp = nb * TS;
+    const int ntiles = nb * (nb + 1) / 2;
+    float* Ys = sm;                               // [2][kBatch][kp]  staged rows [factor row | rating | 0...]
+    float* Lm = Ys + 2 * kBatch * kp;             // [kp][kp]         Lm[j*kp + pos(i)] = L[i][j]
+    float* Ld = Lm + kp * kp;                     // [TS][TS]         diagonal tile being applied (natural order)
+    float* dv = Ld + TS * TS;                     // [kp]             1 / L[i][i]  (0 for i >= k)
+    float* xs = dv + kp;                          // [kp]             solution at positions pos(i)
+    uint32_t* sidx = reinterpret_cast<uint32_t*>(xs + kp);  // [2][kBatch] row ids of the batches to be fetched
+    float* scratch = sm;                          // split-K partial tiles, aliases Ys (+ Lm): [(ks-1)][TS*TS][ntiles]
     __shared__ unsigned s_next;
 
     const int tid = threadIdx.x;
-    const int nb = kp >> 2;                   // 4x4 tile grid
-    const int ntiles = nb * (nb + 1) / 2;
-    int ti[MAXT], tj[MAXT];
-#pragma unroll
-    for (int m = 0; m < MAXT; ++m) {
-        int q = tid + m * TPS;
-        if (q < ntiles) {
-            int I = (int)((sqrtf(8.0f * q + 1.0f) - 1.0f) * 0.5f);
-            while ((I + 1) * (I + 2) / 2 <= q) ++I;
-            while (I * (I + 1) / 2 > q) --I;
-            ti[m] = I;
-            tj[m] = q - I * (I + 1) / 2;
-        } else {
-            ti[m] = -1;
-            tj[m] = 0;
-        }
+    const int TPS = blockDim.x;
+    const int g = tid / ntiles;                   // split-K group
+    const int q = tid - g * ntiles;               // tile id, column-major over the lower triangle
+    const bool active = g < ks;
+    int I, J;
+    {
+        int off = 0;
+        J = 0;
+        while (q >= off + (nb - J)) { off += nb - J; ++J; }
+        I = J + (q - off);
     }
-    // the pad columns k..kp-1 of both staging buffers stay zero for the whole kernel (the copies never touch them)
+    const bool owner = tid < ntiles;              // group 0 keeps the tile for the factorisation
+    const int posk = pos_of<TS>(k, nb);           // where the rating sits in a staged row / y = L[k][.] in a column
+    const int cpr = k / VW;                       // copies per factor row
+
     for (int e = tid; e < 2 * kBatch * kp; e += TPS) Ys[e] = 0.0f;
-    const int vec_per_row = k / VW;
 
     for (;;) {
         __syncthreads();
@@ -103,30 +139,36 @@ __global__ void __launch_bounds__(TPS) k_als_half(int64_t nseg, const uint32_t* 
             for (int c = tid; c < k; c += TPS) x[c] = 0.0f;
             continue;
         }
-        float acc[MAXT][16];
+        float acc[TS][TS];
 #pragma unroll
-        for (int m = 0; m < MAXT; ++m)
+        for (int i = 0; i < TS; ++i)
 #pragma unroll
-            for (int e = 0; e < 16; ++e) acc[m][e] = 0.0f;
-        float bacc = 0.0f;
+            for (int j = 0; j < TS; ++j) acc[i][j] = 0.0f;
 
         const int nbatch = (int)((hi - lo + kBatch - 1) / kBatch);
+        // the split-K scratch of the previous segment overwrote the staging buffers: the pad columns behind the
+        // rating have to be zero again (the copies never touch them)
+        if (ks > 1)
+            for (int e = tid; e < 2 * kBatch * (kp - k - 1); e += TPS) {
+                const int r = e / (kp - k - 1), c = k + 1 + (e - r * (kp - k - 1));
+                Ys[r * kp + pos_of<TS>(c, nb)] = 0.0f;
+            }
         // issue the asynchronous gather of batch `b` into buffer b&1, row ids taken from sidx[b&1]
         auto issue_rows = [&](int b) {
             const int nrow = (int)min((uint32_t)kBatch, hi - (lo + (uint32_t)b * kBatch));
             float* dst = Ys + (b & 1) * kBatch * kp;
             const uint32_t* ids = sidx + (b & 1) * kBatch;
-            for (int e = tid; e < nrow * vec_per_row; e += TPS) {
-                const int r = e / vec_per_row, c = (e - r * vec_per_row) * VW;
-                cp_async<VW * 4>(dst + r * kp + c, Y + (size_t)ids[r] * k + c);
+            for (int e = tid; e < nrow * cpr; e += TPS) {
+                const int r = e / cpr, c = (e - r * cpr) * VW;
+                cp_async<VW * 4>(dst + r * kp + pos_of<TS>(c, nb), Y + (size_t)ids[r] * k + c);
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
         };
         // prologue: ids + ratings of batches 0 and 1, rows of batch 0
         if (tid < kBatch) {
             const uint32_t e0 = lo + tid, e1 = lo + kBatch + tid;
-            if (e0 < hi) { sidx[tid] = __ldg(idx + e0); rs[tid] = __ldg(val + e0); }
-            if (e1 < hi) { sidx[kBatch + tid] = __ldg(idx + e1); rs[kBatch + tid] = __ldg(val + e1); }
+            if (e0 < hi) { sidx[tid] = __ldg(idx + e0); Ys[tid * kp + posk] = __ldg(val + e0); }
+            if (e1 < hi) { sidx[kBatch + tid] = __ldg(idx + e1); Ys[(kBatch + tid) * kp + posk] = __ldg(val + e1); }
         }
         __syncthreads();
         issue_rows(0);
@@ -142,143 +184,231 @@ __global__ void __launch_bounds__(TPS) k_als_half(int64_t nseg, const uint32_t* 
             asm volatile("cp.async.wait_group 1;" ::: "memory");  // batch b has landed (batch b+1 may be in flight)
             __syncthreads();
             const float* Yb = Ys + (b & 1) * kBatch * kp;
-            const float* rb = rs + (b & 1) * kBatch;
-#pragma unroll
-            for (int m = 0; m < MAXT; ++m) {
-                if (ti[m] < 0) continue;
-                const float* yi = Yb + 4 * ti[m];
-                const float* yj = Yb + 4 * tj[m];
-                for (int r = 0; r < nrow; ++r) {
-                    const float4 a = *reinterpret_cast<const float4*>(yi + r * kp);
-                    const float4 c = *reinterpret_cast<const float4*>(yj + r * kp);
-                    acc[m][0] = fmaf(a.x, c.x, acc[m][0]);   acc[m][1] = fmaf(a.x, c.y, acc[m][1]);
-                    acc[m][2] = fmaf(a.x, c.z, acc[m][2]);   acc[m][3] = fmaf(a.x, c.w, acc[m][3]);
-                    acc[m][4] = fmaf(a.y, c.x, acc[m][4]);   acc[m][5] = fmaf(a.y, c.y, acc[m][5]);
-                    acc[m][6] = fmaf(a.y, c.z, acc[m][6]);   acc[m][7] = fmaf(a.y, c.w, acc[m][7]);
-                    acc[m][8] = fmaf(a.z, c.x, acc[m][8]);   acc[m][9] = fmaf(a.z, c.y, acc[m][9]);
-                    acc[m][10] = fmaf(a.z, c.z, acc[m][10]); acc[m][11] = fmaf(a.z, c.w, acc[m][11]);
-                    acc[m][12] = fmaf(a.w, c.x, acc[m][12]); acc[m][13] = fmaf(a.w, c.y, acc[m][13]);
-                    acc[m][14] = fmaf(a.w, c.z, acc[m][14]); acc[m][15] = fmaf(a.w, c.w, acc[m][15]);
+            if (active) {
+#pragma unroll 2
+                for (int r = g; r < nrow; r += ks) {
+                    float a[TS], c[TS];
+                    load_tile_vec<TS>(Yb + r * kp, I, nb, a);
+                    load_tile_vec<TS>(Yb + r * kp, J, nb, c);
+                    rank1<TS, false>(acc, a, c);
                 }
             }
-            if (tid < k)
-                for (int r = 0; r < nrow; ++r) bacc = fmaf(rb[r], Yb[r * kp + tid], bacc);
-            __syncthreads();  // everyone is done with buffer b&1 and its ratings / ids
-            if (has2) { sidx[(b & 1) * kBatch + tid] = nid; rs[(b & 1) * kBatch + tid] = nr; }
+            __syncthreads();  // everyone is done with buffer b&1 and its ids
+            if (has2) { sidx[(b & 1) * kBatch + tid] = nid; Ys[((b & 1) * kBatch + tid) * kp + posk] = nr; }
             __syncthreads();  // ids of batch b+2 are in place before the next iteration issues its rows
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
-        // tiles -> A (lower triangle incl. the whole diagonal tiles), + lambda on the diagonal
-#pragma unroll
-        for (int m = 0; m < MAXT; ++m) {
-            if (ti[m] < 0) continue;
-#pragma unroll
-            for (int e = 0; e < 16; ++e) {
-                const int i = 4 * ti[m] + (e >> 2), j = 4 * tj[m] + (e & 3);
-                float v = acc[m][e];
-                if (i == j) v += (i < k) ? lambda : 1.0f;  // padded diagonal -> 1 keeps the factorisation finite
-                A[i * kp + j] = v;
-            }
-        }
-        if (tid < kp) bvec[tid] = tid < k ? bacc : 0.0f;
-        __syncthreads();
 
-        // in-place lower Cholesky, right-looking
-        for (int j = 0; j < k; ++j) {
-            if (tid == 0) A[j * kp + j] = sqrtf(A[j * kp + j]);
+        // split-K: groups 1.. hand their partial tiles to group 0, added in group order
+        if (ks > 1) {
+            if (active && g > 0) {
+                float* dst = scratch + (size_t)(g - 1) * TS * TS * ntiles + q;
+#pragma unroll
+                for (int i = 0; i < TS; ++i)
+#pragma unroll
+                    for (int j = 0; j < TS; ++j) dst[(i * TS + j) * ntiles] = acc[i][j];
+            }
             __syncthreads();
-            const float inv = 1.0f / A[j * kp + j];
-            for (int i = j + 1 + tid; i < k; i += TPS) A[i * kp + j] *= inv;
-            __syncthreads();
-            const int n = k - 1 - j;
-            for (int e = tid; e < n * n; e += TPS) {
-                const int a = e / n, b = e - a * n;
-                if (b <= a) {
-                    const int i = j + 1 + a, l = j + 1 + b;
-                    A[i * kp + l] = fmaf(-A[i * kp + j], A[l * kp + j], A[i * kp + l]);
+            if (owner) {
+                for (int gg = 1; gg < ks; ++gg) {
+                    const float* src = scratch + (size_t)(gg - 1) * TS * TS * ntiles + q;
+#pragma unroll
+                    for (int i = 0; i < TS; ++i)
+#pragma unroll
+                        for (int j = 0; j < TS; ++j) acc[i][j] += src[(i * TS + j) * ntiles];
+                }
+            }
+            __syncthreads();  // the scratch may reach into Lm, which the factorisation is about to write
+        }
+        if (owner && I == J) {
+#pragma unroll
+            for (int i = 0; i < TS; ++i)
+                if (TS * I + i < k) acc[i][i] += lambda;
+        }
+
+        // ---- blocked right-looking Cholesky of M on the register tiles (columns >= k are switched off: dv = 0)
+        for (int Jb = 0; Jb < nb; ++Jb) {
+            const int jlo = Jb * TS;
+            if (owner && J == Jb && I == Jb) {
+                // diagonal tile: unblocked factorisation in registers
+#pragma unroll
+                for (int c = 0; c < TS; ++c) {
+                    const float d = acc[c][c];
+                    float inv = rsqrtf(d);
+                    inv = inv * (1.5f - 0.5f * d * inv * inv);  // one Newton step: full FP32 accuracy
+                    if (jlo + c >= k) inv = 0.0f;
+                    dv[jlo + c] = inv;
+                    acc[c][c] = d * inv;
+#pragma unroll
+                    for (int r = c + 1; r < TS; ++r) acc[r][c] *= inv;
+#pragma unroll
+                    for (int r = c + 1; r < TS; ++r)
+#pragma unroll
+                        for (int c2 = c + 1; c2 <= r; ++c2) acc[r][c2] = fmaf(-acc[r][c], acc[c2][c], acc[r][c2]);
+                }
+#pragma unroll
+                for (int c = 0; c < TS; ++c) {
+#pragma unroll
+                    for (int r = 0; r < TS; ++r) Ld[r * TS + c] = r >= c ? acc[r][c] : 0.0f;
+                    float* col = Lm + (jlo + c) * kp;
+                    *reinterpret_cast<float4*>(col + 4 * Jb) =
+                        make_float4(c <= 0 ? acc[0][c] : 0.0f, c <= 1 ? acc[1][c] : 0.0f, c <= 2 ? acc[2][c] : 0.0f, c <= 3 ? acc[3][c] : 0.0f);
+                    if (TS == 8)
+                        *reinterpret_cast<float4*>(col + 4 * (nb + Jb)) =
+                            make_float4(c <= TS - 4 ? acc[TS - 4][c] : 0.0f, c <= TS - 3 ? acc[TS - 3][c] : 0.0f,
+                                        c <= TS - 2 ? acc[TS - 2][c] : 0.0f, acc[TS - 1][c]);
                 }
             }
             __syncthreads();
+            if (owner && J == Jb && I > Jb) {
+                // panel tile: X L_JJ^T = A_IJ, row by row
+#pragma unroll
+                for (int c = 0; c < TS; ++c) {
+                    const float dc = dv[jlo + c];
+#pragma unroll
+                    for (int r = 0; r < TS; ++r) {
+                        float v = acc[r][c];
+#pragma unroll
+                        for (int c2 = 0; c2 < c; ++c2) v = fmaf(-acc[r][c2], Ld[c * TS + c2], v);
+                        acc[r][c] = v * dc;
+                    }
+                    float* col = Lm + (jlo + c) * kp;
+                    *reinterpret_cast<float4*>(col + 4 * I) = make_float4(acc[0][c], acc[1][c], acc[2][c], acc[3][c]);
+                    if (TS == 8)
+                        *reinterpret_cast<float4*>(col + 4 * (nb + I)) =
+                            make_float4(acc[TS - 4][c], acc[TS - 3][c], acc[TS - 2][c], acc[TS - 1][c]);
+                }
+            }
+            __syncthreads();
+            if (owner && J > Jb) {
+                // trailing tile: A_IJ -= L_I,Jb L_J,Jb^T — the Gram loop with a minus sign over the TS fresh columns of L
+#pragma unroll 2
+                for (int c = 0; c < TS; ++c) {
+                    float a[TS], b[TS];
+                    load_tile_vec<TS>(Lm + (jlo + c) * kp, I, nb, a);
+                    load_tile_vec<TS>(Lm + (jlo + c) * kp, J, nb, b);
+                    rank1<TS, true>(acc, a, b);
+                }
+            }
         }
-        // L y = b, then L^T x = y, by warp 0
+        __syncthreads();
+
+        // ---- L^T x = y by warp 0, last block first; y_j = L[k][j] sits at position posk of column j
         if (tid < 32) {
-            for (int i = 0; i < k; ++i) {
-                float p = 0.0f;
-                for (int q = tid; q < i; q += 32) p = fmaf(A[i * kp + q], bvec[q], p);
-                p = warp_sum(p);
-                if (tid == 0) bvec[i] = (bvec[i] - p) / A[i * kp + i];
+            const int nch = kp >> 2;
+            for (int Jb = nb - 1; Jb >= 0; --Jb) {
+                const int jlo = Jb * TS;
+                float p[TS];
+#pragma unroll
+                for (int c = 0; c < TS; ++c) p[c] = 0.0f;
+                for (int pc = tid; pc < nch; pc += 32) {
+                    const int nat = TS == 8 ? (pc < nb ? 2 * pc : 2 * (pc - nb) + 1) : pc;  // natural chunk at this position
+                    if (4 * nat >= jlo + TS) {                                                // rows already solved
+                        const float4 xv = *reinterpret_cast<const float4*>(xs + 4 * pc);
+#pragma unroll
+                        for (int c = 0; c < TS; ++c) {
+                            const float4 lv = *reinterpret_cast<const float4*>(Lm + (jlo + c) * kp + 4 * pc);
+                            p[c] = fmaf(lv.x, xv.x, fmaf(lv.y, xv.y, fmaf(lv.z, xv.z, fmaf(lv.w, xv.w, p[c]))));
+                        }
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < TS; ++c) p[c] = warp_sum(p[c]);
+                float xb[TS];
+#pragma unroll
+                for (int c = TS - 1; c >= 0; --c) {
+                    const float* col = Lm + (jlo + c) * kp;
+                    float v = col[posk] - p[c];
+#pragma unroll
+                    for (int c2 = c + 1; c2 < TS; ++c2) v = fmaf(-col[pos_of<TS>(jlo + c2, nb)], xb[c2], v);
+                    xb[c] = (jlo + c < k) ? v * dv[jlo + c] : 0.0f;
+                }
+                if (tid == 0) {
+#pragma unroll
+                    for (int c = 0; c < TS; ++c) xs[pos_of<TS>(jlo + c, nb)] = xb[c];
+                }
                 __syncwarp();
             }
-            for (int i = k - 1; i >= 0; --i) {
-                float p = 0.0f;
-                for (int q = i + 1 + tid; q < k; q += 32) p = fmaf(A[q * kp + i], bvec[q], p);
-                p = warp_sum(p);
-                if (tid == 0) bvec[i] = (bvec[i] - p) / A[i * kp + i];
-                __syncwarp();
-            }
-            for (int c = tid; c < k; c += 32) x[c] = bvec[c];
+            for (int c = tid; c < k; c += 32) x[c] = xs[pos_of<TS>(c, nb)];
         }
     }
 }
 
-template <int TPS, int MAXT, int VW>
-int launch_als_vw(int64_t nseg, const uint32_t* order, unsigned* queue, const Side& s, const float* Y, float* X, int k,
-                  int kp, float lambda, int sm_count, cudaStream_t st) {
-    const size_t smem = sizeof(float) * ((size_t)kp * kp + kp + 2 * (size_t)kBatch * kp + 2 * kBatch) + sizeof(uint32_t) * 2 * kBatch;
+struct AlsGeometry {
+    int TS, nb, kp, ntiles, ks, tps;
+    size_t smem;
+};
+
+AlsGeometry als_geometry(int k) {
+    AlsGeometry G;
+    G.TS = (k + 1 <= 24) ? 4 : 8;
+    G.nb = (k + 1 + G.TS - 1) / G.TS;
+    G.kp = G.nb * G.TS;
+    G.ntiles = G.nb * (G.nb + 1) / 2;
+    const int target = G.TS == 4 ? (G.ntiles <= 10 ? 32 : 64) : (G.ntiles <= 36 ? 96 : 192);
+    G.ks = std::max(1, std::min(8, target / G.ntiles));
+    G.tps = (G.ntiles * G.ks + 31) / 32 * 32;
+    const size_t stage = 2 * (size_t)kBatch * G.kp + (size_t)G.kp * G.kp;
+    const size_t scratch = (size_t)(G.ks - 1) * G.TS * G.TS * G.ntiles;
+    const size_t floats = std::max(stage, scratch) + G.TS * G.TS + 2 * (size_t)G.kp;
+    G.smem = sizeof(float) * floats + sizeof(uint32_t) * 2 * kBatch;
+    return G;
+}
+
+template <int TS, int VW>
+int launch_als(const AlsGeometry& G, int64_t nseg, const uint32_t* order, unsigned* queue, const Side& s, const float* Y, float* X,
+               int k, float lambda, int sm_count, cudaStream_t st) {
     static size_t attr = 0;
-    if (smem > 48 * 1024 && smem > attr) {
-        MF_CUDA(cudaFuncSetAttribute(k_als_half<TPS, MAXT, VW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr = smem;
+    if (G.smem > 48 * 1024 && G.smem > attr) {
+        MF_CUDA(cudaFuncSetAttribute(k_als_tile<TS, VW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.smem));
+        attr = G.smem;
     }
     int per_sm = 1;
-    MF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_als_half<TPS, MAXT, VW>, TPS, smem));
+    MF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_als_tile<TS, VW>, G.tps, G.smem));
     if (per_sm < 1) per_sm = 1;
     int64_t grid = (int64_t)sm_count * per_sm;
     if (grid > nseg) grid = nseg;
-    k_als_half<TPS, MAXT, VW><<<(unsigned)grid, TPS, smem, st>>>(nseg, order, queue, s.ptr, s.idx, s.val, Y, X, k, kp, lambda);
+    k_als_tile<TS, VW><<<(unsigned)grid, G.tps, G.smem, st>>>(nseg, order, queue, s.ptr, s.idx, s.val, Y, X, k, G.nb, G.ks, lambda);
     MF_CUDA(cudaGetLastError());
     return MF_OK;
 }
 
-template <int TPS, int MAXT>
-int launch_als(int64_t nseg, const uint32_t* order, unsigned* queue, const Side& s, const float* Y, float* X, int k,
-               int kp, float lambda, int sm_count, cudaStream_t st) {
-    if (k % 4 == 0) return launch_als_vw<TPS, MAXT, 4>(nseg, order, queue, s, Y, X, k, kp, lambda, sm_count, st);
-    if (k % 2 == 0) return launch_als_vw<TPS, MAXT, 2>(nseg, order, queue, s, Y, X, k, kp, lambda, sm_count, st);
-    return launch_als_vw<TPS, MAXT, 1>(nseg, order, queue, s, Y, X, k, kp, lambda, sm_count, st);
+template <int TS>
+int launch_als_ts(const AlsGeometry& G, int64_t nseg, const uint32_t* order, unsigned* queue, const Side& s, const float* Y,
+                  float* X, int k, float lambda, int sm_count, cudaStream_t st) {
+    if (k % 4 == 0) return launch_als<TS, 4>(G, nseg, order, queue, s, Y, X, k, lambda, sm_count, st);
+    if (k % 2 == 0) return launch_als<TS, 2>(G, nseg, order, queue, s, Y, X, k, lambda, sm_count, st);
+    return launch_als<TS, 1>(G, nseg, order, queue, s, Y, X, k, lambda, sm_count, st);
 }
 
 }  // namespace
 
-int als_half_step(const Side& s, const float* Y, float* X, int k, float lambda, int sm_count, cudaStream_t st) {
-    if (s.nseg <= 0) return MF_OK;
-    const int kp = (k + 3) / 4 * 4;
-    const int nb = kp / 4, ntiles = nb * (nb + 1) / 2;
-    // scratch: bin counters, cursors, queue head, longest-first order (rebuilt per call: a few microseconds)
-    unsigned* scratch = nullptr;
-    uint32_t* order = nullptr;
-    MF_TRY(dev_alloc(&scratch, 33 + 33 + 1));
-    MF_TRY(dev_alloc(&order, (size_t)s.nseg));
-    MF_CUDA(cudaMemsetAsync(scratch, 0, sizeof(unsigned) * 67, st));
+// the longest-first segment order of a side, built on first use and kept for the life of the session
+int als_prepare(Side& s, cudaStream_t st) {
+    if (s.als_order || s.nseg <= 0) return MF_OK;
+    MF_TRY(dev_alloc(&s.als_scratch, 33 + 33 + 1));
+    MF_TRY(dev_alloc(&s.als_order, (size_t)s.nseg));
+    MF_CUDA(cudaMemsetAsync(s.als_scratch, 0, sizeof(unsigned) * 67, st));
     const unsigned g = (unsigned)((s.nseg + 255) / 256);
-    k_bin_count<<<g, 256, 0, st>>>(s.nseg, s.ptr, scratch);
-    k_bin_scan<<<1, 32, 0, st>>>(scratch, scratch + 33);
-    k_order_by_bin<<<g, 256, 0, st>>>(s.nseg, s.ptr, scratch + 33, order);
+    k_bin_count<<<g, 256, 0, st>>>(s.nseg, s.ptr, s.als_scratch);
+    k_bin_scan<<<1, 32, 0, st>>>(s.als_scratch, s.als_scratch + 33);
+    k_order_by_bin<<<g, 256, 0, st>>>(s.nseg, s.ptr, s.als_scratch + 33, s.als_order);
     MF_CUDA(cudaGetLastError());
-    unsigned* queue = scratch + 66;
-    int rc;
-    if (ntiles <= 32)       rc = launch_als<32, 1>(s.nseg, order, queue, s, Y, X, k, kp, lambda, sm_count, st);
-    else if (ntiles <= 64)  rc = launch_als<64, 1>(s.nseg, order, queue, s, Y, X, k, kp, lambda, sm_count, st);
-    else if (ntiles <= 128) rc = launch_als<128, 1>(s.nseg, order, queue, s, Y, X, k, kp, lambda, sm_count, st);
-    else if (ntiles <= 256) rc = launch_als<256, 1>(s.nseg, order, queue, s, Y, X, k, kp, lambda, sm_count, st);
-    else if (ntiles <= 512) rc = launch_als<256, 2>(s.nseg, order, queue, s, Y, X, k, kp, lambda, sm_count, st);
-    else if (ntiles <= 768) rc = launch_als<256, 3>(s.nseg, order, queue, s, Y, X, k, kp, lambda, sm_count, st);
-    else { set_error("ALS: k=%d not supported yet (k <= 152)", k); rc = MF_ERR_UNSUPPORTED; }
-    cudaError_t e = cudaStreamSynchronize(st);
-    cudaFree(scratch);
-    cudaFree(order);
-    if (rc == MF_OK && e != cudaSuccess) { set_error("ALS half-step failed: %s", cudaGetErrorString(e)); rc = MF_ERR_CUDA; }
-    return rc;
+    return MF_OK;
+}
+
+int als_half_step(Side& s, const float* Y, float* X, int k, float lambda, int sm_count, cudaStream_t st) {
+    if (s.nseg <= 0) return MF_OK;
+    const AlsGeometry G = als_geometry(k);
+    if (G.smem > 227 * 1024 || G.tps > (G.TS == 8 ? 384 : 128)) {
+        set_error("ALS: k=%d needs %zu bytes of shared memory per CTA (limit 227 KB)", k, G.smem);
+        return MF_ERR_UNSUPPORTED;
+    }
+    MF_TRY(als_prepare(s, st));
+    unsigned* queue = s.als_scratch + 66;
+    MF_CUDA(cudaMemsetAsync(queue, 0, sizeof(unsigned), st));
+    if (G.TS == 8) return launch_als_ts<8>(G, s.nseg, s.als_order, queue, s, Y, X, k, lambda, sm_count, st);
+    return launch_als_ts<4>(G, s.nseg, s.als_order, queue, s, Y, X, k, lambda, sm_count, st);
 }
 
 }  // namespace mf

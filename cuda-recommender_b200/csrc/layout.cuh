@@ -63,6 +63,9 @@ struct Side {
     uint32_t* panel_item_ptr = nullptr; // [npanels+1]
     int ncta = 0;
     bool sorted = true;
+    // ALS: longest-first segment order + bin counters / queue head (als.cu, built on first use)
+    uint32_t* als_order = nullptr;  // [nseg]
+    unsigned* als_scratch = nullptr;
 };
 
 int side_free(Side& s);

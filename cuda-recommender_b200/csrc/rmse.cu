@@ -3,8 +3,9 @@
 // (cuda_src/CUDA_AUX.cu:3-27) plus a D2H copy of one float per test rating and a serial host sum
 // (cuda_src/CCD_CUDA.cu:385-401) on the GPU path.  Here: one thread per test rating, prediction =
 // sum over ranks of the FP32 product W*H promoted into a double accumulator (the CPU path's
-// arithmetic), squared error in double, warp + CTA reduction, one double atomicAdd per CTA, and a
-// single scalar comes back to the host.
+// arithmetic), squared error in double, warp + CTA reduction, one partial per CTA; the last CTA to
+// finish adds the partials in CTA order (fixed tree: the sum does not depend on scheduling, so two
+// runs over the same factors give the same bits), and a single scalar comes back to the host.
 #include "rmse.cuh"
 
 namespace mf {
@@ -15,7 +16,9 @@ __global__ void __launch_bounds__(256) k_rmse(int64_t nt, const uint32_t* __rest
                                                const float* __restrict__ H, int k, int64_t w_rank_stride,
                                                int64_t w_row_stride, int64_t h_rank_stride, int64_t h_row_stride,
                                                double* __restrict__ acc) {
+    // acc[0] = result, acc[1 .. gridDim.x] = per-CTA partials, ticket counter behind them (rmse_scratch_doubles)
     __shared__ double part[8];
+    __shared__ bool s_last;
     double local = 0.0;
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < nt; e += (int64_t)gridDim.x * blockDim.x) {
         const float* w = W + (int64_t)trow[e] * w_row_stride;
@@ -32,19 +35,40 @@ __global__ void __launch_bounds__(256) k_rmse(int64_t nt, const uint32_t* __rest
     if (threadIdx.x < 32) {
         double v = threadIdx.x < (blockDim.x >> 5) ? part[threadIdx.x] : 0.0;
         v = warp_sum(v);
-        if (threadIdx.x == 0 && v != 0.0) atomicAdd(acc, v);
+        if (threadIdx.x == 0) {
+            acc[1 + blockIdx.x] = v;
+            __threadfence();
+            unsigned* ticket = reinterpret_cast<unsigned*>(acc + 1 + gridDim.x);
+            s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+        }
+    }
+    __syncthreads();
+    if (s_last && threadIdx.x < 32) {
+        __threadfence();
+        double v = 0.0;
+        for (unsigned b = threadIdx.x; b < gridDim.x; b += 32) v += __ldcg(acc + 1 + b);
+        v = warp_sum(v);
+        if (threadIdx.x == 0) {
+            acc[0] = v;
+            *reinterpret_cast<unsigned*>(acc + 1 + gridDim.x) = 0u;
+        }
     }
 }
 
 }  // namespace
 
+size_t rmse_scratch_doubles(int sm_count) { return 1 + (size_t)sm_count * 8 + 1; }
+
 int rmse_accumulate(int64_t nt, const uint32_t* trow, const uint32_t* tcol, const float* tval, const float* W,
                     const float* H, int k, int64_t w_rank_stride, int64_t w_row_stride, int64_t h_rank_stride,
                     int64_t h_row_stride, double* d_acc, int sm_count, cudaStream_t st) {
-    MF_CUDA(cudaMemsetAsync(d_acc, 0, sizeof(double), st));
-    if (nt <= 0) return MF_OK;
+    if (nt <= 0) {
+        MF_CUDA(cudaMemsetAsync(d_acc, 0, sizeof(double), st));
+        return MF_OK;
+    }
     int64_t blocks = (nt + 255) / 256;
     if (blocks > (int64_t)sm_count * 8) blocks = (int64_t)sm_count * 8;
+    MF_CUDA(cudaMemsetAsync(d_acc + 1 + blocks, 0, sizeof(double), st));  // ticket
     k_rmse<<<(unsigned)blocks, 256, 0, st>>>(nt, trow, tcol, tval, W, H, k, w_rank_stride, w_row_stride, h_rank_stride,
                                             h_row_stride, d_acc);
     MF_CUDA(cudaGetLastError());

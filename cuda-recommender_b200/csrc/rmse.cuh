@@ -3,6 +3,8 @@
 namespace mf {
 // *d_acc <- sum over test ratings of (w_i . h_j - r)^2.  Strides describe the factor layout:
 // CCD++ (W[t*ld + i]): rank_stride = ld, row_stride = 1;  ALS (W[i*k + t]): rank_stride = 1, row_stride = k.
+// d_acc needs rmse_scratch_doubles(sm_count) doubles: [0] result, per-CTA partials, ticket word.
+size_t rmse_scratch_doubles(int sm_count);
 int rmse_accumulate(int64_t nt, const uint32_t* trow, const uint32_t* tcol, const float* tval, const float* W,
                     const float* H, int k, int64_t w_rank_stride, int64_t w_row_stride, int64_t h_rank_stride,
                     int64_t h_row_stride, double* d_acc, int sm_count, cudaStream_t st);

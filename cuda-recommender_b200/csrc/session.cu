@@ -439,7 +439,7 @@ int create_impl(const mf_ratings* R, const mf_testset* T, const mf_params* param
         cudaMemcpyAsync(s->tcol, T->col, sizeof(uint32_t) * (size_t)s->nt, cudaMemcpyDefault, s->st);
         cudaMemcpyAsync(s->tval, T->val, sizeof(float) * (size_t)s->nt, cudaMemcpyDefault, s->st);
     }
-    if ((rc = dev_alloc(&s->d_acc, 1)) != MF_OK) return fail(rc);
+    if ((rc = dev_alloc(&s->d_acc, rmse_scratch_doubles(s->sm_count))) != MF_OK) return fail(rc);
     if (nranks > 1) {
         if (!nccl_id) { set_error("multi-GPU session needs the shared ncclUniqueId"); return fail(MF_ERR_ARG); }
         if ((rc = dist_create(&s->dist, rank, nranks, nccl_id, s->device)) != MF_OK) return fail(rc);

@@ -80,5 +80,5 @@ unsigned dist_next_epoch(Dist* d);
 int dist_allgather_blocks(Dist* d, float* vec, const std::vector<int64_t>& bound, int64_t elems_per_unit, cudaStream_t st);
 int dist_allreduce_sum_double(Dist* d, double* dev_value, cudaStream_t st);
 // als.cu
-int als_half_step(const Side& s, const float* Y, float* X, int k, float lambda, int sm_count, cudaStream_t st);
+int als_half_step(Side& s, const float* Y, float* X, int k, float lambda, int sm_count, cudaStream_t st);
 }  // namespace mf
