@@ -30,6 +30,7 @@ namespace mf {
 namespace {
 
 constexpr int kBatch = 32;  // factor rows staged per step
+constexpr int kStages = 3;  // staging buffers
 
 // segment order: longest-first by degree bin (bit length of the degree), via per-bin cursors
 __global__ void k_order_by_bin(int64_t nseg, const uint32_t* __restrict__ ptr, unsigned* __restrict__ cursor /*[33]*/,
@@ -91,21 +92,25 @@ __device__ __forceinline__ void rank1(float (&acc)[TS][TS], const float (&a)[TS]
 
 // TS = tile edge; VW = floats per copy (4 when k % 4 == 0, 2 when k is even, else 1): every factor row starts VW-aligned.
 // nb = tiles per matrix edge (nb * TS >= k + 1); ks = split-K groups; threads 0 .. ks*ntiles-1 work on the Gram matrix.
-template <int TS, int VW>
-__global__ void __launch_bounds__(TS == 8 ? 384 : 128)
+// MAXREG: register cap (sets how many CTAs fit an SM: 112 -> 3 x 192 or 6 x 96 threads, 168 -> 384 threads, 64 -> 2048).
+// Staging: three buffers of kBatch rows, one barrier per batch — while batch b is accumulated, batch b+1 is landing and
+// batch b+2 is being issued into the buffer batch b-1 just left.  2^tl threads share the copies of one row.
+// Shared memory is one region used in turn as staging buffers (Gram loop), split-K scratch and L (factorisation).
+template <int TS, int VW, int MAXREG>
+__global__ void __maxnreg__(MAXREG)
 k_als_tile(int64_t nseg, const uint32_t* __restrict__ order, unsigned* __restrict__ queue, const uint32_t* __restrict__ ptr,
            const uint32_t* __restrict__ idx, const float* __restrict__ val, const float* __restrict__ Y, float* __restrict__ X,
-           int k, int nb, int ks, float lambda) {
+           int k, int nb, int ks, int tl, int region_floats, float lambda) {
     extern __shared__ __align__(16) float sm[];
     const int kp = nb * TS;
     const int ntiles = nb * (nb + 1) / 2;
-    float* Ys = sm;                               // [2][kBatch][kp]  staged rows [factor row | rating | 0...]
-    float* Lm = Ys + 2 * kBatch * kp;             // [kp][kp]         Lm[j*kp + pos(i)] = L[i][j]
-    float* Ld = Lm + kp * kp;                     // [TS][TS]         diagonal tile being applied (natural order)
-    float* dv = Ld + TS * TS;                     // [kp]             1 / L[i][i]  (0 for i >= k)
-    float* xs = dv + kp;                          // [kp]             solution at positions pos(i)
-    uint32_t* sidx = reinterpret_cast<uint32_t*>(xs + kp);  // [2][kBatch] row ids of the batches to be fetched
-    float* scratch = sm;                          // split-K partial tiles, aliases Ys (+ Lm): [(ks-1)][TS*TS][ntiles]
+    float* Ys = sm;                               // [kStages][kBatch][kp]  staged rows [factor row | rating | 0...]
+    float* Lm = sm;                               // [kp][kp]               Lm[j*kp + pos(i)] = L[i][j]
+    float* scratch = sm;                          // [(ks-1)][TS*TS][ntiles] split-K partial tiles
+    float* Ld = sm + region_floats;               // [TS][TS]               diagonal tile being applied (natural order)
+    float* dv = Ld + TS * TS;                     // [kp]                   1 / L[i][i]  (0 for i >= k)
+    float* xs = dv + kp;                          // [kp]                   solution at positions pos(i)
+    uint32_t* sidx = reinterpret_cast<uint32_t*>(xs + kp);  // [kStages][kBatch] row ids of the batches to be fetched
     __shared__ unsigned s_next;
 
     const int tid = threadIdx.x;
@@ -123,8 +128,8 @@ k_als_tile(int64_t nseg, const uint32_t* __restrict__ order, unsigned* __restric
     const bool owner = tid < ntiles;              // group 0 keeps the tile for the factorisation
     const int posk = pos_of<TS>(k, nb);           // where the rating sits in a staged row / y = L[k][.] in a column
     const int cpr = k / VW;                       // copies per factor row
-
-    for (int e = tid; e < 2 * kBatch * kp; e += TPS) Ys[e] = 0.0f;
+    const int cl = tid & ((1 << tl) - 1);         // this thread's first copy inside a row
+    const int r0 = tid >> tl, rstep = TPS >> tl;  // its first row, rows per pass
 
     for (;;) {
         __syncthreads();
@@ -146,46 +151,56 @@ k_als_tile(int64_t nseg, const uint32_t* __restrict__ order, unsigned* __restric
             for (int j = 0; j < TS; ++j) acc[i][j] = 0.0f;
 
         const int nbatch = (int)((hi - lo + kBatch - 1) / kBatch);
-        // the split-K scratch of the previous segment overwrote the staging buffers: the pad columns behind the
-        // rating have to be zero again (the copies never touch them)
-        if (ks > 1)
-            for (int e = tid; e < 2 * kBatch * (kp - k - 1); e += TPS) {
-                const int r = e / (kp - k - 1), c = k + 1 + (e - r * (kp - k - 1));
+        // the previous segment left its L in the staging region: the pad columns behind the rating have to be zero
+        // again (the copies never touch them)
+        {
+            const int npad = kp - k - 1;
+            for (int e = tid; e < kStages * kBatch * npad; e += TPS) {
+                const int r = e / npad, c = k + 1 + (e - r * npad);
                 Ys[r * kp + pos_of<TS>(c, nb)] = 0.0f;
             }
-        // issue the asynchronous gather of batch `b` into buffer b&1, row ids taken from sidx[b&1]
-        auto issue_rows = [&](int b) {
-            const int nrow = (int)min((uint32_t)kBatch, hi - (lo + (uint32_t)b * kBatch));
-            float* dst = Ys + (b & 1) * kBatch * kp;
-            const uint32_t* ids = sidx + (b & 1) * kBatch;
-            for (int e = tid; e < nrow * cpr; e += TPS) {
-                const int r = e / cpr, c = (e - r * cpr) * VW;
-                cp_async<VW * 4>(dst + r * kp + pos_of<TS>(c, nb), Y + (size_t)ids[r] * k + c);
+        }
+        // asynchronous gather of batch `b` (factor rows + ratings) into buffer b % kStages, row ids from sidx
+        auto issue_rows = [&](int b, int buf) {
+            const uint32_t base = lo + (uint32_t)b * kBatch;
+            const int nrow = (int)min((uint32_t)kBatch, hi - base);
+            float* dst = Ys + buf * kBatch * kp;
+            const uint32_t* ids = sidx + buf * kBatch;
+            for (int r = r0; r < nrow; r += rstep) {
+                const float* src = Y + (size_t)ids[r] * k;
+                for (int c = cl; c < cpr; c += (1 << tl)) cp_async<VW * 4>(dst + r * kp + pos_of<TS>(c * VW, nb), src + c * VW);
+                if (cl == 0) cp_async<4>(dst + r * kp + posk, val + base + r);
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
         };
-        // prologue: ids + ratings of batches 0 and 1, rows of batch 0
+        // prologue: ids of batches 0..2, rows of batches 0 and 1
         if (tid < kBatch) {
-            const uint32_t e0 = lo + tid, e1 = lo + kBatch + tid;
-            if (e0 < hi) { sidx[tid] = __ldg(idx + e0); Ys[tid * kp + posk] = __ldg(val + e0); }
-            if (e1 < hi) { sidx[kBatch + tid] = __ldg(idx + e1); Ys[(kBatch + tid) * kp + posk] = __ldg(val + e1); }
+#pragma unroll
+            for (int j = 0; j < kStages; ++j) {
+                const uint32_t e = lo + j * kBatch + tid;
+                if (e < hi) sidx[j * kBatch + tid] = __ldg(idx + e);
+            }
         }
         __syncthreads();
-        issue_rows(0);
+        issue_rows(0, 0);
+        if (nbatch > 1) issue_rows(1, 1); else asm volatile("cp.async.commit_group;" ::: "memory");
 
+        int buf = 0;  // b % kStages
         for (int b = 0; b < nbatch; ++b) {
             const int nrow = (int)min((uint32_t)kBatch, hi - (lo + (uint32_t)b * kBatch));
-            if (b + 1 < nbatch) issue_rows(b + 1); else asm volatile("cp.async.commit_group;" ::: "memory");
-            // ids + ratings of batch b+2 travel in registers while batch b is accumulated
-            uint32_t nid = 0; float nr = 0.0f;
-            const uint32_t e2 = lo + (uint32_t)(b + 2) * kBatch + tid;
-            const bool has2 = tid < kBatch && b + 2 < nbatch && e2 < hi;
-            if (has2) { nid = __ldg(idx + e2); nr = __ldg(val + e2); }
+            // ids of batch b+3 travel in a register across the barrier
+            uint32_t nid = 0;
+            const uint32_t e3 = lo + (uint32_t)(b + kStages) * kBatch + tid;
+            const bool has3 = tid < kBatch && e3 < hi;
+            if (has3) nid = __ldg(idx + e3);
             asm volatile("cp.async.wait_group 1;" ::: "memory");  // batch b has landed (batch b+1 may be in flight)
-            __syncthreads();
-            const float* Yb = Ys + (b & 1) * kBatch * kp;
+            __syncthreads();                                      // ... for everybody; everybody is done with batch b-1
+            const int buf2 = buf >= 1 ? buf - 1 : kStages - 1;    // (b + 2) % kStages: the buffer batch b-1 left
+            if (b + 2 < nbatch) issue_rows(b + 2, buf2); else asm volatile("cp.async.commit_group;" ::: "memory");
+            if (has3) sidx[buf * kBatch + tid] = nid;             // the ids of batch b were consumed two iterations ago
+            const float* Yb = Ys + buf * kBatch * kp;
             if (active) {
-#pragma unroll 2
+#pragma unroll(TS == 8 ? 2 : 4)
                 for (int r = g; r < nrow; r += ks) {
                     float a[TS], c[TS];
                     load_tile_vec<TS>(Yb + r * kp, I, nb, a);
@@ -193,11 +208,10 @@ k_als_tile(int64_t nseg, const uint32_t* __restrict__ order, unsigned* __restric
                     rank1<TS, false>(acc, a, c);
                 }
             }
-            __syncthreads();  // everyone is done with buffer b&1 and its ids
-            if (has2) { sidx[(b & 1) * kBatch + tid] = nid; Ys[((b & 1) * kBatch + tid) * kp + posk] = nr; }
-            __syncthreads();  // ids of batch b+2 are in place before the next iteration issues its rows
+            buf = buf + 1 == kStages ? 0 : buf + 1;
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();  // everybody is done with the staging buffers: the region becomes scratch / L
 
         // split-K: groups 1.. hand their partial tiles to group 0, added in group order
         if (ks > 1) {
@@ -335,7 +349,7 @@ k_als_tile(int64_t nseg, const uint32_t* __restrict__ order, unsigned* __restric
 }
 
 struct AlsGeometry {
-    int TS, nb, kp, ntiles, ks, tps;
+    int TS, nb, kp, ntiles, ks, tps, tl, region_floats;
     size_t smem;
 };
 
@@ -348,37 +362,53 @@ AlsGeometry als_geometry(int k) {
     const int target = G.TS == 4 ? (G.ntiles <= 10 ? 32 : 64) : (G.ntiles <= 36 ? 96 : 192);
     G.ks = std::max(1, std::min(8, target / G.ntiles));
     G.tps = (G.ntiles * G.ks + 31) / 32 * 32;
-    const size_t stage = 2 * (size_t)kBatch * G.kp + (size_t)G.kp * G.kp;
+    const int vw = k % 4 == 0 ? 4 : (k % 2 == 0 ? 2 : 1);
+    G.tl = 0;
+    while ((1 << G.tl) < k / vw && G.tl < 5) ++G.tl;
+    const size_t stage = (size_t)kStages * kBatch * G.kp, lmat = (size_t)G.kp * G.kp;
     const size_t scratch = (size_t)(G.ks - 1) * G.TS * G.TS * G.ntiles;
-    const size_t floats = std::max(stage, scratch) + G.TS * G.TS + 2 * (size_t)G.kp;
-    G.smem = sizeof(float) * floats + sizeof(uint32_t) * 2 * kBatch;
+    G.region_floats = (int)((std::max(std::max(stage, lmat), scratch) + 3) / 4 * 4);
+    G.smem = sizeof(float) * ((size_t)G.region_floats + G.TS * G.TS + 2 * (size_t)G.kp) + sizeof(uint32_t) * kStages * kBatch;
     return G;
 }
 
-template <int TS, int VW>
+template <int TS, int VW, int MAXREG>
 int launch_als(const AlsGeometry& G, int64_t nseg, const uint32_t* order, unsigned* queue, const Side& s, const float* Y, float* X,
                int k, float lambda, int sm_count, cudaStream_t st) {
     static size_t attr = 0;
     if (G.smem > 48 * 1024 && G.smem > attr) {
-        MF_CUDA(cudaFuncSetAttribute(k_als_tile<TS, VW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.smem));
+        MF_CUDA(cudaFuncSetAttribute(k_als_tile<TS, VW, MAXREG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.smem));
         attr = G.smem;
     }
     int per_sm = 1;
-    MF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_als_tile<TS, VW>, G.tps, G.smem));
+    MF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_als_tile<TS, VW, MAXREG>, G.tps, G.smem));
     if (per_sm < 1) per_sm = 1;
     int64_t grid = (int64_t)sm_count * per_sm;
     if (grid > nseg) grid = nseg;
-    k_als_tile<TS, VW><<<(unsigned)grid, G.tps, G.smem, st>>>(nseg, order, queue, s.ptr, s.idx, s.val, Y, X, k, G.nb, G.ks, lambda);
+    k_als_tile<TS, VW, MAXREG><<<(unsigned)grid, G.tps, G.smem, st>>>(nseg, order, queue, s.ptr, s.idx, s.val, Y, X, k, G.nb,
+                                                                        G.ks, G.tl, G.region_floats, lambda);
     MF_CUDA(cudaGetLastError());
     return MF_OK;
+}
+
+template <int TS, int VW>
+int launch_als_vw(const AlsGeometry& G, int64_t nseg, const uint32_t* order, unsigned* queue, const Side& s, const float* Y,
+                  float* X, int k, float lambda, int sm_count, cudaStream_t st) {
+    // register classes: 64 (4 x 4 tiles: any number of 32/64-thread CTAs), 112 (8 x 8 tiles: 3 x 192 or 6 x 96 threads per
+    // SM), 168 (8 x 8 tiles, up to 384 threads)
+    if constexpr (TS == 4) return launch_als<TS, VW, 64>(G, nseg, order, queue, s, Y, X, k, lambda, sm_count, st);
+    else {
+        if (G.tps <= 192) return launch_als<TS, VW, 112>(G, nseg, order, queue, s, Y, X, k, lambda, sm_count, st);
+        return launch_als<TS, VW, 168>(G, nseg, order, queue, s, Y, X, k, lambda, sm_count, st);
+    }
 }
 
 template <int TS>
 int launch_als_ts(const AlsGeometry& G, int64_t nseg, const uint32_t* order, unsigned* queue, const Side& s, const float* Y,
                   float* X, int k, float lambda, int sm_count, cudaStream_t st) {
-    if (k % 4 == 0) return launch_als<TS, 4>(G, nseg, order, queue, s, Y, X, k, lambda, sm_count, st);
-    if (k % 2 == 0) return launch_als<TS, 2>(G, nseg, order, queue, s, Y, X, k, lambda, sm_count, st);
-    return launch_als<TS, 1>(G, nseg, order, queue, s, Y, X, k, lambda, sm_count, st);
+    if (k % 4 == 0) return launch_als_vw<TS, 4>(G, nseg, order, queue, s, Y, X, k, lambda, sm_count, st);
+    if (k % 2 == 0) return launch_als_vw<TS, 2>(G, nseg, order, queue, s, Y, X, k, lambda, sm_count, st);
+    return launch_als_vw<TS, 1>(G, nseg, order, queue, s, Y, X, k, lambda, sm_count, st);
 }
 
 }  // namespace
@@ -400,7 +430,7 @@ int als_prepare(Side& s, cudaStream_t st) {
 int als_half_step(Side& s, const float* Y, float* X, int k, float lambda, int sm_count, cudaStream_t st) {
     if (s.nseg <= 0) return MF_OK;
     const AlsGeometry G = als_geometry(k);
-    if (G.smem > 227 * 1024 || G.tps > (G.TS == 8 ? 384 : 128)) {
+    if (G.smem > 227 * 1024 || G.tps > (G.TS == 8 ? 384 : 64)) {
         set_error("ALS: k=%d needs %zu bytes of shared memory per CTA (limit 227 KB)", k, G.smem);
         return MF_ERR_UNSUPPORTED;
     }

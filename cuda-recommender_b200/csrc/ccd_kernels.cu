@@ -137,6 +137,76 @@ __device__ __forceinline__ void stream_batch(const PanelSweepArgs& a, uint32_t p
 #undef MF_USE_ALL
 }
 
+// Adds a segment's slots, applies the regulariser, divides: out = g / (lambda*deg + h), with lambda*deg a
+// float*unsigned product as at src/CCD.cpp:112,120; empty segment -> 0 (src/CCD.cpp:8).
+// LANES = 1: one thread per segment (slots added in order); LANES = 32: one warp per segment, lane l adds
+// slots l, l+32, ... in order and the lanes are combined by an xor-butterfly — both are fixed trees.
+// Multi-GPU epilogue (fused solve -> exchange over NVLink, CUDA IPC mappings of the
+// peers' buffers, dist.cu).  Low-latency protocol, as NCCL's LL: every freshly solved coordinate is stored into
+// each peer's receive buffer as ONE 8-byte word {value bits, epoch} — 8-byte stores arrive whole, so the epoch
+// half is the "data valid" flag and no fence or separate signal is needed.  The receiving side (k_ll_unpack)
+// polls each word of the blocks it does not own until the epoch matches and writes the value into its factor
+// vector.  (Measured alternatives, 2 GPUs, per exchange: NCCL grouped broadcast 21 us; 4-byte remote stores +
+// __threadfence_system + flag 19 us; flag + peer pull 47 us — a system-scope fence alone costs >10 us here.)
+// One receive buffer per factor matrix suffices: a rank can only produce the next generation of a vector after
+// it has unpacked everybody's blocks of the other vector, and everybody sends those only after their last sweep
+// that read the old generation (sweeps alternate u / v).  flag-based signalling remains for the rare barrier.
+struct PushArgs {
+    unsigned long long* const* peer_ll;  // [nranks] LL receive buffer (for this factor matrix) of every rank; nullptr = no push
+    unsigned* const* peer_flags;         // [nranks] flag words of every rank (barrier only)
+    unsigned* ticket;                    // local CTA counter (barrier only)
+    int64_t vec_off;                     // index of out[0] inside the factor vector (this shard's first segment)
+    int rank, nranks;
+    unsigned epoch;
+    int barrier;                         // 1: no values, publish the epoch in the peers' flag words
+};
+
+// grid-stride over segments; `partials` is read through L2 (written by other CTAs of the same launch when the
+// finalize runs inside the sweep kernel)
+template <int LANES>
+__device__ __forceinline__ void finalize_segments(int64_t nseg, const uint32_t* __restrict__ slot_ptr, const float2* partials,
+                                                  const uint32_t* __restrict__ seg_ptr, float lambda, int nmf,
+                                                  float* __restrict__ out, unsigned long long* const* peer_ll, int64_t vec_off,
+                                                  int rank, int nranks, unsigned epoch) {
+    for (int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; tid < nseg * LANES; tid += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t s = tid / LANES;
+        const int l = (int)(tid % LANES);
+        const uint32_t deg = seg_ptr[s + 1] - seg_ptr[s];
+        float g = 0.0f, h = 0.0f;
+        if (deg != 0u) {
+            const uint32_t hi = slot_ptr[s + 1];
+            for (uint32_t q = slot_ptr[s] + l; q < hi; q += LANES) {
+                const float2 pr = __ldcg(partials + q);
+                g += pr.x;
+                h += pr.y;
+            }
+        }
+        if (LANES > 1) {
+#pragma unroll
+            for (int o = 1; o < LANES; o <<= 1) {
+                g += __shfl_xor_sync(0xffffffffu, g, o);
+                h += __shfl_xor_sync(0xffffffffu, h, o);
+            }
+        }
+        if (l == 0) {
+            float r = 0.0f;
+            if (deg != 0u) {
+                r = g / (lambda * deg + h);
+                if (nmf) r = fmaxf(r, 0.0f);
+            }
+            out[s] = r;
+            if (peer_ll != nullptr) {
+                const unsigned long long word = ((unsigned long long)epoch << 32) | (unsigned long long)__float_as_uint(r);
+                for (int p = 0; p < nranks; ++p)
+                    if (p != rank) {
+                        unsigned long long* dst = peer_ll[p] + vec_off + s;
+                        asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(dst), "l"(word) : "memory");
+                    }
+            }
+        }
+    }
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(1024, 1) k_panel_sweep(PanelSweepArgs a) {
     constexpr bool SUB = MODE & kSub, ADD = MODE & kAdd, SOLVE = MODE & kSolve, ADDSEP = MODE & kAddSep;
@@ -222,6 +292,27 @@ __global__ void __launch_bounds__(1024, 1) k_panel_sweep(PanelSweepArgs a) {
         }
         ib = pe;
         ++p;
+    }
+    if (SOLVE && a.fin.enabled) {
+        // grid-wide barrier (monotonic counter; every CTA of the launch is resident), then the CTAs share the segments
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            atomicAdd(a.fin.bar, 1u);
+            unsigned v, spins = 0;
+            for (;;) {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(a.fin.bar) : "memory");
+                if ((int)(v - a.fin.bar_target) >= 0) break;
+                if (++spins > (1u << 26)) __trap();
+            }
+        }
+        __syncthreads();
+        if (a.fin.lanes == 32)
+            finalize_segments<32>(a.fin.nseg, a.fin.slot_ptr, a.partials, a.fin.seg_ptr, a.fin.lambda, a.fin.nmf, a.fin.out,
+                                  a.fin.peer_ll, a.fin.vec_off, a.fin.rank, a.fin.nranks, a.fin.epoch);
+        else
+            finalize_segments<1>(a.fin.nseg, a.fin.slot_ptr, a.partials, a.fin.seg_ptr, a.fin.lambda, a.fin.nmf, a.fin.out,
+                                 a.fin.peer_ll, a.fin.vec_off, a.fin.rank, a.fin.nranks, a.fin.epoch);
     }
 }
 
@@ -629,72 +720,13 @@ __global__ void __launch_bounds__(1024, 1) k_panel_sweep_async(PanelSweepArgs a)
     }
 }
 
-// Adds a segment's slots, applies the regulariser, divides: out = g / (lambda*deg + h), with lambda*deg a
-// float*unsigned product as at src/CCD.cpp:112,120; empty segment -> 0 (src/CCD.cpp:8).
-// LANES = 1: one thread per segment (slots added in order); LANES = 32: one warp per segment, lane l adds
-// slots l, l+32, ... in order and the lanes are combined by an xor-butterfly — both are fixed trees.
-// Multi-GPU epilogue of the finalize kernel (fused solve -> exchange over NVLink, CUDA IPC mappings of the
-// peers' buffers, dist.cu).  Low-latency protocol, as NCCL's LL: every freshly solved coordinate is stored into
-// each peer's receive buffer as ONE 8-byte word {value bits, epoch} — 8-byte stores arrive whole, so the epoch
-// half is the "data valid" flag and no fence or separate signal is needed.  The receiving side (k_ll_unpack)
-// polls each word of the blocks it does not own until the epoch matches and writes the value into its factor
-// vector.  (Measured alternatives, 2 GPUs, per exchange: NCCL grouped broadcast 21 us; 4-byte remote stores +
-// __threadfence_system + flag 19 us; flag + peer pull 47 us — a system-scope fence alone costs >10 us here.)
-// One receive buffer per factor matrix suffices: a rank can only produce the next generation of a vector after
-// it has unpacked everybody's blocks of the other vector, and everybody sends those only after their last sweep
-// that read the old generation (sweeps alternate u / v).  flag-based signalling remains for the rare barrier.
-struct PushArgs {
-    unsigned long long* const* peer_ll;  // [nranks] LL receive buffer (for this factor matrix) of every rank; nullptr = no push
-    unsigned* const* peer_flags;         // [nranks] flag words of every rank (barrier only)
-    unsigned* ticket;                    // local CTA counter (barrier only)
-    int64_t vec_off;                     // index of out[0] inside the factor vector (this shard's first segment)
-    int rank, nranks;
-    unsigned epoch;
-    int barrier;                         // 1: no values, publish the epoch in the peers' flag words
-};
-
 template <int LANES>
 __global__ void __launch_bounds__(256) k_finalize(int64_t nseg, const uint32_t* __restrict__ slot_ptr,
                                                   const float2* __restrict__ partials, const uint32_t* __restrict__ seg_ptr,
                                                   float lambda, int nmf, float* __restrict__ out, PushArgs push) {
     // grid-stride over segments (a push launch uses few, large CTAs so that few system-scope fences are needed)
-    for (int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; tid < nseg * LANES; tid += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t s = tid / LANES;
-        const int l = (int)(tid % LANES);
-        const uint32_t deg = seg_ptr[s + 1] - seg_ptr[s];
-        float g = 0.0f, h = 0.0f;
-        if (deg != 0u) {
-            const uint32_t hi = slot_ptr[s + 1];
-            for (uint32_t q = slot_ptr[s] + l; q < hi; q += LANES) {
-                const float2 pr = partials[q];
-                g += pr.x;
-                h += pr.y;
-            }
-        }
-        if (LANES > 1) {
-#pragma unroll
-            for (int o = 1; o < LANES; o <<= 1) {
-                g += __shfl_xor_sync(0xffffffffu, g, o);
-                h += __shfl_xor_sync(0xffffffffu, h, o);
-            }
-        }
-        if (l == 0) {
-            float r = 0.0f;
-            if (deg != 0u) {
-                r = g / (lambda * deg + h);
-                if (nmf) r = fmaxf(r, 0.0f);
-            }
-            out[s] = r;
-            if (push.peer_ll != nullptr) {
-                const unsigned long long word = ((unsigned long long)push.epoch << 32) | (unsigned long long)__float_as_uint(r);
-                for (int p = 0; p < push.nranks; ++p)
-                    if (p != push.rank) {
-                        unsigned long long* dst = push.peer_ll[p] + push.vec_off + s;
-                        asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(dst), "l"(word) : "memory");
-                    }
-            }
-        }
-    }
+    finalize_segments<LANES>(nseg, slot_ptr, partials, seg_ptr, lambda, nmf, out, push.peer_ll, push.vec_off, push.rank,
+                             push.nranks, push.epoch);
     if (push.barrier) {
         // rare (once per outer iteration): everything this rank did before is visible, then publish the epoch
         __threadfence_system();
@@ -874,6 +906,7 @@ int panel_sweep(int mode, const PanelSweepArgs& a_in, int ncta, int threads, int
         if (ns > 64) ns = 64;
         if (ns >= 40) {  // fewer slots could deadlock the producers against their own un-signalled batches
             a.nslots = (uint32_t)ns;
+            a.fin.enabled = 0;
             const size_t smem = vec_al + ns * per_slot;
 #define MF_DISPATCH(LAUNCH)                                                                                         \
     switch (mode) {                                                                                                 \
@@ -905,6 +938,8 @@ int panel_sweep(int mode, const PanelSweepArgs& a_in, int ncta, int threads, int
         default: set_error("panel sweep: unsupported mode %d", mode); return MF_ERR_ARG;
     }
 }
+
+int panel_finalize_lanes(int64_t nseg, int64_t nslots) { return nslots > 4 * nseg ? 32 : 1; }
 
 int panel_finalize(int64_t nseg, int64_t nslots, const uint32_t* slot_ptr, const float2* partials, const uint32_t* seg_ptr,
                    float lambda, int nmf, float* out, const FinalizePush* fp, cudaStream_t st) {

@@ -12,6 +12,27 @@ enum : int {
     kAddSep = 8,  // the add-back gathers a vector other than g_new (CSR side of the fused schedule)
 };
 
+// In-kernel finalize of a solving sweep (register-ring pipeline): after its items every CTA arrives at a grid-wide
+// barrier (all CTAs are co-resident: one persistent CTA per SM), then the CTAs share the segments: add the slots in
+// order, out = g / (lambda*deg + h), and — multi-GPU — store the block into the peers' LL receive buffers.  Same
+// reduction trees as the stand-alone finalize kernel, so both give identical bits.
+struct SweepFinalize {
+    int enabled;                         // 0: partial sums only (a separate panel_finalize launch follows)
+    int lanes;                           // 1: a thread per segment, 32: a warp per segment
+    int64_t nseg;
+    const uint32_t* slot_ptr;
+    const uint32_t* seg_ptr;
+    float lambda;
+    int nmf;
+    float* out;                          // this shard's block of the factor vector
+    unsigned* bar;                       // grid barrier counter (monotonic)
+    unsigned bar_target;                 // value of *bar once every CTA of this launch has arrived
+    unsigned long long* const* peer_ll;  // multi-GPU push (nullptr: none), as FinalizePush
+    int64_t vec_off;
+    int rank, nranks;
+    unsigned epoch;
+};
+
 struct PanelSweepArgs {
     const uint16_t* idx16;
     float* val;
@@ -29,6 +50,7 @@ struct PanelSweepArgs {
     const float* s_old;   // per-segment factor of the rank being subtracted
     float2* partials;
     uint32_t nslots;      // TMA pipeline: shared-memory slots of the ring (set by panel_sweep)
+    SweepFinalize fin;    // register-ring pipeline only
 };
 
 struct DirectSweepArgs {
@@ -62,6 +84,7 @@ struct FinalizePush {
     unsigned epoch;
     int barrier;                         // 1 = send no values, publish the epoch (exchange_wait on the other side)
 };
+int panel_finalize_lanes(int64_t nseg, int64_t nslots);  // 32: many slots per segment -> a warp per segment, else 1
 int panel_finalize(int64_t nseg, int64_t nslots, const uint32_t* slot_ptr, const float2* partials, const uint32_t* seg_ptr,
                    float lambda, int nmf, float* out, const FinalizePush* push, cudaStream_t st);
 int exchange_wait(const unsigned* flags, int rank, int nranks, unsigned epoch, cudaStream_t st);

@@ -150,26 +150,43 @@ int run_sweep(mf_session* s, Side& sd, int mode, const SweepVectors& v, float* o
         a.seg_offset = sd.seg_offset;
         a.g_new = v.g_new; a.g_add = v.g_add; a.g_old = v.g_old; a.s_add = v.s_add; a.s_old = v.s_old;
         a.partials = sd.partials;
+        a.nslots = 0;
+        a.fin.enabled = 0;
+        const bool solve = (mode & kSolve) != 0;
+        const bool is_h = push && out >= s->H && out < s->H + (int64_t)s->k * s->ldn;
+        FinalizePush fp;
+        if (solve && push) {  // fused solve -> exchange: the finalize sends the block to every peer (LL words over NVLink)
+            fp.peer_ll = dist_peer_ll(s->dist, is_h);
+            fp.peer_flags = dist_peer_flags(s->dist);
+            fp.ticket = dist_flags(s->dist) + s->nranks;
+            fp.vec_off = sd.seg_offset;
+            fp.rank = s->rank; fp.nranks = s->nranks; fp.epoch = dist_next_epoch(s->dist); fp.barrier = 0;
+        }
+        // finalize inside the sweep kernel (grid barrier, register-ring pipeline) unless switched off
+        const bool in_kernel = solve && sd.nitems > 0 && s->fin_in_kernel && s->prm.pipeline == MF_PIPELINE_REGISTERS;
+        if (in_kernel) {
+            SweepFinalize& f = a.fin;
+            f.enabled = 1;
+            f.lanes = panel_finalize_lanes(sd.nseg, sd.nslots);
+            f.nseg = sd.nseg; f.slot_ptr = sd.slot_ptr; f.seg_ptr = sd.ptr;
+            f.lambda = s->prm.lambda; f.nmf = nmf; f.out = out + sd.seg_offset;
+            s->gridbar_total += (unsigned)sd.ncta;
+            f.bar = s->d_gridbar; f.bar_target = s->gridbar_total;
+            f.peer_ll = push ? fp.peer_ll : nullptr;
+            f.vec_off = sd.seg_offset; f.rank = s->rank; f.nranks = s->nranks; f.epoch = push ? fp.epoch : 0u;
+        }
         if (sd.nitems > 0) {
             s->timer.start(family_of(mode));
-            a.nslots = 0;
             MF_TRY(panel_sweep(mode, a, sd.ncta, kThreads, sd.chunk, s->prm.pipeline, s->st));
             s->timer.stop();
         }
-        if (mode & kSolve) {
-            FinalizePush fp;
-            const bool is_h = push && out >= s->H && out < s->H + (int64_t)s->k * s->ldn;
-            if (push) {  // fused solve -> exchange: the finalize kernel sends the block to every peer (LL words over NVLink)
-                fp.peer_ll = dist_peer_ll(s->dist, is_h);
-                fp.peer_flags = dist_peer_flags(s->dist);
-                fp.ticket = dist_flags(s->dist) + s->nranks;
-                fp.vec_off = sd.seg_offset;
-                fp.rank = s->rank; fp.nranks = s->nranks; fp.epoch = dist_next_epoch(s->dist); fp.barrier = 0;
+        if (solve) {
+            if (!in_kernel) {
+                s->timer.start(F_FINALIZE);
+                MF_TRY(panel_finalize(sd.nseg, sd.nslots, sd.slot_ptr, sd.partials, sd.ptr, s->prm.lambda, nmf, out + sd.seg_offset,
+                                      push ? &fp : nullptr, s->st));
+                s->timer.stop();
             }
-            s->timer.start(F_FINALIZE);
-            MF_TRY(panel_finalize(sd.nseg, sd.nslots, sd.slot_ptr, sd.partials, sd.ptr, s->prm.lambda, nmf, out + sd.seg_offset,
-                                  push ? &fp : nullptr, s->st));
-            s->timer.stop();
             if (push) {
                 s->timer.start(F_COLLECTIVE);
                 MF_TRY(exchange_unpack(dist_ll(s->dist, is_h), out, is_h ? s->cols : s->rows, sd.seg_offset, sd.seg_offset + sd.nseg,
@@ -440,6 +457,9 @@ int create_impl(const mf_ratings* R, const mf_testset* T, const mf_params* param
         cudaMemcpyAsync(s->tval, T->val, sizeof(float) * (size_t)s->nt, cudaMemcpyDefault, s->st);
     }
     if ((rc = dev_alloc(&s->d_acc, rmse_scratch_doubles(s->sm_count))) != MF_OK) return fail(rc);
+    if ((rc = dev_alloc(&s->d_gridbar, 1)) != MF_OK) return fail(rc);
+    cudaMemsetAsync(s->d_gridbar, 0, sizeof(unsigned), s->st);
+    s->fin_in_kernel = getenv("MF_SEPARATE_FINALIZE") == nullptr;
     if (nranks > 1) {
         if (!nccl_id) { set_error("multi-GPU session needs the shared ncclUniqueId"); return fail(MF_ERR_ARG); }
         if ((rc = dist_create(&s->dist, rank, nranks, nccl_id, s->device)) != MF_OK) return fail(rc);
@@ -524,7 +544,7 @@ int mf_session_destroy(mf_session* s) {
     if (s->dist) dist_destroy(s->dist);
     side_free(s->csc);
     side_free(s->csr);
-    void* ptrs[] = {s->W, s->H, s->v_old, s->trow, s->tcol, s->tval, s->d_acc};
+    void* ptrs[] = {s->W, s->H, s->v_old, s->trow, s->tcol, s->tval, s->d_acc, s->d_gridbar};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     s->timer.destroy();
@@ -789,11 +809,13 @@ static int train_impl(const mf_ratings* R, const mf_testset* T, float* W, float*
     mf_session* s = nullptr;
     MF_TRY(mf_session_create(R, T, &p, &s));
     int rc = mf_session_set_factors(s, W, solver == MF_SOLVER_CCD ? nullptr : H);
+    trace_mark("train: set_factors");
     double rank_acc = 0.0, upd_acc = 0.0;
     for (int it = 0; rc == MF_OK && it < p.maxiter; ++it) {
         mf_iter_stats st;
         rc = solver == MF_SOLVER_CCD ? mf_session_ccdpp_iterate(s, 1, &st) : mf_session_als_iterate(s, 1, &st);
         if (rc != MF_OK) break;
+        trace_mark("train: one iteration + rmse");
         rank_acc += st.rank_time;
         upd_acc += st.update_time;
         if (stats) stats[it] = st;
@@ -807,7 +829,9 @@ static int train_impl(const mf_ratings* R, const mf_testset* T, float* W, float*
         }
     }
     if (rc == MF_OK) rc = mf_session_get_factors(s, W, H);
+    trace_mark("train: get_factors");
     mf_session_destroy(s);
+    trace_mark("train: destroy");
     return rc;
 }
 

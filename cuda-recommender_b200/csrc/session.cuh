@@ -50,6 +50,9 @@ struct mf_session {
     uint32_t *trow = nullptr, *tcol = nullptr;
     float* tval = nullptr;
     double* d_acc = nullptr;
+    unsigned* d_gridbar = nullptr;  // grid barrier counter of the in-kernel finalize (monotonic; gridbar_total = expected value)
+    unsigned gridbar_total = 0;
+    bool fin_in_kernel = true;
     int outer_done = 0;
     int pending = -1;  // rank whose subtraction from the residual is still deferred (fused schedule)
     mf::FamilyTimer timer;
