@@ -31,6 +31,20 @@ namespace {
 
 constexpr int kBatch = 32;  // factor rows staged per step
 constexpr int kStages = 3;  // staging buffers
+// register caps of the kernel classes (A/B knobs: scripts/build_variant.sh)
+#ifndef MF_ALS_REG4
+#define MF_ALS_REG4 64
+#endif
+#ifndef MF_ALS_REG8
+#define MF_ALS_REG8 112
+#endif
+#ifndef MF_ALS_UNROLL8
+#define MF_ALS_UNROLL8 2
+#endif
+#ifndef MF_ALS_UNROLL4
+#define MF_ALS_UNROLL4 4
+#endif
+constexpr int kUnroll8 = MF_ALS_UNROLL8, kUnroll4 = MF_ALS_UNROLL4;  // rows of the Gram loop per unrolled iteration
 
 // segment order: longest-first by degree bin (bit length of the degree), via per-bin cursors
 __global__ void k_order_by_bin(int64_t nseg, const uint32_t* __restrict__ ptr, unsigned* __restrict__ cursor /*[33]*/,
@@ -200,7 +214,7 @@ k_als_tile(int64_t nseg, const uint32_t* __restrict__ order, unsigned* __restric
             if (has3) sidx[buf * kBatch + tid] = nid;             // the ids of batch b were consumed two iterations ago
             const float* Yb = Ys + buf * kBatch * kp;
             if (active) {
-#pragma unroll(TS == 8 ? 2 : 4)
+#pragma unroll(TS == 8 ? kUnroll8 : kUnroll4)
                 for (int r = g; r < nrow; r += ks) {
                     float a[TS], c[TS];
                     load_tile_vec<TS>(Yb + r * kp, I, nb, a);
@@ -396,9 +410,9 @@ int launch_als_vw(const AlsGeometry& G, int64_t nseg, const uint32_t* order, uns
                   float* X, int k, float lambda, int sm_count, cudaStream_t st) {
     // register classes: 64 (4 x 4 tiles: any number of 32/64-thread CTAs), 112 (8 x 8 tiles: 3 x 192 or 6 x 96 threads per
     // SM), 168 (8 x 8 tiles, up to 384 threads)
-    if constexpr (TS == 4) return launch_als<TS, VW, 64>(G, nseg, order, queue, s, Y, X, k, lambda, sm_count, st);
+    if constexpr (TS == 4) return launch_als<TS, VW, MF_ALS_REG4>(G, nseg, order, queue, s, Y, X, k, lambda, sm_count, st);
     else {
-        if (G.tps <= 192) return launch_als<TS, VW, 112>(G, nseg, order, queue, s, Y, X, k, lambda, sm_count, st);
+        if (G.tps <= 192) return launch_als<TS, VW, MF_ALS_REG8>(G, nseg, order, queue, s, Y, X, k, lambda, sm_count, st);
         return launch_als<TS, VW, 168>(G, nseg, order, queue, s, Y, X, k, lambda, sm_count, st);
     }
 }

@@ -24,8 +24,9 @@ def torch_cuda():
 
 
 def _bit_checksums(torch, val_np):
+    """Order-independent integer checksums of the float bit patterns (exact: no floating-point reduction involved)."""
     v = torch.from_numpy(val_np).cuda().view(torch.int32).to(torch.int64)
-    return int(v.sum().item()), int((v * v % 1000003).sum().item()), float(torch.from_numpy(val_np).cuda().double().abs().sum().item())
+    return int(v.sum().item()), int((v * v % 1000003).sum().item()), int(((v >> 9) * 2654435761 % 998244353).sum().item())
 
 
 def test_netflix_shape_ccdpp_properties(gpu, datagen, torch_cuda):
