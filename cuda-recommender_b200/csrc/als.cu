@@ -22,6 +22,8 @@
 //   * an empty segment writes zeros (src/ALS.cpp:151-157).
 // Shared-memory layout of a staged row / of a column of L: 4-float chunks; with TS = 8 the two chunks of tile t
 // sit at chunk positions t and nb + t, so that consecutive tiles read consecutive 16-byte words (no bank conflicts).
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "session.cuh"
@@ -125,7 +127,6 @@ k_als_tile(int64_t nseg, const uint32_t* __restrict__ order, unsigned* __restric
     float* dv = Ld + TS * TS;                     // [kp]                   1 / L[i][i]  (0 for i >= k)
     float* xs = dv + kp;                          // [kp]                   solution at positions pos(i)
     uint32_t* sidx = reinterpret_cast<uint32_t*>(xs + kp);  // [kStages][kBatch] row ids of the batches to be fetched
-    __shared__ unsigned s_next;
 
     const int tid = threadIdx.x;
     const int TPS = blockDim.x;
@@ -145,17 +146,33 @@ k_als_tile(int64_t nseg, const uint32_t* __restrict__ order, unsigned* __restric
     const int cl = tid & ((1 << tl) - 1);         // this thread's first copy inside a row
     const int r0 = tid >> tl, rstep = TPS >> tl;  // its first row, rows per pass
 
-    for (;;) {
-        __syncthreads();
-        if (tid == 0) s_next = atomicAdd(queue, 1u);
-        __syncthreads();
-        const unsigned qi = s_next;
-        if (qi >= nseg) break;
-        const int64_t s = order[qi];
-        const uint32_t lo = ptr[s], hi = ptr[s + 1];
-        float* x = X + s * k;
+    // The queue runs one segment ahead: while a segment is processed, thread 0 already holds the ticket, the segment
+    // id and the extent of the next one (loads in flight), and leaves them in s_desc[parity] at the end.
+    __shared__ uint32_t s_desc[2][3];  // {segment or 0xffffffff, lo, hi}
+    uint32_t nx_seg = 0xffffffffu, nx_lo = 0, nx_hi = 0;
+    auto fetch_next = [&]() {
+        const unsigned t = atomicAdd(queue, 1u);
+        nx_seg = 0xffffffffu; nx_lo = 0; nx_hi = 0;
+        if (t < nseg) {
+            nx_seg = __ldg(order + t);
+            nx_lo = __ldg(ptr + nx_seg);
+            nx_hi = __ldg(ptr + nx_seg + 1);
+        }
+    };
+    if (tid == 0) {
+        fetch_next();
+        s_desc[0][0] = nx_seg; s_desc[0][1] = nx_lo; s_desc[0][2] = nx_hi;
+    }
+    for (int par = 0;; par ^= 1) {
+        __syncthreads();  // the previous segment is finished; s_desc[par] is in place
+        const uint32_t seg = s_desc[par][0];
+        if (seg == 0xffffffffu) break;
+        const uint32_t lo = s_desc[par][1], hi = s_desc[par][2];
+        if (tid == 0) fetch_next();
+        float* x = X + (int64_t)seg * k;
         if (hi == lo) {
             for (int c = tid; c < k; c += TPS) x[c] = 0.0f;
+            if (tid == 0) { s_desc[par ^ 1][0] = nx_seg; s_desc[par ^ 1][1] = nx_lo; s_desc[par ^ 1][2] = nx_hi; }
             continue;
         }
         float acc[TS][TS];
@@ -211,7 +228,6 @@ k_als_tile(int64_t nseg, const uint32_t* __restrict__ order, unsigned* __restric
             __syncthreads();                                      // ... for everybody; everybody is done with batch b-1
             const int buf2 = buf >= 1 ? buf - 1 : kStages - 1;    // (b + 2) % kStages: the buffer batch b-1 left
             if (b + 2 < nbatch) issue_rows(b + 2, buf2); else asm volatile("cp.async.commit_group;" ::: "memory");
-            if (has3) sidx[buf * kBatch + tid] = nid;             // the ids of batch b were consumed two iterations ago
             const float* Yb = Ys + buf * kBatch * kp;
             if (active) {
 #pragma unroll(TS == 8 ? kUnroll8 : kUnroll4)
@@ -222,6 +238,9 @@ k_als_tile(int64_t nseg, const uint32_t* __restrict__ order, unsigned* __restric
                     rank1<TS, false>(acc, a, c);
                 }
             }
+            // ids of batch b+3 (loaded before the barrier, used only now: their latency hides behind the Gram loop); the
+            // ids of batch b that sat here were consumed two iterations ago
+            if (has3) sidx[buf * kBatch + tid] = nid;
             buf = buf + 1 == kStages ? 0 : buf + 1;
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -359,6 +378,7 @@ k_als_tile(int64_t nseg, const uint32_t* __restrict__ order, unsigned* __restric
             }
             for (int c = tid; c < k; c += 32) x[c] = xs[pos_of<TS>(c, nb)];
         }
+        if (tid == 0) { s_desc[par ^ 1][0] = nx_seg; s_desc[par ^ 1][1] = nx_lo; s_desc[par ^ 1][2] = nx_hi; }
     }
 }
 
@@ -375,6 +395,10 @@ AlsGeometry als_geometry(int k) {
     G.ntiles = G.nb * (G.nb + 1) / 2;
     const int target = G.TS == 4 ? (G.ntiles <= 10 ? 32 : 64) : (G.ntiles <= 36 ? 96 : 192);
     G.ks = std::max(1, std::min(8, target / G.ntiles));
+    if (const char* e = getenv("MF_ALS_KS")) {  // tuning knob: split-K groups per CTA
+        const int v = atoi(e);
+        if (v >= 1 && v <= 8 && G.ntiles * v <= (G.TS == 8 ? 384 : 64)) G.ks = v;
+    }
     G.tps = (G.ntiles * G.ks + 31) / 32 * 32;
     const int vw = k % 4 == 0 ? 4 : (k % 2 == 0 ? 2 : 1);
     G.tl = 0;
@@ -394,6 +418,11 @@ int launch_als(const AlsGeometry& G, int64_t nseg, const uint32_t* order, unsign
         MF_CUDA(cudaFuncSetAttribute(k_als_tile<TS, VW, MAXREG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.smem));
         attr = G.smem;
     }
+    static bool carveout = false;
+    if (!carveout) {  // all of the SM's configurable memory as shared memory: the CTA count per SM is what hides the serial phases
+        MF_CUDA(cudaFuncSetAttribute(k_als_tile<TS, VW, MAXREG>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        carveout = true;
+    }
     int per_sm = 1;
     MF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_als_tile<TS, VW, MAXREG>, G.tps, G.smem));
     if (per_sm < 1) per_sm = 1;
@@ -410,9 +439,12 @@ int launch_als_vw(const AlsGeometry& G, int64_t nseg, const uint32_t* order, uns
                   float* X, int k, float lambda, int sm_count, cudaStream_t st) {
     // register classes: 64 (4 x 4 tiles: any number of 32/64-thread CTAs), 112 (8 x 8 tiles: 3 x 192 or 6 x 96 threads per
     // SM), 168 (8 x 8 tiles, up to 384 threads)
+    const char* fr = getenv("MF_ALS_REGS");  // tuning knob: 112 or 168
+    const int force_regs = fr ? atoi(fr) : 0;
     if constexpr (TS == 4) return launch_als<TS, VW, MF_ALS_REG4>(G, nseg, order, queue, s, Y, X, k, lambda, sm_count, st);
     else {
-        if (G.tps <= 192) return launch_als<TS, VW, MF_ALS_REG8>(G, nseg, order, queue, s, Y, X, k, lambda, sm_count, st);
+        const bool small = force_regs ? force_regs < 168 : G.tps <= 192;
+        if (small && G.tps <= 192) return launch_als<TS, VW, MF_ALS_REG8>(G, nseg, order, queue, s, Y, X, k, lambda, sm_count, st);
         return launch_als<TS, VW, 168>(G, nseg, order, queue, s, Y, X, k, lambda, sm_count, st);
     }
 }

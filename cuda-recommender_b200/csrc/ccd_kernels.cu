@@ -88,63 +88,53 @@ __device__ __forceinline__ void calc4(Step& e, const float* __restrict__ sm_new,
 }
 
 // Streams the (up to four) items of a batch through the 8-lane groups of a warp: a lane owns 4 consecutive
-// entries of its group's 32-entry step.  Four steps are in flight per lane (register ring e0..e3, slot j holds the
-// steps j, j+4, ... of the item).  The ring does not drain between batches: as soon as a lane has consumed its last
-// step of the current item in slot j, it loads step j of the NEXT batch's item into that slot (slots the current item
-// never uses are filled right away), so the next batch starts with its first four steps already in flight.
-// Invariant on entry: slot j holds step j of the current item (for the lanes that have one).
-// While every group still has 128 entries ahead (o + 128 <= minlen) the steps are consumed without per-lane checks.
+// entries of its group's 32-entry step.  Four steps are in flight per group (register ring e0..e3): the load
+// of step s+4 is issued right after step s is consumed.  While every group still has 128 entries ahead
+// (o + 128 <= minlen) the steps are consumed without per-lane checks; the ragged end runs predicated.
 template <int MODE>
-__device__ __forceinline__ void stream_batch(const PanelSweepArgs& a, Step& e0, Step& e1, Step& e2, Step& e3, uint32_t pos,
-                                             uint32_t len, uint32_t npos, uint32_t nlen, uint32_t minlen, uint32_t maxlen,
-                                             uint32_t lane_off, const float* __restrict__ sm_new,
+__device__ __forceinline__ void stream_batch(const PanelSweepArgs& a, uint32_t pos, uint32_t len, uint32_t minlen,
+                                             uint32_t maxlen, uint32_t lane_off, const float* __restrict__ sm_new,
                                              const float* __restrict__ sm_add, const float* __restrict__ sm_old, float s_add,
                                              float s_old, float& g, float& h) {
     constexpr bool WRITE = (MODE & kSub) || (MODE & kAdd);
-#define MF_NEXT(e, j) if (32u * (j) + lane_off < nlen) e = load_step(a.idx16, a.val, npos + 32u * (j))
-#define MF_REFILL(e, o2, j)                                                                 \
-    {                                                                                       \
-        if ((o2) + lane_off < len) e = load_step(a.idx16, a.val, pos + (o2));               \
-        else MF_NEXT(e, j);                                                                 \
-    }
+    Step e0, e1, e2, e3;
+#define MF_LOAD(e, o) if ((o) + lane_off < len) e = load_step(a.idx16, a.val, pos + (o))
 #define MF_USE_ALL(e, o)                                                                    \
     {                                                                                       \
         calc4<MODE>(e, sm_new, sm_add, sm_old, s_add, s_old, g, h);                         \
         if (WRITE) __stcs(reinterpret_cast<float4*>(a.val + pos + (o)), e.v);               \
     }
-#define MF_STEP(e, o, j)                                                                    \
-    if ((o) + lane_off < len) {                                                             \
-        MF_USE_ALL(e, o);                                                                   \
-        MF_REFILL(e, (o) + 128u, j);                                                        \
-    }
-    // slots this lane's item never uses take the next item's steps right away
-    if (!(lane_off < len)) MF_NEXT(e0, 0u);
-    if (!(32u + lane_off < len)) MF_NEXT(e1, 1u);
-    if (!(64u + lane_off < len)) MF_NEXT(e2, 2u);
-    if (!(96u + lane_off < len)) MF_NEXT(e3, 3u);
+#define MF_USE(e, o) if ((o) + lane_off < len) MF_USE_ALL(e, o)
+    MF_LOAD(e0, 0u);
+    MF_LOAD(e1, 32u);
+    MF_LOAD(e2, 64u);
+    MF_LOAD(e3, 96u);
     uint32_t o = 0;
 #pragma unroll 1
     for (; o + 128u <= minlen; o += 128u) {
         MF_USE_ALL(e0, o);
-        MF_REFILL(e0, o + 128u, 0u);
+        MF_LOAD(e0, o + 128u);
         MF_USE_ALL(e1, o + 32u);
-        MF_REFILL(e1, o + 160u, 1u);
+        MF_LOAD(e1, o + 160u);
         MF_USE_ALL(e2, o + 64u);
-        MF_REFILL(e2, o + 192u, 2u);
+        MF_LOAD(e2, o + 192u);
         MF_USE_ALL(e3, o + 96u);
-        MF_REFILL(e3, o + 224u, 3u);
+        MF_LOAD(e3, o + 224u);
     }
 #pragma unroll 1
     for (; o < maxlen; o += 128u) {
-        MF_STEP(e0, o, 0u);
-        MF_STEP(e1, o + 32u, 1u);
-        MF_STEP(e2, o + 64u, 2u);
-        MF_STEP(e3, o + 96u, 3u);
+        MF_USE(e0, o);
+        MF_LOAD(e0, o + 128u);
+        MF_USE(e1, o + 32u);
+        MF_LOAD(e1, o + 160u);
+        MF_USE(e2, o + 64u);
+        MF_LOAD(e2, o + 192u);
+        MF_USE(e3, o + 96u);
+        MF_LOAD(e3, o + 224u);
     }
-#undef MF_NEXT
-#undef MF_REFILL
+#undef MF_LOAD
+#undef MF_USE
 #undef MF_USE_ALL
-#undef MF_STEP
 }
 
 // Adds a segment's slots, applies the regulariser, divides: out = g / (lambda*deg + h), with lambda*deg a
@@ -217,6 +207,24 @@ __device__ __forceinline__ void finalize_segments(int64_t nseg, const uint32_t* 
     }
 }
 
+// receiving side of the LL exchange: grid-stride over the factor entries owned by peers; polls the entry's receive
+// word until its epoch half matches, then stores the value half into the factor vector
+__device__ __forceinline__ void ll_unpack_entries(const unsigned long long* ll, float* __restrict__ vec, int64_t dim, int64_t own_lo,
+                                                  int64_t own_hi, unsigned epoch) {
+    const int64_t nother = dim - (own_hi - own_lo);
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < nother; j += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = j < own_lo ? j : j + (own_hi - own_lo);
+        unsigned long long w;
+        unsigned spins = 0;
+        for (;;) {
+            asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(w) : "l"(ll + i) : "memory");
+            if ((unsigned)(w >> 32) == epoch) break;
+            if (++spins > (1u << 27)) __trap();
+        }
+        vec[i] = __uint_as_float((unsigned)(w & 0xffffffffull));
+    }
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(1024, 1) k_panel_sweep(PanelSweepArgs a) {
     constexpr bool SUB = MODE & kSub, ADD = MODE & kAdd, SOLVE = MODE & kSolve, ADDSEP = MODE & kAddSep;
@@ -270,13 +278,6 @@ __global__ void __launch_bounds__(1024, 1) k_panel_sweep(PanelSweepArgs a) {
             i0 = __shfl_sync(kFull, i0, 0);
             uint4 d = make_uint4(0u, 0u, 0u, 0u);  // {start, len, seg, slot}; len 0 = no item
             if (i0 + grp < pe) d = __ldg(items + i0 + grp);
-            const uint32_t lane_off = 4u * (uint32_t)sl;     // this lane's 4 entries inside a 32-entry step
-            // register ring: first four steps of the first batch (later batches arrive pre-loaded by their predecessor)
-            Step e0, e1, e2, e3;
-            if (lane_off < d.y) e0 = load_step(a.idx16, a.val, d.x + lane_off);
-            if (32u + lane_off < d.y) e1 = load_step(a.idx16, a.val, d.x + lane_off + 32u);
-            if (64u + lane_off < d.y) e2 = load_step(a.idx16, a.val, d.x + lane_off + 64u);
-            if (96u + lane_off < d.y) e3 = load_step(a.idx16, a.val, d.x + lane_off + 96u);
             while (i0 < pe) {
                 uint32_t i0n = 0;
                 if (lane == 0) i0n = atomicAdd(&s_ctr, 4u);
@@ -285,6 +286,7 @@ __global__ void __launch_bounds__(1024, 1) k_panel_sweep(PanelSweepArgs a) {
                 if (i0n + grp < pe) dn = __ldg(items + i0n + grp);
 
                 const uint32_t len = d.y;
+                const uint32_t lane_off = 4u * (uint32_t)sl;     // this lane's 4 entries inside a 32-entry step
                 float s_add = 0.0f, s_old = 0.0f;
                 if (len != 0u) {
                     if (ADD) s_add = __ldg(a.s_add + a.seg_offset + d.z);
@@ -293,8 +295,7 @@ __global__ void __launch_bounds__(1024, 1) k_panel_sweep(PanelSweepArgs a) {
                 const uint32_t maxlen = __reduce_max_sync(kFull, len);
                 const uint32_t minlen = __reduce_min_sync(kFull, len);
                 float g = 0.0f, h = 0.0f;
-                stream_batch<MODE>(a, e0, e1, e2, e3, d.x + lane_off, len, dn.x + lane_off, dn.y, minlen, maxlen, lane_off, sm_new,
-                                   sm_add, sm_old, s_add, s_old, g, h);
+                stream_batch<MODE>(a, d.x + lane_off, len, minlen, maxlen, lane_off, sm_new, sm_add, sm_old, s_add, s_old, g, h);
                 if (SOLVE) {
 #pragma unroll
                     for (int o = 1; o < 8; o <<= 1) {
@@ -330,6 +331,7 @@ __global__ void __launch_bounds__(1024, 1) k_panel_sweep(PanelSweepArgs a) {
         else
             finalize_segments<1>(a.fin.nseg, a.fin.slot_ptr, a.partials, a.fin.seg_ptr, a.fin.lambda, a.fin.nmf, a.fin.out,
                                  a.fin.peer_ll, a.fin.vec_off, a.fin.rank, a.fin.nranks, a.fin.epoch);
+        if (a.fin.ll != nullptr) ll_unpack_entries(a.fin.ll, a.fin.vec, a.fin.dim, a.fin.own_lo, a.fin.own_hi, a.fin.epoch);
     }
 }
 
@@ -763,22 +765,9 @@ __global__ void __launch_bounds__(256) k_finalize(int64_t nseg, const uint32_t* 
     }
 }
 
-// receiving side of the LL exchange: one thread per factor entry owned by a peer; polls the entry's receive word
-// until its epoch half matches, then stores the value half into the factor vector
 __global__ void __launch_bounds__(256) k_ll_unpack(const unsigned long long* ll, float* __restrict__ vec, int64_t dim,
                                                    int64_t own_lo, int64_t own_hi, unsigned epoch) {
-    const int64_t nother = dim - (own_hi - own_lo);
-    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < nother; j += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t i = j < own_lo ? j : j + (own_hi - own_lo);
-        unsigned long long w;
-        unsigned spins = 0;
-        for (;;) {
-            asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(w) : "l"(ll + i) : "memory");
-            if ((unsigned)(w >> 32) == epoch) break;
-            if (++spins > (1u << 27)) __trap();
-        }
-        vec[i] = __uint_as_float((unsigned)(w & 0xffffffffull));
-    }
+    ll_unpack_entries(ll, vec, dim, own_lo, own_hi, epoch);
 }
 
 // waits until every peer has published `epoch` (or later) in this rank's flag words

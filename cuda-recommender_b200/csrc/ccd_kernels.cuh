@@ -31,6 +31,11 @@ struct SweepFinalize {
     int64_t vec_off;
     int rank, nranks;
     unsigned epoch;
+    // multi-GPU receive side, in the same launch: after its own block is sent, the kernel polls this rank's LL receive
+    // buffer for the blocks of the peers and completes the factor vector (what exchange_unpack does as a launch)
+    const unsigned long long* ll;        // nullptr: none
+    float* vec;                          // the full-length factor vector
+    int64_t dim, own_lo, own_hi;
 };
 
 struct PanelSweepArgs {

@@ -174,6 +174,8 @@ int run_sweep(mf_session* s, Side& sd, int mode, const SweepVectors& v, float* o
             f.bar = s->d_gridbar; f.bar_target = s->gridbar_total;
             f.peer_ll = push ? fp.peer_ll : nullptr;
             f.vec_off = sd.seg_offset; f.rank = s->rank; f.nranks = s->nranks; f.epoch = push ? fp.epoch : 0u;
+            f.ll = push ? dist_ll(s->dist, is_h) : nullptr;  // receive the peers' blocks in the same launch
+            f.vec = out; f.dim = is_h ? s->cols : s->rows; f.own_lo = sd.seg_offset; f.own_hi = sd.seg_offset + sd.nseg;
         }
         if (sd.nitems > 0) {
             s->timer.start(family_of(mode));
@@ -187,7 +189,7 @@ int run_sweep(mf_session* s, Side& sd, int mode, const SweepVectors& v, float* o
                                       push ? &fp : nullptr, s->st));
                 s->timer.stop();
             }
-            if (push) {
+            if (push && !in_kernel) {
                 s->timer.start(F_COLLECTIVE);
                 MF_TRY(exchange_unpack(dist_ll(s->dist, is_h), out, is_h ? s->cols : s->rows, sd.seg_offset, sd.seg_offset + sd.nseg,
                                        fp.epoch, s->st));
