@@ -38,7 +38,7 @@ constexpr int kStages = 3;  // staging buffers
 #define MF_ALS_REG4 64
 #endif
 #ifndef MF_ALS_REG8
-#define MF_ALS_REG8 112
+#define MF_ALS_REG8 168
 #endif
 #ifndef MF_ALS_UNROLL8
 #define MF_ALS_UNROLL8 2
@@ -110,13 +110,13 @@ __device__ __forceinline__ void rank1(float (&acc)[TS][TS], const float (&a)[TS]
 // nb = tiles per matrix edge (nb * TS >= k + 1); ks = split-K groups; threads 0 .. ks*ntiles-1 work on the Gram matrix.
 // MAXREG: register cap (sets how many CTAs fit an SM: 112 -> 3 x 192 or 6 x 96 threads, 168 -> 384 threads, 64 -> 2048).
 // Staging: three buffers of kBatch rows, one barrier per batch — while batch b is accumulated, batch b+1 is landing and
-// batch b+2 is being issued into the buffer batch b-1 just left.  2^tl threads share the copies of one row.
+// batch b+2 is being issued into the buffer batch b-1 just left.
 // Shared memory is one region used in turn as staging buffers (Gram loop), split-K scratch and L (factorisation).
 template <int TS, int VW, int MAXREG>
 __global__ void __maxnreg__(MAXREG)
 k_als_tile(int64_t nseg, const uint32_t* __restrict__ order, unsigned* __restrict__ queue, const uint32_t* __restrict__ ptr,
            const uint32_t* __restrict__ idx, const float* __restrict__ val, const float* __restrict__ Y, float* __restrict__ X,
-           int k, int nb, int ks, int tl, int region_floats, float lambda) {
+           int k, int nb, int ks, int region_floats, float lambda) {
     extern __shared__ __align__(16) float sm[];
     const int kp = nb * TS;
     const int ntiles = nb * (nb + 1) / 2;
@@ -143,8 +143,10 @@ k_als_tile(int64_t nseg, const uint32_t* __restrict__ order, unsigned* __restric
     const bool owner = tid < ntiles;              // group 0 keeps the tile for the factorisation
     const int posk = pos_of<TS>(k, nb);           // where the rating sits in a staged row / y = L[k][.] in a column
     const int cpr = k / VW;                       // copies per factor row
-    const int cl = tid & ((1 << tl) - 1);         // this thread's first copy inside a row
-    const int r0 = tid >> tl, rstep = TPS >> tl;  // its first row, rows per pass
+    // staged rows are ldy floats apart: ldy = 4 mod 8, so that the 16-byte copies of 8 neighbouring lanes (one row per
+    // lane) fall into 8 different bank groups
+    const int ldy = kp + ((kp & 7) == 0 ? 4 : 0);
+    const int lane = tid & 31, wv = tid >> 5, nwarp = TPS >> 5;
 
     // The queue runs one segment ahead: while a segment is processed, thread 0 already holds the ticket, the segment
     // id and the extent of the next one (loads in flight), and leaves them in s_desc[parity] at the end.
@@ -184,23 +186,18 @@ k_als_tile(int64_t nseg, const uint32_t* __restrict__ order, unsigned* __restric
         const int nbatch = (int)((hi - lo + kBatch - 1) / kBatch);
         // the previous segment left its L in the staging region: the pad columns behind the rating have to be zero
         // again (the copies never touch them)
-        {
-            const int npad = kp - k - 1;
-            for (int e = tid; e < kStages * kBatch * npad; e += TPS) {
-                const int r = e / npad, c = k + 1 + (e - r * npad);
-                Ys[r * kp + pos_of<TS>(c, nb)] = 0.0f;
-            }
-        }
-        // asynchronous gather of batch `b` (factor rows + ratings) into buffer b % kStages, row ids from sidx
+        for (int r = tid; r < kStages * kBatch; r += TPS)
+            for (int c = k + 1; c < kp; ++c) Ys[r * ldy + pos_of<TS>(c, nb)] = 0.0f;
+        // asynchronous gather of batch `b` (factor rows + ratings) into buffer `buf`, row ids from sidx: lane = row, the
+        // warps share the 16-byte pieces of the row (no index arithmetic beyond one multiply per row)
         auto issue_rows = [&](int b, int buf) {
             const uint32_t base = lo + (uint32_t)b * kBatch;
             const int nrow = (int)min((uint32_t)kBatch, hi - base);
-            float* dst = Ys + buf * kBatch * kp;
-            const uint32_t* ids = sidx + buf * kBatch;
-            for (int r = r0; r < nrow; r += rstep) {
-                const float* src = Y + (size_t)ids[r] * k;
-                for (int c = cl; c < cpr; c += (1 << tl)) cp_async<VW * 4>(dst + r * kp + pos_of<TS>(c * VW, nb), src + c * VW);
-                if (cl == 0) cp_async<4>(dst + r * kp + posk, val + base + r);
+            if (lane < nrow) {
+                const float* src = Y + (size_t)sidx[buf * kBatch + lane] * k;
+                float* dst = Ys + (buf * kBatch + lane) * ldy;
+                for (int c = wv; c < cpr; c += nwarp) cp_async<VW * 4>(dst + pos_of<TS>(c * VW, nb), src + c * VW);
+                if (wv == nwarp - 1) cp_async<4>(dst + posk, val + base + lane);
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
         };
@@ -228,13 +225,13 @@ k_als_tile(int64_t nseg, const uint32_t* __restrict__ order, unsigned* __restric
             __syncthreads();                                      // ... for everybody; everybody is done with batch b-1
             const int buf2 = buf >= 1 ? buf - 1 : kStages - 1;    // (b + 2) % kStages: the buffer batch b-1 left
             if (b + 2 < nbatch) issue_rows(b + 2, buf2); else asm volatile("cp.async.commit_group;" ::: "memory");
-            const float* Yb = Ys + buf * kBatch * kp;
+            const float* Yb = Ys + buf * kBatch * ldy;
             if (active) {
 #pragma unroll(TS == 8 ? kUnroll8 : kUnroll4)
                 for (int r = g; r < nrow; r += ks) {
                     float a[TS], c[TS];
-                    load_tile_vec<TS>(Yb + r * kp, I, nb, a);
-                    load_tile_vec<TS>(Yb + r * kp, J, nb, c);
+                    load_tile_vec<TS>(Yb + r * ldy, I, nb, a);
+                    load_tile_vec<TS>(Yb + r * ldy, J, nb, c);
                     rank1<TS, false>(acc, a, c);
                 }
             }
@@ -383,7 +380,7 @@ k_als_tile(int64_t nseg, const uint32_t* __restrict__ order, unsigned* __restric
 }
 
 struct AlsGeometry {
-    int TS, nb, kp, ntiles, ks, tps, tl, region_floats;
+    int TS, nb, kp, ntiles, ks, tps, region_floats;
     size_t smem;
 };
 
@@ -393,17 +390,17 @@ AlsGeometry als_geometry(int k) {
     G.nb = (k + 1 + G.TS - 1) / G.TS;
     G.kp = G.nb * G.TS;
     G.ntiles = G.nb * (G.nb + 1) / 2;
-    const int target = G.TS == 4 ? (G.ntiles <= 10 ? 32 : 64) : (G.ntiles <= 36 ? 96 : 192);
-    G.ks = std::max(1, std::min(8, target / G.ntiles));
+    // split-K groups: small matrices need several groups to fill a CTA; from ~64 tiles on one group per CTA is best
+    // (measured: k = 100 -> ks = 1, k = 40 -> ks = 4, k = 10 -> ks = 8)
+    if (G.TS == 4) G.ks = std::max(1, std::min(8, 64 / G.ntiles));
+    else G.ks = G.ntiles >= 64 ? 1 : std::max(1, std::min(8, 96 / G.ntiles));
     if (const char* e = getenv("MF_ALS_KS")) {  // tuning knob: split-K groups per CTA
         const int v = atoi(e);
         if (v >= 1 && v <= 8 && G.ntiles * v <= (G.TS == 8 ? 384 : 64)) G.ks = v;
     }
     G.tps = (G.ntiles * G.ks + 31) / 32 * 32;
-    const int vw = k % 4 == 0 ? 4 : (k % 2 == 0 ? 2 : 1);
-    G.tl = 0;
-    while ((1 << G.tl) < k / vw && G.tl < 5) ++G.tl;
-    const size_t stage = (size_t)kStages * kBatch * G.kp, lmat = (size_t)G.kp * G.kp;
+    const int ldy = G.kp + (G.kp % 8 == 0 ? 4 : 0);
+    const size_t stage = (size_t)kStages * kBatch * ldy, lmat = (size_t)G.kp * G.kp;
     const size_t scratch = (size_t)(G.ks - 1) * G.TS * G.TS * G.ntiles;
     G.region_floats = (int)((std::max(std::max(stage, lmat), scratch) + 3) / 4 * 4);
     G.smem = sizeof(float) * ((size_t)G.region_floats + G.TS * G.TS + 2 * (size_t)G.kp) + sizeof(uint32_t) * kStages * kBatch;
@@ -429,7 +426,7 @@ int launch_als(const AlsGeometry& G, int64_t nseg, const uint32_t* order, unsign
     int64_t grid = (int64_t)sm_count * per_sm;
     if (grid > nseg) grid = nseg;
     k_als_tile<TS, VW, MAXREG><<<(unsigned)grid, G.tps, G.smem, st>>>(nseg, order, queue, s.ptr, s.idx, s.val, Y, X, k, G.nb,
-                                                                        G.ks, G.tl, G.region_floats, lambda);
+                                                                        G.ks, G.region_floats, lambda);
     MF_CUDA(cudaGetLastError());
     return MF_OK;
 }

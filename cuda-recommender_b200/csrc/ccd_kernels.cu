@@ -87,6 +87,40 @@ __device__ __forceinline__ void calc4(Step& e, const float* __restrict__ sm_new,
     if (SUB || ADD) e.v = make_float4(v[0], v[1], v[2], v[3]);
 }
 
+// One panel of a factor vector -> shared memory, zeros beyond `cnt` (the panel's last valid entry) up to `stride`.
+// 16-byte loads, four in flight per thread: a 64 KB panel costs a 1024-thread CTA one L2 round trip instead of 16
+// dependent ones (a scalar loop here was ~6 us per panel and vector: the fixed cost that kept the sweeps from scaling
+// across GPUs).  g + base is 32-byte aligned (panels are multiples of 8 entries, factor rows 128-byte aligned) and the
+// factor rows are padded to 32 entries, so the vector load that straddles `cnt` stays inside the allocation.
+__device__ __forceinline__ void stage_panel(float* __restrict__ sm, const float* __restrict__ g, int64_t base, uint32_t cnt,
+                                            uint32_t stride) {
+    const float4* __restrict__ src = reinterpret_cast<const float4*>(g + base);
+    float4* __restrict__ dst = reinterpret_cast<float4*>(sm);
+    const uint32_t n4 = stride >> 2;
+    for (uint32_t i = threadIdx.x; i < n4; i += 4u * blockDim.x) {
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const uint32_t j = i + (uint32_t)u * blockDim.x;
+            v[u] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            if (j < n4 && 4u * j < cnt) v[u] = src[j];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const uint32_t j = i + (uint32_t)u * blockDim.x;
+            if (j < n4) {
+                if (4u * j + 3u >= cnt) {  // the vector that straddles the end of the panel
+                    if (4u * j + 1u >= cnt) v[u].y = 0.0f;
+                    if (4u * j + 2u >= cnt) v[u].z = 0.0f;
+                    v[u].w = 0.0f;
+                    if (4u * j >= cnt) v[u].x = 0.0f;
+                }
+                dst[j] = v[u];
+            }
+        }
+    }
+}
+
 // Streams the (up to four) items of a batch through the 8-lane groups of a warp: a lane owns 4 consecutive
 // entries of its group's 32-entry step.  Four steps are in flight per group (register ring e0..e3): the load
 // of step s+4 is issued right after step s is consumed.  While every group still has 128 entries ahead
@@ -262,12 +296,9 @@ __global__ void __launch_bounds__(1024, 1) k_panel_sweep(PanelSweepArgs a) {
             __syncthreads();  // every warp is done with the previous panel and counter
             const int64_t base = (int64_t)p * PR;
             const uint32_t cnt = (uint32_t)((a.gdim - base) < (int64_t)PR ? (a.gdim - base) : (int64_t)PR);
-            for (uint32_t i = threadIdx.x; i < stride; i += blockDim.x) {
-                const bool in = i < cnt;
-                if (NEEDNEW) sm_new[i] = in ? a.g_new[base + i] : 0.0f;
-                if (ADD && ADDSEP) sm_add[i] = in ? g_add[base + i] : 0.0f;
-                if (SUB) sm_old[i] = in ? a.g_old[base + i] : 0.0f;
-            }
+            if (NEEDNEW) stage_panel(sm_new, a.g_new, base, cnt, stride);
+            if (ADD && ADDSEP) stage_panel(sm_add, g_add, base, cnt, stride);
+            if (SUB) stage_panel(sm_old, a.g_old, base, cnt, stride);
             if (threadIdx.x == 0) s_ctr = ib;
             __syncthreads();
 
@@ -516,12 +547,9 @@ __global__ void __launch_bounds__(1024, 1) k_panel_sweep_tma(PanelSweepArgs a) {
             __syncthreads();  // consumers are done with the previous panel's vectors and counter
             const int64_t base = (int64_t)p * PR;
             const uint32_t cnt = (uint32_t)((a.gdim - base) < (int64_t)PR ? (a.gdim - base) : (int64_t)PR);
-            for (uint32_t i = threadIdx.x; i < stride; i += blockDim.x) {
-                const bool in = i < cnt;
-                if (NEEDNEW) sm_new[i] = in ? a.g_new[base + i] : 0.0f;
-                if (ADD && ADDSEP) sm_add[i] = in ? g_add[base + i] : 0.0f;
-                if (SUB) sm_old[i] = in ? a.g_old[base + i] : 0.0f;
-            }
+            if (NEEDNEW) stage_panel(sm_new, a.g_new, base, cnt, stride);
+            if (ADD && ADDSEP) stage_panel(sm_add, g_add, base, cnt, stride);
+            if (SUB) stage_panel(sm_old, a.g_old, base, cnt, stride);
             if (threadIdx.x == 0) s_ctr = ib;
             __syncthreads();
 
@@ -650,12 +678,9 @@ __global__ void __launch_bounds__(1024, 1) k_panel_sweep_async(PanelSweepArgs a)
             __syncthreads();  // consumers are done with the previous panel's vectors and counter
             const int64_t base = (int64_t)p * PR;
             const uint32_t cnt = (uint32_t)((a.gdim - base) < (int64_t)PR ? (a.gdim - base) : (int64_t)PR);
-            for (uint32_t i = threadIdx.x; i < stride; i += blockDim.x) {
-                const bool in = i < cnt;
-                if (NEEDNEW) sm_new[i] = in ? a.g_new[base + i] : 0.0f;
-                if (ADD && ADDSEP) sm_add[i] = in ? g_add[base + i] : 0.0f;
-                if (SUB) sm_old[i] = in ? a.g_old[base + i] : 0.0f;
-            }
+            if (NEEDNEW) stage_panel(sm_new, a.g_new, base, cnt, stride);
+            if (ADD && ADDSEP) stage_panel(sm_add, g_add, base, cnt, stride);
+            if (SUB) stage_panel(sm_old, a.g_old, base, cnt, stride);
             if (threadIdx.x == 0) s_ctr = ib;
             __syncthreads();
 

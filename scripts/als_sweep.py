@@ -11,10 +11,10 @@ from __graft_entry__ import load_package  # noqa: E402
 pkg = load_package()
 import cuda_recommender_b200.datagen as dg  # noqa: E402
 
-WL = {"ml20m_k10": ("ml20m", 10, [(0, 0), (1, 0), (2, 0), (3, 0), (8, 0)]),
-      "netflix_k40": ("netflix", 40, [(0, 0), (1, 168), (1, 112), (2, 168), (2, 112), (3, 168), (4, 168), (4, 112)]),
-      "netflix_k100": ("netflix", 100, [(0, 0), (1, 168), (1, 112), (2, 168), (2, 112)]),
-      "netflix_k64": ("netflix", 64, [(0, 0), (1, 168), (1, 112), (2, 168), (2, 112)])}
+WL = {"ml20m_k10": ("ml20m", 10, [(0, 0), (4, 0), (5, 0)]),
+      "netflix_k40": ("netflix", 40, [(0, 0), (2, 0), (8, 0)]),
+      "netflix_k100": ("netflix", 100, [(0, 0), (2, 0)]),
+      "netflix_k64": ("netflix", 64, [(0, 0), (1, 0), (4, 0)])}
 for name in sys.argv[1:] or ["ml20m_k10", "netflix_k40", "netflix_k100"]:
     shape, k, configs = WL[name]
     data = dg.synth_named(shape, seed=1 + list(dg.SHAPES).index(shape), device="cuda")
