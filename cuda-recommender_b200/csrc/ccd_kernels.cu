@@ -87,6 +87,18 @@ __device__ __forceinline__ void calc4(Step& e, const float* __restrict__ sm_new,
     if (SUB || ADD) e.v = make_float4(v[0], v[1], v[2], v[3]);
 }
 
+// The panel holding item `ib` = the number of panels that end at or before it (panel_item_ptr is non-decreasing).
+// Counted by the whole CTA at once: a serial walk is one dependent L2 round trip per panel, i.e. the CTAs of the
+// last of 30 panels started ~12 us late.
+__device__ __forceinline__ int first_panel(const uint32_t* __restrict__ panel_item_ptr, int npanels, uint32_t ib) {
+    int p = 0;
+    for (int base = 0; base < npanels; base += (int)blockDim.x) {
+        const int j = base + (int)threadIdx.x;
+        p += __syncthreads_count(j < npanels && panel_item_ptr[j + 1] <= ib);
+    }
+    return p;
+}
+
 // One panel of a factor vector -> shared memory, zeros beyond `cnt` (the panel's last valid entry) up to `stride`.
 // 16-byte loads, four in flight per thread: a 64 KB panel costs a 1024-thread CTA one L2 round trip instead of 16
 // dependent ones (a scalar loop here was ~6 us per panel and vector: the fixed cost that kept the sweeps from scaling
@@ -195,47 +207,65 @@ struct PushArgs {
     int barrier;                         // 1: no values, publish the epoch in the peers' flag words
 };
 
-// grid-stride over segments; `partials` is read through L2 (written by other CTAs of the same launch when the
-// finalize runs inside the sweep kernel)
+// grid-stride over segments, four segments per thread and round with their metadata loads issued together (the
+// finalize is a chain of dependent L2 round trips: pointers -> slots -> result); `partials` is read through L2
+// (written by other CTAs of the same launch when the finalize runs inside the sweep kernel)
 template <int LANES>
 __device__ __forceinline__ void finalize_segments(int64_t nseg, const uint32_t* __restrict__ slot_ptr, const float2* partials,
                                                   const uint32_t* __restrict__ seg_ptr, float lambda, int nmf,
                                                   float* __restrict__ out, unsigned long long* const* peer_ll, int64_t vec_off,
                                                   int rank, int nranks, unsigned epoch) {
-    for (int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; tid < nseg * LANES; tid += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t s = tid / LANES;
-        const int l = (int)(tid % LANES);
-        const uint32_t deg = seg_ptr[s + 1] - seg_ptr[s];
-        float g = 0.0f, h = 0.0f;
-        if (deg != 0u) {
-            const uint32_t hi = slot_ptr[s + 1];
-            for (uint32_t q = slot_ptr[s] + l; q < hi; q += LANES) {
-                const float2 pr = __ldcg(partials + q);
-                g += pr.x;
-                h += pr.y;
-            }
-        }
-        if (LANES > 1) {
+    constexpr int U = 4;
+    const int64_t total = nseg * LANES, stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t0 < total; t0 += U * stride) {
+        uint32_t deg[U], lo[U], hi[U];
 #pragma unroll
-            for (int o = 1; o < LANES; o <<= 1) {
-                g += __shfl_xor_sync(0xffffffffu, g, o);
-                h += __shfl_xor_sync(0xffffffffu, h, o);
+        for (int u = 0; u < U; ++u) {
+            const int64_t tid = t0 + u * stride;
+            deg[u] = 0u; lo[u] = 0u; hi[u] = 0u;
+            if (tid < total) {
+                const int64_t s = tid / LANES;
+                deg[u] = seg_ptr[s + 1] - seg_ptr[s];
+                lo[u] = slot_ptr[s];
+                hi[u] = slot_ptr[s + 1];
             }
         }
-        if (l == 0) {
-            float r = 0.0f;
-            if (deg != 0u) {
-                r = g / (lambda * deg + h);
-                if (nmf) r = fmaxf(r, 0.0f);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t tid = t0 + u * stride;
+            if (tid >= total) break;  // warp-uniform for LANES = 32 (a warp shares its segment)
+            const int64_t s = tid / LANES;
+            const int l = (int)(tid % LANES);
+            float g = 0.0f, h = 0.0f;
+            if (deg[u] != 0u) {
+                for (uint32_t q = lo[u] + l; q < hi[u]; q += LANES) {
+                    const float2 pr = __ldcg(partials + q);
+                    g += pr.x;
+                    h += pr.y;
+                }
             }
-            out[s] = r;
-            if (peer_ll != nullptr) {
-                const unsigned long long word = ((unsigned long long)epoch << 32) | (unsigned long long)__float_as_uint(r);
-                for (int p = 0; p < nranks; ++p)
-                    if (p != rank) {
-                        unsigned long long* dst = peer_ll[p] + vec_off + s;
-                        asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(dst), "l"(word) : "memory");
-                    }
+            if (LANES > 1) {
+#pragma unroll
+                for (int o = 1; o < LANES; o <<= 1) {
+                    g += __shfl_xor_sync(0xffffffffu, g, o);
+                    h += __shfl_xor_sync(0xffffffffu, h, o);
+                }
+            }
+            if (l == 0) {
+                float r = 0.0f;
+                if (deg[u] != 0u) {
+                    r = g / (lambda * deg[u] + h);
+                    if (nmf) r = fmaxf(r, 0.0f);
+                }
+                out[s] = r;
+                if (peer_ll != nullptr) {
+                    const unsigned long long word = ((unsigned long long)epoch << 32) | (unsigned long long)__float_as_uint(r);
+                    for (int p = 0; p < nranks; ++p)
+                        if (p != rank) {
+                            unsigned long long* dst = peer_ll[p] + vec_off + s;
+                            asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(dst), "l"(word) : "memory");
+                        }
+                }
             }
         }
     }
@@ -286,8 +316,7 @@ __global__ void __launch_bounds__(1024, 1) k_panel_sweep(PanelSweepArgs a) {
 
     uint32_t ib = a.cta_item_ptr[blockIdx.x];
     const uint32_t ie = a.cta_item_ptr[blockIdx.x + 1];
-    int p = 0;
-    while (p < a.npanels && a.panel_item_ptr[p + 1] <= ib) ++p;
+    int p = first_panel(a.panel_item_ptr, a.npanels, ib);
 
     while (ib < ie && p < a.npanels) {
         const uint32_t pend = a.panel_item_ptr[p + 1];
@@ -537,8 +566,7 @@ __global__ void __launch_bounds__(1024, 1) k_panel_sweep_tma(PanelSweepArgs a) {
     const uint32_t ib0 = a.cta_item_ptr[blockIdx.x];
     uint32_t ib = ib0;
     const uint32_t ie = a.cta_item_ptr[blockIdx.x + 1];
-    int p = 0;
-    while (p < a.npanels && a.panel_item_ptr[p + 1] <= ib) ++p;
+    int p = first_panel(a.panel_item_ptr, a.npanels, ib);
 
     while (ib < ie && p < a.npanels) {
         const uint32_t pend = a.panel_item_ptr[p + 1];
@@ -668,8 +696,7 @@ __global__ void __launch_bounds__(1024, 1) k_panel_sweep_async(PanelSweepArgs a)
     const uint32_t ib0 = a.cta_item_ptr[blockIdx.x];
     uint32_t ib = ib0;
     const uint32_t ie = a.cta_item_ptr[blockIdx.x + 1];
-    int p = 0;
-    while (p < a.npanels && a.panel_item_ptr[p + 1] <= ib) ++p;
+    int p = first_panel(a.panel_item_ptr, a.npanels, ib);
 
     while (ib < ie && p < a.npanels) {
         const uint32_t pend = a.panel_item_ptr[p + 1];
