@@ -325,7 +325,12 @@ def run_b200_arm(args):
         per_step = {"solve": 2 * k * (T - 1), "fused": 2 * k, "update": 0, "finalize": 2 * k * T}
     else:
         per_step = {"solve": 2 * k * T, "fused": 0, "update": 4 * k, "finalize": 2 * k * T}
-    per_step["collective"] = 2 * k * T if world > 1 else 0
+    if kt["finalize_launches"] == 0:
+        # finalize (and, multi-GPU, the exchange) ran inside the sweep kernels; what is left is the once-per-iteration barrier
+        per_step["finalize"] = 0
+        per_step["collective"] = 1 if world > 1 else 0
+    else:
+        per_step["collective"] = 2 * k * T if world > 1 else 0
     roofline = None
     if fam:
         top = max(fam, key=lambda n: fam[n][0])

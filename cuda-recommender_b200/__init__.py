@@ -69,7 +69,7 @@ ABI_SYMBOLS = [
     "mf_ccdpp_train", "mf_als_train",
     "mf_session_create", "mf_session_destroy", "mf_dist_unique_id", "mf_session_create_dist",
     "mf_session_set_factors", "mf_session_get_factors", "mf_session_get_values",
-    "mf_session_ccdpp_iterate", "mf_session_als_iterate", "mf_session_rmse", "mf_session_kernel_times",
+    "mf_session_ccdpp_iterate", "mf_session_als_iterate", "mf_session_rmse", "mf_session_predict", "mf_session_kernel_times",
     "mf_session_last_seconds", "mf_session_ccd_solve", "mf_session_ccd_update", "mf_session_als_half",
     "mf_build_csr_csc", "mf_degree_bins", "mf_partition", "mf_session_panel_layout",
 ]
@@ -111,6 +111,7 @@ def lib():
         L.mf_session_ccdpp_iterate.argtypes = [vp, C.c_int, vp]
         L.mf_session_als_iterate.argtypes = [vp, C.c_int, vp]
         L.mf_session_rmse.argtypes = [vp, C.POINTER(C.c_double)]
+        L.mf_session_predict.argtypes = [vp, C.c_int64, vp, vp, vp]
         L.mf_session_kernel_times.argtypes = [vp, C.POINTER(mf_kernel_times)]
         L.mf_session_last_seconds.argtypes = [vp, C.POINTER(C.c_double)]
         L.mf_session_ccd_solve.argtypes = [vp, C.c_int, C.c_int]
@@ -283,6 +284,14 @@ class Session:
         r = C.c_double()
         _check(lib().mf_session_rmse(self.h, C.byref(r)))
         return r.value
+
+    def predict(self, row, col):
+        """w_i . h_j of the current factors for arbitrary pairs: float64 array (mf_session_predict)."""
+        row = np.ascontiguousarray(row, np.uint32)
+        col = np.ascontiguousarray(col, np.uint32)
+        out = np.zeros(len(row), np.float64)
+        _check(lib().mf_session_predict(self.h, len(row), row.ctypes.data, col.ctypes.data, out.ctypes.data))
+        return out
 
     def last_seconds(self):
         r = C.c_double()

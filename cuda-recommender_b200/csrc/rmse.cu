@@ -55,6 +55,20 @@ __global__ void __launch_bounds__(256) k_rmse(int64_t nt, const uint32_t* __rest
     }
 }
 
+// predictions for arbitrary pairs: the same arithmetic, one thread per pair, the double goes out unrounded
+__global__ void __launch_bounds__(256) k_predict(int64_t n, const uint32_t* __restrict__ row, const uint32_t* __restrict__ col,
+                                                  const float* __restrict__ W, const float* __restrict__ H, int k,
+                                                  int64_t w_rank_stride, int64_t w_row_stride, int64_t h_rank_stride,
+                                                  int64_t h_row_stride, double* __restrict__ out) {
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+        const float* w = W + (int64_t)row[e] * w_row_stride;
+        const float* h = H + (int64_t)col[e] * h_row_stride;
+        double pred = 0.0;
+        for (int t = 0; t < k; ++t) pred += (double)__fmul_rn(w[t * w_rank_stride], h[t * h_rank_stride]);
+        out[e] = pred;
+    }
+}
+
 }  // namespace
 
 size_t rmse_scratch_doubles(int sm_count) { return 1 + (size_t)sm_count * 8 + 1; }
@@ -71,6 +85,17 @@ int rmse_accumulate(int64_t nt, const uint32_t* trow, const uint32_t* tcol, cons
     MF_CUDA(cudaMemsetAsync(d_acc + 1 + blocks, 0, sizeof(double), st));  // ticket
     k_rmse<<<(unsigned)blocks, 256, 0, st>>>(nt, trow, tcol, tval, W, H, k, w_rank_stride, w_row_stride, h_rank_stride,
                                             h_row_stride, d_acc);
+    MF_CUDA(cudaGetLastError());
+    return MF_OK;
+}
+
+int predict_pairs(int64_t n, const uint32_t* row, const uint32_t* col, const float* W, const float* H, int k,
+                  int64_t w_rank_stride, int64_t w_row_stride, int64_t h_rank_stride, int64_t h_row_stride, double* out,
+                  int sm_count, cudaStream_t st) {
+    if (n <= 0) return MF_OK;
+    int64_t blocks = (n + 255) / 256;
+    if (blocks > (int64_t)sm_count * 16) blocks = (int64_t)sm_count * 16;
+    k_predict<<<(unsigned)blocks, 256, 0, st>>>(n, row, col, W, H, k, w_rank_stride, w_row_stride, h_rank_stride, h_row_stride, out);
     MF_CUDA(cudaGetLastError());
     return MF_OK;
 }

@@ -8,4 +8,8 @@ size_t rmse_scratch_doubles(int sm_count);
 int rmse_accumulate(int64_t nt, const uint32_t* trow, const uint32_t* tcol, const float* tval, const float* W,
                     const float* H, int k, int64_t w_rank_stride, int64_t w_row_stride, int64_t h_rank_stride,
                     int64_t h_row_stride, double* d_acc, int sm_count, cudaStream_t st);
+// out[e] <- w_row[e] . h_col[e] (FP32 products, FP64 sum in rank order — src/extras.cpp:165-168); device pointers
+int predict_pairs(int64_t n, const uint32_t* row, const uint32_t* col, const float* W, const float* H, int k,
+                  int64_t w_rank_stride, int64_t w_row_stride, int64_t h_rank_stride, int64_t h_row_stride, double* out,
+                  int sm_count, cudaStream_t st);
 }  // namespace mf

@@ -166,6 +166,10 @@ int mf_session_get_values(mf_session* s, float* csr_val, float* csc_val);
 int mf_session_ccdpp_iterate(mf_session* s, int n_outer, mf_iter_stats* stats);
 int mf_session_als_iterate(mf_session* s, int n_iter, mf_iter_stats* stats);
 int mf_session_rmse(mf_session* s, double* rmse);
+/* Predictions w_i . h_j of the CURRENT factors for n arbitrary (row, col) pairs (0-based; host or device pointers):
+ * FP32 products summed in rank order in FP64 — the loop body of calculate_rmse_from_file, src/extras.cpp:165-168
+ * (and of dot(), src/tools.cpp:184-198) — so the doubles are bit-identical to the CPU path's on the same factors. */
+int mf_session_predict(mf_session* s, int64_t n, const uint32_t* row, const uint32_t* col, double* out);
 int mf_session_kernel_times(mf_session* s, mf_kernel_times* out);
 /* device seconds of the last iterate call, CUDA events on the session stream (RMSE excluded) */
 int mf_session_last_seconds(mf_session* s, double* seconds);

@@ -36,6 +36,8 @@ def lib():
         L.orc_ccd_solve_sweep_f64.argtypes = L.orc_ccd_solve_sweep.argtypes
         L.orc_ccd_update_sweep.argtypes = [C.c_long, u32p, u32p, f32p, f32p, f32p, C.c_int]
         L.orc_rmse.argtypes = [C.c_long, u32p, u32p, f32p, f32p, f32p, C.c_long, C.c_long, C.c_long, C.c_int]
+        L.orc_predict.argtypes = [C.c_long, u32p, u32p, f32p, f32p, C.c_long, C.c_long, C.c_long, C.c_int, f64p]
+        L.orc_predict.restype = None
         L.orc_rmse.restype = C.c_double
         L.orc_ccdpp.argtypes = [C.c_long, C.c_long, u32p, u32p, f32p, u32p, u32p, f32p, f32p, f32p,
                                 C.c_long, C.c_float, C.c_int, C.c_int,
@@ -91,6 +93,14 @@ def rmse(trow, tcol, tval, W, H, rows, cols, k, als_layout):
     trow, tcol, tval = _u32(trow), _u32(tcol), _f32(tval)
     return float(lib().orc_rmse(len(tval), trow, tcol, tval, _f32(W).reshape(-1), _f32(H).reshape(-1),
                                 rows, cols, k, int(bool(als_layout))))
+
+
+def predict(row, col, W, H, rows, cols, k, als_layout):
+    """Predictions w_i . h_j for arbitrary pairs (src/extras.cpp:165-168): float64 array."""
+    row, col = _u32(row), _u32(col)
+    out = np.zeros(len(row), np.float64)
+    lib().orc_predict(len(row), row, col, _f32(W).reshape(-1), _f32(H).reshape(-1), rows, cols, k, int(bool(als_layout)), out)
+    return out
 
 
 def _test_arrays(test):

@@ -24,6 +24,13 @@ def session_panel_rows(gdim, side_is_csr, user_panel_rows=0):
     return choose_panel_rows(gdim, max(min(cap, want), 8))
 
 
+def session_pad(nseg, nnz, gdim, panel_rows):
+    """The padding granularity a session picks (session.cu pick_pad): 16 when pieces average fewer than 24 entries."""
+    npan = -(-gdim // panel_rows)
+    pieces = max(1, min(nseg * npan, max(nnz, 1)))
+    return 16 if nnz // pieces < 24 else 32
+
+
 def panel_layout(ptr, idx, val, gdim, panel_rows, chunk, pad=32):
     if pad < 8 or pad % 8 or chunk % pad:
         pad = 8

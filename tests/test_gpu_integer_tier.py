@@ -43,7 +43,8 @@ def test_panel_layout_bit_exact(gpu, data_factory, shape, panel_rows, chunk):
         for side, (ptr, idx, val), gdim in ((gpu.SIDE_CSC, csc, d["rows"]), (gpu.SIDE_CSR, csr, d["cols"])):
             got = s.panel_layout(side)
             pr = panel_ref.session_panel_rows(gdim, side == gpu.SIDE_CSR, panel_rows)
-            want = panel_ref.panel_layout(ptr, idx, val, gdim, pr, chunk if chunk else 512)
+            pad = panel_ref.session_pad(len(ptr) - 1, len(idx), gdim, pr)
+            want = panel_ref.panel_layout(ptr, idx, val, gdim, pr, chunk if chunk else 512, pad=pad)
             assert got["n_panels"] == want["n_panels"] and got["n_padded"] == want["n_padded"] and got["n_items"] == want["n_items"]
             assert np.array_equal(got["idx16"], want["idx16"])
             assert np.array_equal(got["val"], want["val"])
