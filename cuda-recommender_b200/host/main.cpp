@@ -71,6 +71,16 @@ int main(int argc, char* argv[]) {
         std::fclose(fp);
         std::printf("[info] model written to %s\n", path.c_str());
     }
+    if (param.do_predict != 0 && param.enable_cuda) {
+        // prediction output, one "%lf" line per test rating — what calculate_rmse_from_file writes to <dir>/output
+        // (src/extras.cpp:143-180, commented out in the reference's main.cpp:146-149); same arithmetic (dot())
+        const std::string path = std::string(param.src_dir) + "/output";
+        FILE* fp = std::fopen(path.c_str(), "w");
+        if (!fp) { std::fprintf(stderr, "can't open output file %s\n", path.c_str()); return EXIT_FAILURE; }
+        for (long e = 0; e < T.nnz; ++e) std::fprintf(fp, "%lf\n", dot(W, T.getTestRow()[e], H, T.getTestCol()[e], ifALS));
+        std::fclose(fp);
+        std::printf("[info] %lu predictions written to %s\n", (unsigned long)T.nnz, path.c_str());
+    }
     std::puts(kRule);
     std::cout << "Total Time: " << now_s() - t_begin << " s.\n";
     return EXIT_SUCCESS;

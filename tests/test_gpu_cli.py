@@ -50,3 +50,23 @@ def test_own_cli(gpu, datagen, data_factory, tmp_path):
     assert re.search(r"Test RMSE = [\d.]+", out)
     assert os.path.getsize(os.path.join(str(tmp_path), "model")) == 2 * 16 + 4 * 6 * (300 + 500)
     assert "Usage:" in _run([CLI])
+
+
+def test_own_cli_prediction_output(gpu, port, datagen, data_factory, tmp_path):
+    """-p 1 writes one prediction per test rating to <dir>/output (the format of calculate_rmse_from_file,
+    src/extras.cpp:143-180); with -save the model file holds the factors those predictions come from."""
+    import numpy as np
+    d = data_factory("small")
+    datagen.write_dataset(str(tmp_path), d)
+    out = _run([CLI, "-CUDA", "-ALS", "-k", "5", "-l", "0.05", "-t", "2", "-p", "1", "-save", str(tmp_path)])
+    assert "FAILED" not in out and "predictions written" in out, out
+    pred = np.loadtxt(os.path.join(str(tmp_path), "output"))
+    assert pred.shape == (d["nnz_test"],)
+    raw = open(os.path.join(str(tmp_path), "model"), "rb").read()
+    W = np.frombuffer(raw, np.float32, 300 * 5, offset=16).reshape(300, 5)
+    H = np.frombuffer(raw, np.float32, 500 * 5, offset=16 + 4 * 300 * 5 + 16).reshape(500, 5)
+    want = port.predict(d["test_row"], d["test_col"], W, H, 300, 500, 5, True)
+    assert np.allclose(pred, want, atol=1e-6, rtol=0)  # "%lf" keeps six decimals
+    final = float(re.search(r"Test RMSE = ([\d.]+)", out).group(1))
+    err = want - d["test_val"].astype(np.float64)
+    assert abs(final - float(np.sqrt(np.mean(err * err)))) < 1e-5
