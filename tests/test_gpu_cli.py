@@ -67,6 +67,6 @@ def test_own_cli_prediction_output(gpu, port, datagen, data_factory, tmp_path):
     H = np.frombuffer(raw, np.float32, 500 * 5, offset=16 + 4 * 300 * 5 + 16).reshape(500, 5)
     want = port.predict(d["test_row"], d["test_col"], W, H, 300, 500, 5, True)
     assert np.allclose(pred, want, atol=1e-6, rtol=0)  # "%lf" keeps six decimals
-    final = float(re.search(r"Test RMSE = ([\d.]+)", out).group(1))
+    final = float(re.search(r"Test RMSE = (\d+\.\d+)", out).group(1))
     err = want - d["test_val"].astype(np.float64)
     assert abs(final - float(np.sqrt(np.mean(err * err)))) < 1e-5
