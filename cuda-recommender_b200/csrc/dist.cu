@@ -124,14 +124,14 @@ int dist_create(Dist** out, int rank, int nranks, const void* id128, int device)
 int dist_destroy(Dist* d) {
     if (!d) return MF_OK;
     for (void* p : d->opened) cudaIpcCloseMemHandle(p);
-    if (d->d_peerW) cudaFree(d->d_peerW);
-    if (d->d_peerH) cudaFree(d->d_peerH);
-    if (d->d_peerFlags) cudaFree(d->d_peerFlags);
-    if (d->flags) cudaFree(d->flags);
-    if (d->llW) cudaFree(d->llW);
-    if (d->llH) cudaFree(d->llH);
-    if (d->d_peerLLW) cudaFree(d->d_peerLLW);
-    if (d->d_peerLLH) cudaFree(d->d_peerLLH);
+    if (d->d_peerW) dev_free(d->d_peerW);
+    if (d->d_peerH) dev_free(d->d_peerH);
+    if (d->d_peerFlags) dev_free(d->d_peerFlags);
+    if (d->flags) dev_free(d->flags);
+    if (d->llW) dev_free(d->llW);
+    if (d->llH) dev_free(d->llH);
+    if (d->d_peerLLW) dev_free(d->d_peerLLW);
+    if (d->d_peerLLH) dev_free(d->d_peerLLH);
     if (d->comm) g_api.CommDestroy(d->comm);
     delete d;
     return MF_OK;
@@ -167,7 +167,7 @@ int dist_setup_p2p(Dist* d, float* W, float* H, int64_t ldm, int64_t ldn, cudaSt
     std::vector<Handles> all((size_t)P);
     MF_CUDA(cudaMemcpyAsync(all.data(), d_all, sizeof(Handles) * (size_t)P, cudaMemcpyDeviceToHost, st));
     MF_CUDA(cudaStreamSynchronize(st));
-    cudaFree(d_all);
+    dev_free(d_all);
     std::vector<float*> pw((size_t)P), ph((size_t)P);
     std::vector<unsigned*> pf((size_t)P);
     std::vector<unsigned long long*> plw((size_t)P), plh((size_t)P);

@@ -157,6 +157,6 @@ extern "C" int mf_build_csr_csc(int64_t rows, int64_t cols, int64_t nnz, const u
     copy(csc_row_idx, d_idx, sizeof(uint32_t) * (size_t)nnz);
     copy(csc_val, d_out, sizeof(float) * (size_t)nnz);
     void* ptrs[] = {d_r, d_c, d_v, d_ptr, d_idx, d_out, d_tmp_idx, d_tmp_val, d_count, d_scan};
-    for (void* p : ptrs) if (p) cudaFree(p);
+    for (void* p : ptrs) if (p) dev_free(p);
     return rc;
 }

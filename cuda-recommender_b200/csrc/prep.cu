@@ -247,7 +247,7 @@ int side_free(Side& s) {
     void* ptrs[] = {s.ptr, s.idx, s.val, s.piece_ptr, s.piece_first, s.item_ptr, s.idx16, s.pval, s.items,
                     s.slot_ptr, s.partials, s.cta_item_ptr, s.panel_item_ptr, s.als_order, s.als_scratch};
     for (void* p : ptrs)
-        if (p) cudaFree(p);
+        if (p) dev_free(p);
     s = Side();
     return MF_OK;
 }
@@ -263,7 +263,7 @@ int side_check_sorted(const Side& s, bool* sorted, cudaStream_t st) {
     int h = 0;
     MF_CUDA(cudaMemcpyAsync(&h, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st));
     MF_CUDA(cudaStreamSynchronize(st));
-    cudaFree(d_bad);
+    dev_free(d_bad);
     *sorted = (h == 0);
     return MF_OK;
 }
@@ -352,7 +352,7 @@ int side_build_panels(Side& s, int panel_rows, int chunk, int ncta, cudaStream_t
                                                                    bin_count, sorted, cost);
         MF_CUDA(cudaGetLastError());
         MF_CUDA(cudaStreamSynchronize(st));
-        cudaFree(s.items);
+        dev_free(s.items);
         s.items = sorted;
         tmp_free(bin_count, st); tmp_free(bin_ptr, st); tmp_free(tmp2, st);
     }
@@ -407,8 +407,8 @@ extern "C" int mf_degree_bins(int64_t nseg, const uint32_t* ptr, uint64_t* seg_i
     MF_CUDA(cudaGetLastError());
     MF_CUDA(cudaMemcpy(seg_in_bin, d_bins, 33 * sizeof(uint64_t), cudaMemcpyDefault));
     MF_CUDA(cudaMemcpy(nnz_in_bin, d_bins + 33, 33 * sizeof(uint64_t), cudaMemcpyDefault));
-    cudaFree(d_bins);
-    cudaFree(d_ptr);
+    dev_free(d_bins);
+    dev_free(d_ptr);
     return MF_OK;
 }
 
@@ -422,7 +422,7 @@ extern "C" int mf_partition(int64_t nseg, const uint32_t* ptr, int P, int64_t* b
     k_partition<<<(P + 1 + 127) / 128, 128>>>(nseg, d_ptr, P, d_b);
     MF_CUDA(cudaGetLastError());
     MF_CUDA(cudaMemcpy(bound, d_b, sizeof(int64_t) * ((size_t)P + 1), cudaMemcpyDefault));
-    cudaFree(d_b);
-    cudaFree(d_ptr);
+    dev_free(d_b);
+    dev_free(d_ptr);
     return MF_OK;
 }

@@ -5,6 +5,8 @@
 #include <stdlib.h>
 
 #include <chrono>
+#include <mutex>
+#include <vector>
 
 #include "common.cuh"
 
@@ -26,6 +28,89 @@ void trace_mark(const char* what) {
     auto now = std::chrono::steady_clock::now();
     fprintf(stderr, "[mf trace] %-34s %9.3f ms\n", what, std::chrono::duration<double, std::milli>(now - last).count());
     last = now;
+}
+
+
+// ---- device arena (common.cuh) -------------------------------------------------------------------------------
+struct DeviceArena {
+    struct Chunk { char* base; size_t size, used; };
+    std::vector<Chunk> chunks;
+    size_t next_chunk = (size_t)256 << 20;
+};
+namespace {
+std::mutex g_arena_mu;
+std::vector<DeviceArena*> g_arenas;  // live arenas (for dev_free's membership test)
+thread_local DeviceArena* t_arena = nullptr;
+constexpr size_t kArenaAlign = 256;
+
+bool arena_add_chunk(DeviceArena* a, size_t bytes) {
+    void* p = nullptr;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) { cudaGetLastError(); return false; }
+    std::lock_guard<std::mutex> lk(g_arena_mu);
+    a->chunks.push_back({(char*)p, bytes, 0});
+    return true;
+}
+}  // namespace
+
+DeviceArena* arena_create(size_t first_chunk_bytes) {
+    DeviceArena* a = new DeviceArena();
+    {
+        std::lock_guard<std::mutex> lk(g_arena_mu);
+        g_arenas.push_back(a);
+    }
+    if (first_chunk_bytes > 0) arena_add_chunk(a, (first_chunk_bytes + kArenaAlign - 1) / kArenaAlign * kArenaAlign);  // best effort
+    return a;
+}
+
+void arena_destroy(DeviceArena* a) {
+    if (!a) return;
+    if (t_arena == a) t_arena = nullptr;
+    std::vector<DeviceArena::Chunk> chunks;
+    {
+        std::lock_guard<std::mutex> lk(g_arena_mu);
+        chunks.swap(a->chunks);
+        for (size_t i = 0; i < g_arenas.size(); ++i)
+            if (g_arenas[i] == a) { g_arenas.erase(g_arenas.begin() + i); break; }
+    }
+    for (auto& c : chunks) cudaFree(c.base);
+    delete a;
+}
+
+void arena_bind(DeviceArena* a) { t_arena = a; }
+
+int dev_alloc_bytes(void** p, size_t bytes) {
+    *p = nullptr;
+    if (bytes == 0) bytes = 1;
+    DeviceArena* a = t_arena;
+    if (a) {
+        const size_t need = (bytes + kArenaAlign - 1) / kArenaAlign * kArenaAlign;
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            {
+                std::lock_guard<std::mutex> lk(g_arena_mu);
+                for (auto& c : a->chunks)
+                    if (c.size - c.used >= need) {
+                        *p = c.base + c.used;
+                        c.used += need;
+                        return MF_OK;
+                    }
+            }
+            if (attempt == 0 && !arena_add_chunk(a, need > a->next_chunk ? need : a->next_chunk)) break;
+        }
+        // the arena could not grow: fall through to a plain allocation
+    }
+    MF_CUDA(cudaMalloc(p, bytes));
+    return MF_OK;
+}
+
+void dev_free(void* p) {
+    if (!p) return;
+    {
+        std::lock_guard<std::mutex> lk(g_arena_mu);
+        for (DeviceArena* a : g_arenas)
+            for (auto& c : a->chunks)
+                if ((char*)p >= c.base && (char*)p < c.base + c.size) return;  // released with the arena
+    }
+    cudaFree(p);
 }
 
 namespace {

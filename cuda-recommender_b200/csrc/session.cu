@@ -399,6 +399,16 @@ int create_impl(const mf_ratings* R, const mf_testset* T, const mf_params* param
     }
     partition_host(rp, nranks, s->row_bound);
     partition_host(cp, nranks, s->col_bound);
+    {   // one device arena for this shard's ratings and layout arrays: ~36 B per rating (two raw copies, two panel
+        // copies with padding) + 12 B per (panel, segment) piece + slack; it grows by chunks if the estimate is short
+        const int64_t nnz_r = (int64_t)rp[s->row_bound[rank + 1]] - (int64_t)rp[s->row_bound[rank]];
+        const int64_t nnz_c = (int64_t)cp[s->col_bound[rank + 1]] - (int64_t)cp[s->col_bound[rank]];
+        const int64_t seg_r = s->row_bound[rank + 1] - s->row_bound[rank], seg_c = s->col_bound[rank + 1] - s->col_bound[rank];
+        const int64_t pieces = seg_r * (R->cols / 16376 + 1) + seg_c * (R->rows / 16376 + 1);
+        const size_t hint = (size_t)(18 * (nnz_r + nnz_c) + 12 * pieces + 24 * (seg_r + seg_c)) + ((size_t)64 << 20);
+        s->arena = arena_create(hint);
+    }
+    ArenaScope arena_scope(s->arena);
     if ((rc = upload_side(s->csr, rp, s->row_bound[rank], s->row_bound[rank + 1], R->csr_col_idx, R->csr_val, R->cols, s->st)) != MF_OK) return fail(rc);
     if ((rc = upload_side(s->csc, cp, s->col_bound[rank], s->col_bound[rank + 1], R->csc_row_idx, R->csc_val, R->rows, s->st)) != MF_OK) return fail(rc);
 
@@ -439,10 +449,11 @@ int create_impl(const mf_ratings* R, const mf_testset* T, const mf_params* param
             if ((rc = side_build_panels(s->csr, pr_r, chunk, s->sm_count, s->st)) != MF_OK) return fail(rc);
             trace_mark("  build both panel layouts");
             // the caller-order index/value arrays are no longer needed: the residual lives in the panel arrays
-            cudaFree(s->csc.idx); s->csc.idx = nullptr; cudaFree(s->csc.val); s->csc.val = nullptr;
-            cudaFree(s->csr.idx); s->csr.idx = nullptr; cudaFree(s->csr.val); s->csr.val = nullptr;
+            dev_free(s->csc.idx); s->csc.idx = nullptr; dev_free(s->csc.val); s->csc.val = nullptr;
+            dev_free(s->csr.idx); s->csr.idx = nullptr; dev_free(s->csr.val); s->csr.val = nullptr;
         }
         trace_mark("sortedness + panel layout");
+        arena_bind(nullptr);  // the factor matrices are exported to the peers through CUDA IPC: allocations of their own
         s->ldm = round_up(s->rows, 32);
         s->ldn = round_up(s->cols, 32);
         if ((rc = dev_alloc(&s->W, (size_t)s->k * s->ldm)) != MF_OK) return fail(rc);
@@ -452,6 +463,7 @@ int create_impl(const mf_ratings* R, const mf_testset* T, const mf_params* param
         cudaMemsetAsync(s->H, 0, sizeof(float) * (size_t)s->k * s->ldn, s->st);
         cudaMemsetAsync(s->v_old, 0, sizeof(float) * (size_t)s->k * s->ldn, s->st);
     } else {
+        arena_bind(nullptr);
         s->ldm = s->k; s->ldn = s->k;
         if ((rc = dev_alloc(&s->W, (size_t)s->rows * s->k)) != MF_OK) return fail(rc);
         if ((rc = dev_alloc(&s->H, (size_t)s->cols * s->k)) != MF_OK) return fail(rc);
@@ -559,7 +571,9 @@ int mf_session_destroy(mf_session* s) {
     side_free(s->csr);
     void* ptrs[] = {s->W, s->H, s->v_old, s->trow, s->tcol, s->tval, s->d_acc, s->d_gridbar};
     for (void* p : ptrs)
-        if (p) cudaFree(p);
+        if (p) dev_free(p);
+    arena_destroy(s->arena);
+    s->arena = nullptr;
     s->timer.destroy();
     if (s->ev_a) cudaEventDestroy(s->ev_a);
     if (s->ev_b) cudaEventDestroy(s->ev_b);
@@ -615,7 +629,7 @@ int mf_session_get_values(mf_session* s, float* csr_val, float* csc_val) {
             int rc = side_panel_to_raw(sd, tmp, s->st);
             if (rc == MF_OK && cudaMemcpyAsync(dsts[i], tmp, sizeof(float) * (size_t)sd.nnz, cudaMemcpyDefault, s->st) != cudaSuccess) rc = MF_ERR_CUDA;
             cudaStreamSynchronize(s->st);
-            cudaFree(tmp);
+            dev_free(tmp);
             MF_TRY(rc);
         } else {
             MF_CUDA(cudaMemcpyAsync(dsts[i], sd.val, sizeof(float) * (size_t)sd.nnz, cudaMemcpyDefault, s->st));
@@ -658,7 +672,7 @@ int mf_session_predict(mf_session* s, int64_t n, const uint32_t* row, const uint
     }
     if (rc == MF_OK) cuda_ok(cudaMemcpyAsync(out, d_out, sizeof(double) * (size_t)n, cudaMemcpyDefault, s->st));
     cuda_ok(cudaStreamSynchronize(s->st));
-    cudaFree(d_row); cudaFree(d_col); cudaFree(d_out);
+    dev_free(d_row); dev_free(d_col); dev_free(d_out);
     return rc;
 }
 

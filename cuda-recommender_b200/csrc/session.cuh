@@ -37,6 +37,7 @@ struct mf_session {
     mf_params prm;
     int device = 0, sm_count = 148;
     cudaStream_t st = nullptr;
+    mf::DeviceArena* arena = nullptr;  // ratings, layout arrays (everything long-lived that is not exported through IPC)
     int64_t rows = 0, cols = 0, nnz = 0;
     int rank = 0, nranks = 1;
     std::vector<int64_t> row_bound, col_bound;  // nranks+1 each
