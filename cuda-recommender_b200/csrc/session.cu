@@ -405,8 +405,10 @@ int create_impl(const mf_ratings* R, const mf_testset* T, const mf_params* param
         const int64_t nnz_c = (int64_t)cp[s->col_bound[rank + 1]] - (int64_t)cp[s->col_bound[rank]];
         const int64_t seg_r = s->row_bound[rank + 1] - s->row_bound[rank], seg_c = s->col_bound[rank + 1] - s->col_bound[rank];
         const int64_t pieces = seg_r * (R->cols / 16376 + 1) + seg_c * (R->rows / 16376 + 1);
-        const size_t hint = (size_t)(18 * (nnz_r + nnz_c) + 12 * pieces + 24 * (seg_r + seg_c)) + ((size_t)64 << 20);
+        const int64_t factors = nranks > 1 ? 0 : 4 * (int64_t)params->k * (R->rows + 2 * R->cols + 96);
+        const size_t hint = (size_t)(18 * (nnz_r + nnz_c) + 12 * pieces + 24 * (seg_r + seg_c) + factors + 12 * (T ? T->nnz : 0)) + ((size_t)64 << 20);
         s->arena = arena_create(hint);
+        trace_mark("  arena chunk");
     }
     ArenaScope arena_scope(s->arena);
     if ((rc = upload_side(s->csr, rp, s->row_bound[rank], s->row_bound[rank + 1], R->csr_col_idx, R->csr_val, R->cols, s->st)) != MF_OK) return fail(rc);
@@ -453,7 +455,7 @@ int create_impl(const mf_ratings* R, const mf_testset* T, const mf_params* param
             dev_free(s->csr.idx); s->csr.idx = nullptr; dev_free(s->csr.val); s->csr.val = nullptr;
         }
         trace_mark("sortedness + panel layout");
-        arena_bind(nullptr);  // the factor matrices are exported to the peers through CUDA IPC: allocations of their own
+        if (nranks > 1) arena_bind(nullptr);  // multi-GPU: the factor matrices are exported to the peers through CUDA IPC — allocations of their own
         s->ldm = round_up(s->rows, 32);
         s->ldn = round_up(s->cols, 32);
         if ((rc = dev_alloc(&s->W, (size_t)s->k * s->ldm)) != MF_OK) return fail(rc);
@@ -463,7 +465,7 @@ int create_impl(const mf_ratings* R, const mf_testset* T, const mf_params* param
         cudaMemsetAsync(s->H, 0, sizeof(float) * (size_t)s->k * s->ldn, s->st);
         cudaMemsetAsync(s->v_old, 0, sizeof(float) * (size_t)s->k * s->ldn, s->st);
     } else {
-        arena_bind(nullptr);
+        if (nranks > 1) arena_bind(nullptr);
         s->ldm = s->k; s->ldn = s->k;
         if ((rc = dev_alloc(&s->W, (size_t)s->rows * s->k)) != MF_OK) return fail(rc);
         if ((rc = dev_alloc(&s->H, (size_t)s->cols * s->k)) != MF_OK) return fail(rc);
@@ -471,6 +473,8 @@ int create_impl(const mf_ratings* R, const mf_testset* T, const mf_params* param
         cudaMemsetAsync(s->H, 0, sizeof(float) * (size_t)s->cols * s->k, s->st);
     }
 
+    trace_mark("  factor allocations");
+    arena_bind(s->arena);
     s->nt = T ? T->nnz : 0;
     if (s->nt > 0) {
         if (!(T->row && T->col && T->val)) { set_error("test arrays are NULL"); return fail(MF_ERR_ARG); }
@@ -481,15 +485,18 @@ int create_impl(const mf_ratings* R, const mf_testset* T, const mf_params* param
         cudaMemcpyAsync(s->tcol, T->col, sizeof(uint32_t) * (size_t)s->nt, cudaMemcpyDefault, s->st);
         cudaMemcpyAsync(s->tval, T->val, sizeof(float) * (size_t)s->nt, cudaMemcpyDefault, s->st);
     }
+    trace_mark("  test set");
     if ((rc = dev_alloc(&s->d_acc, rmse_scratch_doubles(s->sm_count))) != MF_OK) return fail(rc);
     if ((rc = dev_alloc(&s->d_gridbar, 1)) != MF_OK) return fail(rc);
     cudaMemsetAsync(s->d_gridbar, 0, sizeof(unsigned), s->st);
     s->fin_in_kernel = getenv("MF_SEPARATE_FINALIZE") == nullptr;
+    arena_bind(nullptr);
     if (nranks > 1) {
         if (!nccl_id) { set_error("multi-GPU session needs the shared ncclUniqueId"); return fail(MF_ERR_ARG); }
         if ((rc = dist_create(&s->dist, rank, nranks, nccl_id, s->device)) != MF_OK) return fail(rc);
         if (ccd && s->panel && (rc = dist_setup_p2p(s->dist, s->W, s->H, s->ldm, s->ldn, s->st)) != MF_OK) return fail(rc);
     }
+    trace_mark("  scratch + comm");
     cudaError_t e = cudaStreamSynchronize(s->st);
     if (e != cudaSuccess) { set_error("session setup failed: %s", cudaGetErrorString(e)); return fail(MF_ERR_CUDA); }
     trace_mark("factors + test set + comm");
