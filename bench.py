@@ -11,7 +11,7 @@ u-solve)).  Prints ONE JSON line (see the contract in the task statement):
   value / ms_per_step  device time (CUDA events on the library's stream), ratings resident in HBM, max over ranks
   e2e                  the same metric through the drop-in C-ABI call with HOST (pinned) buffers:
                        mf_ccdpp_train(..., maxiter=E) wall time / E, uploads, layout build, per-iteration
-                       RMSE and the factor download included
+                       RMSE and the factor download included (median of --e2e-calls calls)
   roofline             dominant kernel family: compulsory HBM bytes of one launch / average launch time
   cpu_baseline         the reference's own OpenMP path (oracle/_ref, unmodified sources) on this box's host
                        cores, on a bounded sample (a few ranks of one steady-state outer iteration, scaled to k)
@@ -58,6 +58,7 @@ def parse_args():
     ap.add_argument("--schedule", default="fused", choices=["fused", "reference"])
     ap.add_argument("--layout", default="panel", choices=["panel", "direct"])
     ap.add_argument("--e2e-iters", type=int, default=3)
+    ap.add_argument("--e2e-calls", type=int, default=3, help="end-to-end calls (the median wall time is reported)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-ranks", type=int, default=2)
@@ -379,23 +380,30 @@ def run_b200_arm(args):
                              no_launch_timing=1, pipeline=params.pipeline, pad_entries=args.pad)
         h2d = sum(v.nbytes for kk, v in pinned.items() if isinstance(v, np.ndarray) and not kk.startswith("coo_")) + Wt.numel() * 4
         d2h = (Wt.numel() + Ht.numel()) * 4 + 8 * E
-        barrier()
-        t0 = time.perf_counter()
-        if world == 1:
-            st = pkg.ccdpp_train(pinned, Wt.numpy(), Ht.numpy(), p2)
-            e2e_rmse = st[-1]["rmse"]
-        else:
-            s2 = pkg.Session(pinned, p2, rank=rank, nranks=world, nccl_id=nccl_id_again(pkg, dist, dev, rank))
-            s2.set_factors(Wt.numpy())
-            st = s2.iterate(E)
-            Wout, Hout = s2.get_factors()
-            e2e_rmse = st[-1]["rmse"]
-            s2.close()
-        barrier()
-        e2e_wall = max_over_ranks(time.perf_counter() - t0)
+        # the call is repeated and the MEDIAN wall time reported: driver calls (cudaMalloc / cudaFree of GB-sized blocks)
+        # sporadically stall for ~250 ms on a box whose GPUs are being polled by a monitor, which is not the library's time
+        walls = []
+        for rep in range(max(1, args.e2e_calls)):
+            Wt.copy_(torch.from_numpy(W0))
+            barrier()
+            t0 = time.perf_counter()
+            if world == 1:
+                st = pkg.ccdpp_train(pinned, Wt.numpy(), Ht.numpy(), p2)
+                e2e_rmse = st[-1]["rmse"]
+            else:
+                s2 = pkg.Session(pinned, p2, rank=rank, nranks=world, nccl_id=nccl_id_again(pkg, dist, dev, rank))
+                s2.set_factors(Wt.numpy())
+                st = s2.iterate(E)
+                Wout, Hout = s2.get_factors()
+                e2e_rmse = st[-1]["rmse"]
+                s2.close()
+            barrier()
+            walls.append(max_over_ranks(time.perf_counter() - t0))
+        e2e_wall = sorted(walls)[len(walls) // 2]
         e2e = {"value": e2e_wall / E, "unit": UNIT, "h2d_bytes_per_step": int(h2d / E), "d2h_bytes_per_step": int(d2h / E),
                "call": "mf_ccdpp_train" if world == 1 else "mf_session_create_dist+iterate+get_factors",
-               "outer_iters_per_call": E, "call_seconds": e2e_wall, "rmse": e2e_rmse}
+               "outer_iters_per_call": E, "call_seconds": e2e_wall, "calls": len(walls), "call_seconds_all": [round(w, 4) for w in walls],
+               "statistic": "median over calls", "rmse": e2e_rmse}
 
     # ---- the reference's CPU path on this box's host cores (rank 0, single-GPU runs only)
     cpu = None
