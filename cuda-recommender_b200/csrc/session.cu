@@ -94,15 +94,18 @@ void partition_host(const std::vector<uint32_t>& ptr, int P, std::vector<int64_t
     bound[P] = nseg;
 }
 
-// upload segments [s0, s1) of one compressed copy (host or device source pointers)
+// upload segments [s0, s1) of one compressed copy (host or device source pointers).  With `keep` the copies are only
+// enqueued on `st` (the rebased pointer array lives in *keep until the caller has synchronised the stream).
 int upload_side(Side& sd, const std::vector<uint32_t>& ptr_full, int64_t s0, int64_t s1, const uint32_t* idx,
-                const float* val, int64_t gdim, cudaStream_t st) {
+                const float* val, int64_t gdim, cudaStream_t st, std::vector<uint32_t>* keep = nullptr) {
     sd.nseg = s1 - s0;
     sd.seg_offset = s0;
     sd.gdim = gdim;
     const uint32_t e0 = ptr_full[s0], e1 = ptr_full[s1];
     sd.nnz = (int64_t)e1 - (int64_t)e0;
-    std::vector<uint32_t> local((size_t)sd.nseg + 1);
+    std::vector<uint32_t> own;
+    std::vector<uint32_t>& local = keep ? *keep : own;
+    local.resize((size_t)sd.nseg + 1);
     for (int64_t s = 0; s <= sd.nseg; ++s) local[s] = ptr_full[s0 + s] - e0;
     MF_TRY(dev_alloc(&sd.ptr, (size_t)sd.nseg + 1));
     MF_TRY(dev_alloc(&sd.idx, (size_t)sd.nnz));
@@ -112,7 +115,7 @@ int upload_side(Side& sd, const std::vector<uint32_t>& ptr_full, int64_t s0, int
         MF_CUDA(cudaMemcpyAsync(sd.idx, idx + e0, sizeof(uint32_t) * (size_t)sd.nnz, cudaMemcpyDefault, st));
         MF_CUDA(cudaMemcpyAsync(sd.val, val + e0, sizeof(float) * (size_t)sd.nnz, cudaMemcpyDefault, st));
     }
-    MF_CUDA(cudaStreamSynchronize(st));  // `local` goes out of scope
+    if (!keep) MF_CUDA(cudaStreamSynchronize(st));  // `local` goes out of scope
     return MF_OK;
 }
 
@@ -411,19 +414,29 @@ int create_impl(const mf_ratings* R, const mf_testset* T, const mf_params* param
         trace_mark("  arena chunk");
     }
     ArenaScope arena_scope(s->arena);
-    if ((rc = upload_side(s->csr, rp, s->row_bound[rank], s->row_bound[rank + 1], R->csr_col_idx, R->csr_val, R->cols, s->st)) != MF_OK) return fail(rc);
-    if ((rc = upload_side(s->csc, cp, s->col_bound[rank], s->col_bound[rank + 1], R->csc_row_idx, R->csc_val, R->rows, s->st)) != MF_OK) return fail(rc);
+    // The CSC copy goes up first; the CSR copy follows on a second stream while the CSC copy is checked and its panel
+    // layout is built (the first sweep of a rank runs on the CSC copy, and the upload is the longest part of a short call).
+    cudaStream_t st_up = nullptr;
+    std::vector<uint32_t> csr_local;
+    if (cudaStreamCreateWithFlags(&st_up, cudaStreamNonBlocking) != cudaSuccess) { set_error("cudaStreamCreate failed"); return fail(MF_ERR_CUDA); }
+    auto fail_up = [&](int code) { cudaStreamSynchronize(st_up); cudaStreamDestroy(st_up); return fail(code); };
+    auto csr_arrived = [&]() {
+        const cudaError_t e = cudaStreamSynchronize(st_up);
+        if (e != cudaSuccess) { set_error("upload of the CSR copy failed: %s", cudaGetErrorString(e)); return (int)MF_ERR_CUDA; }
+        return (int)MF_OK;
+    };
+    if ((rc = upload_side(s->csc, cp, s->col_bound[rank], s->col_bound[rank + 1], R->csc_row_idx, R->csc_val, R->rows, s->st)) != MF_OK) return fail_up(rc);
+    if ((rc = upload_side(s->csr, rp, s->row_bound[rank], s->row_bound[rank + 1], R->csr_col_idx, R->csr_val, R->cols, st_up, &csr_local)) != MF_OK) return fail_up(rc);
 
-    trace_mark("upload CSR + CSC");
+    trace_mark("upload CSC (CSR in flight)");
     const bool ccd = params->solver_type == MF_SOLVER_CCD;
     if (ccd) {
         s->panel = params->layout == MF_LAYOUT_PANEL;
+        bool ok_r = true, ok_c = true;
         if (s->panel) {
-            bool ok_r = true, ok_c = true;
-            if ((rc = side_check_sorted(s->csr, &ok_r, s->st)) != MF_OK) return fail(rc);
-            if ((rc = side_check_sorted(s->csc, &ok_c, s->st)) != MF_OK) return fail(rc);
-            if (!ok_r || !ok_c) s->panel = false;  // the panel cut needs ascending indices inside a segment
-            trace_mark("  sortedness check");
+            if ((rc = side_check_sorted(s->csc, &ok_c, s->st)) != MF_OK) return fail_up(rc);
+            if (!ok_c) s->panel = false;  // the panel cut needs ascending indices inside a segment
+            trace_mark("  sortedness check (CSC)");
         }
         if (s->panel) {
             // Panel size.  Shared memory a sweep needs: CSC side up to 2 vectors (u_new, u_old), CSR side up to 3
@@ -447,32 +460,41 @@ int create_impl(const mf_ratings* R, const mf_testset* T, const mf_params* param
             };
             s->csc.pad = pick_pad(s->csc, pr_c);
             s->csr.pad = pick_pad(s->csr, pr_r);
-            if ((rc = side_build_panels(s->csc, pr_c, chunk, s->sm_count, s->st)) != MF_OK) return fail(rc);
-            if ((rc = side_build_panels(s->csr, pr_r, chunk, s->sm_count, s->st)) != MF_OK) return fail(rc);
-            trace_mark("  build both panel layouts");
-            // the caller-order index/value arrays are no longer needed: the residual lives in the panel arrays
-            dev_free(s->csc.idx); s->csc.idx = nullptr; dev_free(s->csc.val); s->csc.val = nullptr;
-            dev_free(s->csr.idx); s->csr.idx = nullptr; dev_free(s->csr.val); s->csr.val = nullptr;
+            if ((rc = side_build_panels(s->csc, pr_c, chunk, s->sm_count, s->st)) != MF_OK) return fail_up(rc);
+            if ((rc = csr_arrived()) != MF_OK) return fail_up(rc);
+            if ((rc = side_check_sorted(s->csr, &ok_r, s->st)) != MF_OK) return fail_up(rc);
+            if (ok_r) {
+                if ((rc = side_build_panels(s->csr, pr_r, chunk, s->sm_count, s->st)) != MF_OK) return fail_up(rc);
+                trace_mark("  build both panel layouts");
+                // the caller-order index/value arrays are no longer needed: the residual lives in the panel arrays
+                dev_free(s->csc.idx); s->csc.idx = nullptr; dev_free(s->csc.val); s->csc.val = nullptr;
+                dev_free(s->csr.idx); s->csr.idx = nullptr; dev_free(s->csr.val); s->csr.val = nullptr;
+            } else {
+                s->panel = false;  // DIRECT layout on the caller's arrays; the CSC panel arrays stay unused until destroy
+            }
         }
+        if ((rc = csr_arrived()) != MF_OK) return fail_up(rc);
         trace_mark("sortedness + panel layout");
         if (nranks > 1) arena_bind(nullptr);  // multi-GPU: the factor matrices are exported to the peers through CUDA IPC — allocations of their own
         s->ldm = round_up(s->rows, 32);
         s->ldn = round_up(s->cols, 32);
-        if ((rc = dev_alloc(&s->W, (size_t)s->k * s->ldm)) != MF_OK) return fail(rc);
-        if ((rc = dev_alloc(&s->H, (size_t)s->k * s->ldn)) != MF_OK) return fail(rc);
-        if ((rc = dev_alloc(&s->v_old, (size_t)s->k * s->ldn)) != MF_OK) return fail(rc);
+        if ((rc = dev_alloc(&s->W, (size_t)s->k * s->ldm)) != MF_OK) return fail_up(rc);
+        if ((rc = dev_alloc(&s->H, (size_t)s->k * s->ldn)) != MF_OK) return fail_up(rc);
+        if ((rc = dev_alloc(&s->v_old, (size_t)s->k * s->ldn)) != MF_OK) return fail_up(rc);
         cudaMemsetAsync(s->W, 0, sizeof(float) * (size_t)s->k * s->ldm, s->st);
         cudaMemsetAsync(s->H, 0, sizeof(float) * (size_t)s->k * s->ldn, s->st);
         cudaMemsetAsync(s->v_old, 0, sizeof(float) * (size_t)s->k * s->ldn, s->st);
     } else {
+        if ((rc = csr_arrived()) != MF_OK) return fail_up(rc);
         if (nranks > 1) arena_bind(nullptr);
         s->ldm = s->k; s->ldn = s->k;
-        if ((rc = dev_alloc(&s->W, (size_t)s->rows * s->k)) != MF_OK) return fail(rc);
-        if ((rc = dev_alloc(&s->H, (size_t)s->cols * s->k)) != MF_OK) return fail(rc);
+        if ((rc = dev_alloc(&s->W, (size_t)s->rows * s->k)) != MF_OK) return fail_up(rc);
+        if ((rc = dev_alloc(&s->H, (size_t)s->cols * s->k)) != MF_OK) return fail_up(rc);
         cudaMemsetAsync(s->W, 0, sizeof(float) * (size_t)s->rows * s->k, s->st);
         cudaMemsetAsync(s->H, 0, sizeof(float) * (size_t)s->cols * s->k, s->st);
     }
 
+    cudaStreamDestroy(st_up);
     trace_mark("  factor allocations");
     arena_bind(s->arena);
     s->nt = T ? T->nnz : 0;
