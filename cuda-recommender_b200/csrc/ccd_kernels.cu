@@ -349,8 +349,10 @@ __global__ void __launch_bounds__(1024, 1) k_panel_sweep(PanelSweepArgs a) {
                 const uint32_t lane_off = 4u * (uint32_t)sl;     // this lane's 4 entries inside a 32-entry step
                 float s_add = 0.0f, s_old = 0.0f;
                 if (len != 0u) {
-                    if (ADD) s_add = __ldg(a.s_add + a.seg_offset + d.z);
-                    if (SUB) s_old = __ldg(a.s_old + a.seg_offset + d.z);
+                    // plain loads: the finalize of this very launch rewrites the vector s_add points into (after the grid
+                    // barrier), so the non-coherent path is off limits
+                    if (ADD) s_add = a.s_add[a.seg_offset + d.z];
+                    if (SUB) s_old = a.s_old[a.seg_offset + d.z];
                 }
                 const uint32_t maxlen = __reduce_max_sync(kFull, len);
                 const uint32_t minlen = __reduce_min_sync(kFull, len);
@@ -995,6 +997,22 @@ int panel_sweep(int mode, const PanelSweepArgs& a_in, int ncta, int threads, int
         case kSub | kAdd | kAddSep | kSolve: return launch_panel<kSub | kAdd | kAddSep | kSolve>(a, ncta, threads, smem, st);
         default: set_error("panel sweep: unsupported mode %d", mode); return MF_ERR_ARG;
     }
+}
+
+// Can `ncta` CTAs of the register-ring sweep be resident at once (the in-kernel finalize needs a grid barrier)?
+bool panel_sweep_grid_resident(int ncta, int threads, int panel_rows, int sm_count) {
+    const size_t smem = panel_sweep_smem(kSolve | kSub | kAdd | kAddSep, panel_rows);  // the largest footprint of any mode
+    if (smem > 227 * 1024 - 256) return false;
+    if (cudaFuncSetAttribute(k_panel_sweep<kSolve | kSub | kAdd | kAddSep>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 256) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_panel_sweep<kSolve | kSub | kAdd | kAddSep>, threads, smem) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return (int64_t)per_sm * sm_count >= ncta;
 }
 
 int panel_finalize_lanes(int64_t nseg, int64_t nslots) { return nslots > 4 * nseg ? 32 : 1; }

@@ -89,6 +89,7 @@ struct FinalizePush {
     unsigned epoch;
     int barrier;                         // 1 = send no values, publish the epoch (exchange_wait on the other side)
 };
+bool panel_sweep_grid_resident(int ncta, int threads, int panel_rows, int sm_count);  // grid barrier possible?
 int panel_finalize_lanes(int64_t nseg, int64_t nslots);  // 32: many slots per segment -> a warp per segment, else 1
 int panel_finalize(int64_t nseg, int64_t nslots, const uint32_t* slot_ptr, const float2* partials, const uint32_t* seg_ptr,
                    float lambda, int nmf, float* out, const FinalizePush* push, cudaStream_t st);

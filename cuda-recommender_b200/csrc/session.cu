@@ -511,7 +511,9 @@ int create_impl(const mf_ratings* R, const mf_testset* T, const mf_params* param
     if ((rc = dev_alloc(&s->d_acc, rmse_scratch_doubles(s->sm_count))) != MF_OK) return fail(rc);
     if ((rc = dev_alloc(&s->d_gridbar, 1)) != MF_OK) return fail(rc);
     cudaMemsetAsync(s->d_gridbar, 0, sizeof(unsigned), s->st);
-    s->fin_in_kernel = getenv("MF_SEPARATE_FINALIZE") == nullptr;
+    // finalize inside the sweep kernel needs every CTA of a sweep resident at once (grid barrier): checked, not assumed
+    s->fin_in_kernel = getenv("MF_SEPARATE_FINALIZE") == nullptr && s->panel &&
+                       panel_sweep_grid_resident(std::max(s->csc.ncta, s->csr.ncta), kThreads, std::max(s->csc.panel_rows, s->csr.panel_rows), s->sm_count);
     arena_bind(nullptr);
     if (nranks > 1) {
         if (!nccl_id) { set_error("multi-GPU session needs the shared ncclUniqueId"); return fail(MF_ERR_ARG); }
