@@ -25,6 +25,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <vector>
 
 #include "session.cuh"
 
@@ -48,27 +49,17 @@ constexpr int kStages = 3;  // staging buffers
 #endif
 constexpr int kUnroll8 = MF_ALS_UNROLL8, kUnroll4 = MF_ALS_UNROLL4;  // rows of the Gram loop per unrolled iteration
 
-// segment order: longest-first by degree bin (bit length of the degree), via per-bin cursors
-__global__ void k_order_by_bin(int64_t nseg, const uint32_t* __restrict__ ptr, unsigned* __restrict__ cursor /*[33]*/,
-                               uint32_t* __restrict__ order) {
-    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= nseg) return;
-    const uint32_t d = ptr[s + 1] - ptr[s];
-    const int b = 32 - __clz(d);
-    order[atomicAdd(&cursor[32 - b], 1u)] = (uint32_t)s;
-}
-__global__ void k_bin_count(int64_t nseg, const uint32_t* __restrict__ ptr, unsigned* __restrict__ count /*[33]*/) {
-    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= nseg) return;
-    const uint32_t d = ptr[s + 1] - ptr[s];
-    atomicAdd(&count[32 - (32 - __clz(d))], 1u);
-}
-__global__ void k_bin_scan(unsigned* __restrict__ count, unsigned* __restrict__ cursor) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        unsigned acc = 0;
-        for (int i = 0; i < 33; ++i) { cursor[i] = acc; acc += count[i]; }
-    }
-}
+// Work list of a half-step: one item per segment, or several for a long one — a segment with more than `split` entries
+// is cut into parts of equal length (a multiple of the batch), each part accumulates its share of M on its own CTA and
+// leaves it in global memory; the CTA that finishes a segment's last part adds the parts IN PART ORDER (a fixed tree,
+// whoever arrives last) and factors the sum.  Without it the longest item column of the Netflix shape (180 K ratings)
+// keeps one CTA busy for ~15 ms: nothing on one GPU, the whole half-step on eight.  Items are sorted longest-first.
+struct AlsItem {
+    uint32_t seg;     // local segment
+    uint32_t part;    // part of the segment this item covers
+    uint32_t nparts;  // 1: the whole segment
+    uint32_t slot;    // split segments: index of part 0 in the partial-tile array (also the segment's arrival counter)
+};
 
 // 4/8/16-byte asynchronous global->shared copies (LDGSTS)
 template <int BYTES>
@@ -114,9 +105,9 @@ __device__ __forceinline__ void rank1(float (&acc)[TS][TS], const float (&a)[TS]
 // Shared memory is one region used in turn as staging buffers (Gram loop), split-K scratch and L (factorisation).
 template <int TS, int VW, int MAXREG>
 __global__ void __maxnreg__(MAXREG)
-k_als_tile(int64_t nseg, const uint32_t* __restrict__ order, unsigned* __restrict__ queue, const uint32_t* __restrict__ ptr,
-           const uint32_t* __restrict__ idx, const float* __restrict__ val, const float* __restrict__ Y, float* __restrict__ X,
-           int k, int nb, int ks, int region_floats, float lambda) {
+k_als_tile(int64_t nitems, const AlsItem* __restrict__ items, unsigned* __restrict__ queue, float* partial, unsigned* counters,
+           const uint32_t* __restrict__ ptr, const uint32_t* __restrict__ idx, const float* __restrict__ val,
+           const float* __restrict__ Y, float* __restrict__ X, int k, int nb, int ks, int region_floats, float lambda) {
     extern __shared__ __align__(16) float sm[];
     const int kp = nb * TS;
     const int ntiles = nb * (nb + 1) / 2;
@@ -148,33 +139,41 @@ k_als_tile(int64_t nseg, const uint32_t* __restrict__ order, unsigned* __restric
     const int ldy = kp + ((kp & 7) == 0 ? 4 : 0);
     const int lane = tid & 31, wv = tid >> 5, nwarp = TPS >> 5;
 
-    // The queue runs one segment ahead: while a segment is processed, thread 0 already holds the ticket, the segment
-    // id and the extent of the next one (loads in flight), and leaves them in s_desc[parity] at the end.
-    __shared__ uint32_t s_desc[2][3];  // {segment or 0xffffffff, lo, hi}
-    uint32_t nx_seg = 0xffffffffu, nx_lo = 0, nx_hi = 0;
+    // The queue runs one item ahead: while an item is processed, thread 0 already holds the ticket, the descriptor
+    // and the extent of the next one (loads in flight), and leaves them in s_desc[parity] at the end.
+    __shared__ uint32_t s_desc[2][6];  // {segment or 0xffffffff, lo, hi, part, nparts, slot}
+    __shared__ unsigned s_last;
+    uint32_t nx[6] = {0xffffffffu, 0, 0, 0, 1, 0};
     auto fetch_next = [&]() {
         const unsigned t = atomicAdd(queue, 1u);
-        nx_seg = 0xffffffffu; nx_lo = 0; nx_hi = 0;
-        if (t < nseg) {
-            nx_seg = __ldg(order + t);
-            nx_lo = __ldg(ptr + nx_seg);
-            nx_hi = __ldg(ptr + nx_seg + 1);
+        nx[0] = 0xffffffffu; nx[1] = 0; nx[2] = 0; nx[3] = 0; nx[4] = 1; nx[5] = 0;
+        if (t < nitems) {
+            const uint4 it = __ldg(reinterpret_cast<const uint4*>(items) + t);
+            const uint32_t lo = __ldg(ptr + it.x), hi = __ldg(ptr + it.x + 1);
+            const uint32_t plen = ((hi - lo + it.z - 1) / it.z + kBatch - 1) / kBatch * kBatch;  // part length (als_prepare's rule)
+            const uint32_t plo = min(hi, lo + it.y * plen);
+            nx[0] = it.x; nx[1] = plo; nx[2] = min(hi, plo + plen); nx[3] = it.y; nx[4] = it.z; nx[5] = it.w;
         }
+    };
+    auto publish_next = [&](int slot) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) s_desc[slot][i] = nx[i];
     };
     if (tid == 0) {
         fetch_next();
-        s_desc[0][0] = nx_seg; s_desc[0][1] = nx_lo; s_desc[0][2] = nx_hi;
+        publish_next(0);
     }
     for (int par = 0;; par ^= 1) {
-        __syncthreads();  // the previous segment is finished; s_desc[par] is in place
+        __syncthreads();  // the previous item is finished; s_desc[par] is in place
         const uint32_t seg = s_desc[par][0];
         if (seg == 0xffffffffu) break;
         const uint32_t lo = s_desc[par][1], hi = s_desc[par][2];
+        const uint32_t part = s_desc[par][3], nparts = s_desc[par][4], slot = s_desc[par][5];
         if (tid == 0) fetch_next();
         float* x = X + (int64_t)seg * k;
-        if (hi == lo) {
+        if (hi == lo && nparts == 1) {
             for (int c = tid; c < k; c += TPS) x[c] = 0.0f;
-            if (tid == 0) { s_desc[par ^ 1][0] = nx_seg; s_desc[par ^ 1][1] = nx_lo; s_desc[par ^ 1][2] = nx_hi; }
+            if (tid == 0) publish_next(par ^ 1);
             continue;
         }
         float acc[TS][TS];
@@ -263,6 +262,43 @@ k_als_tile(int64_t nseg, const uint32_t* __restrict__ order, unsigned* __restric
                 }
             }
             __syncthreads();  // the scratch may reach into Lm, which the factorisation is about to write
+        }
+        if (nparts > 1) {
+            // this CTA holds one part of the segment's M: leave it in global memory; the CTA that completes the segment
+            // adds all parts in part order (its own included: the tree does not depend on who arrives last)
+            if (owner) {
+                float* dst = partial + (size_t)(slot + part) * TS * TS * ntiles + q;
+#pragma unroll
+                for (int i = 0; i < TS; ++i)
+#pragma unroll
+                    for (int j = 0; j < TS; ++j) dst[(i * TS + j) * ntiles] = acc[i][j];
+            }
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) {
+                const unsigned arrived = atomicAdd(counters + slot, 1u);
+                s_last = arrived == nparts - 1;
+                if (s_last) counters[slot] = 0u;  // ready for the next half-step
+            }
+            __syncthreads();
+            if (!s_last) {
+                if (tid == 0) publish_next(par ^ 1);
+                continue;
+            }
+            __threadfence();
+            if (owner) {
+#pragma unroll
+                for (int i = 0; i < TS; ++i)
+#pragma unroll
+                    for (int j = 0; j < TS; ++j) acc[i][j] = 0.0f;
+                for (uint32_t pp = 0; pp < nparts; ++pp) {
+                    const float* src = partial + (size_t)(slot + pp) * TS * TS * ntiles + q;
+#pragma unroll
+                    for (int i = 0; i < TS; ++i)
+#pragma unroll
+                        for (int j = 0; j < TS; ++j) acc[i][j] += __ldcg(src + (i * TS + j) * ntiles);
+                }
+            }
         }
         if (owner && I == J) {
 #pragma unroll
@@ -375,7 +411,7 @@ k_als_tile(int64_t nseg, const uint32_t* __restrict__ order, unsigned* __restric
             }
             for (int c = tid; c < k; c += 32) x[c] = xs[pos_of<TS>(c, nb)];
         }
-        if (tid == 0) { s_desc[par ^ 1][0] = nx_seg; s_desc[par ^ 1][1] = nx_lo; s_desc[par ^ 1][2] = nx_hi; }
+        if (tid == 0) publish_next(par ^ 1);
     }
 }
 
@@ -408,7 +444,7 @@ AlsGeometry als_geometry(int k) {
 }
 
 template <int TS, int VW, int MAXREG>
-int launch_als(const AlsGeometry& G, int64_t nseg, const uint32_t* order, unsigned* queue, const Side& s, const float* Y, float* X,
+int launch_als(const AlsGeometry& G, const Side& s, const float* Y, float* X,
                int k, float lambda, int sm_count, cudaStream_t st) {
     static size_t attr = 0;
     if (G.smem > 48 * 1024 && G.smem > attr) {
@@ -424,49 +460,85 @@ int launch_als(const AlsGeometry& G, int64_t nseg, const uint32_t* order, unsign
     MF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_als_tile<TS, VW, MAXREG>, G.tps, G.smem));
     if (per_sm < 1) per_sm = 1;
     int64_t grid = (int64_t)sm_count * per_sm;
-    if (grid > nseg) grid = nseg;
-    k_als_tile<TS, VW, MAXREG><<<(unsigned)grid, G.tps, G.smem, st>>>(nseg, order, queue, s.ptr, s.idx, s.val, Y, X, k, G.nb,
-                                                                        G.ks, G.region_floats, lambda);
+    if (grid > s.als_nitems) grid = s.als_nitems;
+    k_als_tile<TS, VW, MAXREG><<<(unsigned)grid, G.tps, G.smem, st>>>(s.als_nitems, reinterpret_cast<const AlsItem*>(s.als_items),
+                                                                        s.als_queue, s.als_partial, s.als_counters, s.ptr, s.idx,
+                                                                        s.val, Y, X, k, G.nb, G.ks, G.region_floats, lambda);
     MF_CUDA(cudaGetLastError());
     return MF_OK;
 }
 
 template <int TS, int VW>
-int launch_als_vw(const AlsGeometry& G, int64_t nseg, const uint32_t* order, unsigned* queue, const Side& s, const float* Y,
+int launch_als_vw(const AlsGeometry& G, const Side& s, const float* Y,
                   float* X, int k, float lambda, int sm_count, cudaStream_t st) {
     // register classes: 64 (4 x 4 tiles: any number of 32/64-thread CTAs), 112 (8 x 8 tiles: 3 x 192 or 6 x 96 threads per
     // SM), 168 (8 x 8 tiles, up to 384 threads)
     const char* fr = getenv("MF_ALS_REGS");  // tuning knob: 112 or 168
     const int force_regs = fr ? atoi(fr) : 0;
-    if constexpr (TS == 4) return launch_als<TS, VW, MF_ALS_REG4>(G, nseg, order, queue, s, Y, X, k, lambda, sm_count, st);
+    if constexpr (TS == 4) return launch_als<TS, VW, MF_ALS_REG4>(G, s, Y, X, k, lambda, sm_count, st);
     else {
         const bool small = force_regs ? force_regs < 168 : G.tps <= 192;
-        if (small && G.tps <= 192) return launch_als<TS, VW, MF_ALS_REG8>(G, nseg, order, queue, s, Y, X, k, lambda, sm_count, st);
-        return launch_als<TS, VW, 168>(G, nseg, order, queue, s, Y, X, k, lambda, sm_count, st);
+        if (small && G.tps <= 192) return launch_als<TS, VW, MF_ALS_REG8>(G, s, Y, X, k, lambda, sm_count, st);
+        return launch_als<TS, VW, 168>(G, s, Y, X, k, lambda, sm_count, st);
     }
 }
 
 template <int TS>
-int launch_als_ts(const AlsGeometry& G, int64_t nseg, const uint32_t* order, unsigned* queue, const Side& s, const float* Y,
+int launch_als_ts(const AlsGeometry& G, const Side& s, const float* Y,
                   float* X, int k, float lambda, int sm_count, cudaStream_t st) {
-    if (k % 4 == 0) return launch_als_vw<TS, 4>(G, nseg, order, queue, s, Y, X, k, lambda, sm_count, st);
-    if (k % 2 == 0) return launch_als_vw<TS, 2>(G, nseg, order, queue, s, Y, X, k, lambda, sm_count, st);
-    return launch_als_vw<TS, 1>(G, nseg, order, queue, s, Y, X, k, lambda, sm_count, st);
+    if (k % 4 == 0) return launch_als_vw<TS, 4>(G, s, Y, X, k, lambda, sm_count, st);
+    if (k % 2 == 0) return launch_als_vw<TS, 2>(G, s, Y, X, k, lambda, sm_count, st);
+    return launch_als_vw<TS, 1>(G, s, Y, X, k, lambda, sm_count, st);
 }
 
 }  // namespace
 
-// the longest-first segment order of a side, built on first use and kept for the life of the session
-int als_prepare(Side& s, cudaStream_t st) {
-    if (s.als_order || s.nseg <= 0) return MF_OK;
-    MF_TRY(dev_alloc(&s.als_scratch, 33 + 33 + 1));
-    MF_TRY(dev_alloc(&s.als_order, (size_t)s.nseg));
-    MF_CUDA(cudaMemsetAsync(s.als_scratch, 0, sizeof(unsigned) * 67, st));
-    const unsigned g = (unsigned)((s.nseg + 255) / 256);
-    k_bin_count<<<g, 256, 0, st>>>(s.nseg, s.ptr, s.als_scratch);
-    k_bin_scan<<<1, 32, 0, st>>>(s.als_scratch, s.als_scratch + 33);
-    k_order_by_bin<<<g, 256, 0, st>>>(s.nseg, s.ptr, s.als_scratch + 33, s.als_order);
-    MF_CUDA(cudaGetLastError());
+// the work list of a side (items sorted longest-first, long segments split), built on first use and kept for the life
+// of the session; host-side: one download of the pointer array, one sort
+int als_prepare(Side& s, const AlsGeometry& G, cudaStream_t st) {
+    if (s.als_items || s.nseg <= 0) return MF_OK;
+    std::vector<uint32_t> hptr((size_t)s.nseg + 1);
+    MF_CUDA(cudaMemcpyAsync(hptr.data(), s.ptr, sizeof(uint32_t) * hptr.size(), cudaMemcpyDeviceToHost, st));
+    MF_CUDA(cudaStreamSynchronize(st));
+    uint32_t split = 16384;  // entries per part: ~1.3 ms of Gram work at k = 100
+    if (const char* e = getenv("MF_ALS_SPLIT")) {  // tuning / test knob
+        const long v = atol(e);
+        if (v >= kBatch) split = (uint32_t)v;
+    }
+    std::vector<AlsItem> items;
+    std::vector<uint32_t> len;
+    items.reserve((size_t)s.nseg);
+    len.reserve((size_t)s.nseg);
+    uint32_t slots = 0;
+    for (int64_t sg = 0; sg < s.nseg; ++sg) {
+        const uint32_t deg = hptr[sg + 1] - hptr[sg];
+        uint32_t nparts = deg > split ? (deg + split - 1) / split : 1;
+        uint32_t plen = nparts > 1 ? ((deg + nparts - 1) / nparts + kBatch - 1) / kBatch * kBatch : deg;
+        if (nparts > 1) nparts = (deg + plen - 1) / plen;  // rounding the part length up may save a part
+        if (nparts <= 1) { nparts = 1; plen = deg; }
+        // the kernel derives the part length from (deg, nparts) by the same rule: make sure both agree
+        if (nparts > 1 && ((deg + nparts - 1) / nparts + kBatch - 1) / kBatch * kBatch != plen) { nparts = 1; plen = deg; }
+        for (uint32_t p = 0; p < nparts; ++p) {
+            items.push_back({(uint32_t)sg, p, nparts, nparts > 1 ? slots : 0u});
+            len.push_back(nparts > 1 ? std::min(plen, deg - p * plen) : deg);
+        }
+        if (nparts > 1) slots += nparts;
+    }
+    std::vector<uint32_t> perm(items.size());
+    for (size_t i = 0; i < perm.size(); ++i) perm[i] = (uint32_t)i;
+    std::stable_sort(perm.begin(), perm.end(), [&](uint32_t a, uint32_t b) { return len[a] > len[b]; });
+    std::vector<AlsItem> sorted(items.size());
+    for (size_t i = 0; i < perm.size(); ++i) sorted[i] = items[perm[i]];
+    s.als_nitems = (int64_t)sorted.size();
+    AlsItem* d_items = nullptr;
+    MF_TRY(dev_alloc(&d_items, sorted.size()));
+    s.als_items = d_items;
+    MF_TRY(dev_alloc(&s.als_queue, 1));
+    MF_TRY(dev_alloc(&s.als_counters, (size_t)slots + 1));
+    MF_TRY(dev_alloc(&s.als_partial, (size_t)slots * G.TS * G.TS * G.ntiles + 1));
+    MF_CUDA(cudaMemcpyAsync(d_items, sorted.data(), sizeof(AlsItem) * sorted.size(), cudaMemcpyHostToDevice, st));
+    MF_CUDA(cudaMemsetAsync(s.als_counters, 0, sizeof(unsigned) * ((size_t)slots + 1), st));
+    MF_CUDA(cudaStreamSynchronize(st));  // `sorted` goes out of scope
     return MF_OK;
 }
 
@@ -477,11 +549,10 @@ int als_half_step(Side& s, const float* Y, float* X, int k, float lambda, int sm
         set_error("ALS: k=%d needs %zu bytes of shared memory per CTA (limit 227 KB)", k, G.smem);
         return MF_ERR_UNSUPPORTED;
     }
-    MF_TRY(als_prepare(s, st));
-    unsigned* queue = s.als_scratch + 66;
-    MF_CUDA(cudaMemsetAsync(queue, 0, sizeof(unsigned), st));
-    if (G.TS == 8) return launch_als_ts<8>(G, s.nseg, s.als_order, queue, s, Y, X, k, lambda, sm_count, st);
-    return launch_als_ts<4>(G, s.nseg, s.als_order, queue, s, Y, X, k, lambda, sm_count, st);
+    MF_TRY(als_prepare(s, G, st));
+    MF_CUDA(cudaMemsetAsync(s.als_queue, 0, sizeof(unsigned), st));
+    if (G.TS == 8) return launch_als_ts<8>(G, s, Y, X, k, lambda, sm_count, st);
+    return launch_als_ts<4>(G, s, Y, X, k, lambda, sm_count, st);
 }
 
 }  // namespace mf

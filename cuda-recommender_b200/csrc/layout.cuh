@@ -63,9 +63,12 @@ struct Side {
     uint32_t* panel_item_ptr = nullptr; // [npanels+1]
     int ncta = 0;
     bool sorted = true;
-    // ALS: longest-first segment order + bin counters / queue head (als.cu, built on first use)
-    uint32_t* als_order = nullptr;  // [nseg]
-    unsigned* als_scratch = nullptr;
+    // ALS work list (als.cu, built on first use): items sorted longest-first, long segments split into parts
+    void* als_items = nullptr;        // AlsItem[als_nitems]
+    int64_t als_nitems = 0;
+    unsigned* als_queue = nullptr;    // queue head
+    unsigned* als_counters = nullptr; // arrival counter per split segment
+    float* als_partial = nullptr;     // partial tiles of the parts of split segments
 };
 
 int side_free(Side& s);

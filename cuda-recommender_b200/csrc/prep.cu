@@ -245,7 +245,7 @@ inline unsigned grid_for(int64_t n, int block) { return (unsigned)((n + block - 
 
 int side_free(Side& s) {
     void* ptrs[] = {s.ptr, s.idx, s.val, s.piece_ptr, s.piece_first, s.item_ptr, s.idx16, s.pval, s.items,
-                    s.slot_ptr, s.partials, s.cta_item_ptr, s.panel_item_ptr, s.als_order, s.als_scratch};
+                    s.slot_ptr, s.partials, s.cta_item_ptr, s.panel_item_ptr, s.als_items, s.als_queue, s.als_counters, s.als_partial};
     for (void* p : ptrs)
         if (p) dev_free(p);
     s = Side();

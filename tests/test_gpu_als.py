@@ -59,6 +59,32 @@ def test_trajectory_vs_reference_fixture(gpu, port, golden, name):
         assert rel_l2(got, ref32) <= 1.5 * ref_err + 5e-4
 
 
+@pytest.mark.parametrize("k", [10, 40])
+def test_split_segments_match_unsplit(gpu, port, data_factory, monkeypatch, k):
+    """Long segments are cut into parts that accumulate on different CTAs and are added in part order (als.cu).  With the
+    threshold forced down to 64 entries almost every ML-100K-shape segment takes that path: same result as the unsplit
+    run up to summation order, same distance to the FP64 yardstick."""
+    d = data_factory("ml100k")
+    csr, csc, _ = sides(d)
+    lam = 0.05
+    W0, H0 = port.initial_col(d["rows"], k), port.initial_col(d["cols"], k)
+    outs = []
+    for split in (None, "64"):
+        if split:
+            monkeypatch.setenv("MF_ALS_SPLIT", split)
+        with gpu.Session(d, gpu.make_params(gpu.SOLVER_ALS, k=k, lam=lam)) as s:
+            s.set_factors(W0, H0)
+            s.als_half(gpu.SIDE_CSR)
+            s.als_half(gpu.SIDE_CSC)
+            s.als_half(gpu.SIDE_CSR)  # a second half-step on the same side: the arrival counters were reset
+            outs.append(s.get_factors())
+    (W1, H1), (W2, H2) = outs
+    assert rel_l2(W2, W1) < 5e-5 and rel_l2(H2, H1) < 5e-5
+    hiW = port.als_half_step(csr[0], csr[1], csr[2], H0, k, lam, f64=True)
+    hiH = port.als_half_step(csc[0], csc[1], csc[2], hiW.astype(np.float32), k, lam, f64=True)
+    assert rel_l2(H2, hiH) <= max(5e-4, 2 * rel_l2(H1, hiH))
+
+
 def test_als_rejects_ccd_calls(gpu, data_factory):
     d = data_factory("tiny")
     with gpu.Session(d, gpu.make_params(gpu.SOLVER_ALS, k=4)) as s:
