@@ -403,7 +403,7 @@ def run_b200_arm(args):
         e2e = {"value": e2e_wall / E, "unit": UNIT, "h2d_bytes_per_step": int(h2d / E), "d2h_bytes_per_step": int(d2h / E),
                "call": "mf_ccdpp_train" if world == 1 else "mf_session_create_dist+iterate+get_factors",
                "outer_iters_per_call": E, "call_seconds": e2e_wall, "calls": len(walls), "call_seconds_all": [round(w, 4) for w in walls],
-               "statistic": "median over calls", "rmse": e2e_rmse}
+               "statistic": "median over calls (sessions of one process reuse the pooled arena block)", "rmse": e2e_rmse}
 
     # ---- the reference's CPU path on this box's host cores (rank 0, single-GPU runs only)
     cpu = None

@@ -66,7 +66,7 @@ class mf_kernel_times(C.Structure):
 # every symbol include/mf_abi.h declares (tests/test_abi_symbols.py checks header <-> library <-> this list)
 ABI_SYMBOLS = [
     "mf_abi_version", "mf_last_error", "mf_device_count", "mf_params_default", "mf_host_initial_col",
-    "mf_ccdpp_train", "mf_als_train",
+    "mf_ccdpp_train", "mf_als_train", "mf_release_cached_memory",
     "mf_session_create", "mf_session_destroy", "mf_dist_unique_id", "mf_session_create_dist",
     "mf_session_set_factors", "mf_session_get_factors", "mf_session_get_values",
     "mf_session_ccdpp_iterate", "mf_session_als_iterate", "mf_session_rmse", "mf_session_predict", "mf_session_kernel_times",
@@ -111,6 +111,7 @@ def lib():
         L.mf_session_ccdpp_iterate.argtypes = [vp, C.c_int, vp]
         L.mf_session_als_iterate.argtypes = [vp, C.c_int, vp]
         L.mf_session_rmse.argtypes = [vp, C.POINTER(C.c_double)]
+        L.mf_release_cached_memory.argtypes = [C.c_int]
         L.mf_session_predict.argtypes = [vp, C.c_int64, vp, vp, vp]
         L.mf_session_kernel_times.argtypes = [vp, C.POINTER(mf_kernel_times)]
         L.mf_session_last_seconds.argtypes = [vp, C.POINTER(C.c_double)]
@@ -141,6 +142,11 @@ def device_count():
     n = C.c_int(0)
     _check(lib().mf_device_count(C.byref(n)))
     return n.value
+
+
+def release_cached_memory(device=0):
+    """Hand the device memory cached between sessions (rating arena, scratch pool) back to the driver."""
+    _check(lib().mf_release_cached_memory(int(device)))
 
 
 def _ptr(a):

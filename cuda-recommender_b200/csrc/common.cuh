@@ -48,7 +48,7 @@ const char* get_error();
 // thread, dev_alloc() takes from it; dev_free() is a no-op for arena memory (it goes away with the arena) and
 // cudaFree for everything else.  Arrays that are exported through CUDA IPC are allocated unbound.
 struct DeviceArena;
-DeviceArena* arena_create(size_t first_chunk_bytes);
+DeviceArena* arena_create(size_t first_chunk_bytes, cudaStream_t st);  // st: chunks from the stream-ordered pool
 void arena_destroy(DeviceArena* a);
 void arena_bind(DeviceArena* a);  // nullptr: unbind
 int dev_alloc_bytes(void** p, size_t bytes);

@@ -410,7 +410,7 @@ int create_impl(const mf_ratings* R, const mf_testset* T, const mf_params* param
         const int64_t pieces = seg_r * (R->cols / 16376 + 1) + seg_c * (R->rows / 16376 + 1);
         const int64_t factors = nranks > 1 ? 0 : 4 * (int64_t)params->k * (R->rows + 2 * R->cols + 96);
         const size_t hint = (size_t)(18 * (nnz_r + nnz_c) + 12 * pieces + 24 * (seg_r + seg_c) + factors + 12 * (T ? T->nnz : 0)) + ((size_t)64 << 20);
-        s->arena = arena_create(hint);
+        s->arena = arena_create(hint, s->st);
         trace_mark("  arena chunk");
     }
     ArenaScope arena_scope(s->arena);
@@ -580,6 +580,18 @@ void mf_host_initial_col(float* X, int64_t k, int64_t n) {
     srand(0L);
     for (int64_t i = 0; i < n; ++i)
         for (int64_t j = 0; j < k; ++j) X[j * n + i] = 0.1f * (float(rand()) / RAND_MAX) + 0.001f;
+}
+
+int mf_release_cached_memory(int device) {
+    int ndev = 0;
+    MF_CUDA(cudaGetDeviceCount(&ndev));
+    MF_REQUIRE(device >= 0 && device < ndev, "device %d not present (%d CUDA devices)", device, ndev);
+    MF_CUDA(cudaSetDevice(device));
+    MF_CUDA(cudaDeviceSynchronize());
+    cudaMemPool_t pool;
+    MF_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+    MF_CUDA(cudaMemPoolTrimTo(pool, 0));
+    return MF_OK;
 }
 
 int mf_session_create(const mf_ratings* R, const mf_testset* T, const mf_params* params, mf_session** out) {

@@ -69,7 +69,9 @@ void kernel_wrapper_ccdpp_NV(SparseMatrix& R, TestData& T, MatData& W, MatData& 
     std::vector<float> w, h;  // W[t][i] -> w[t*rows+i]
     flatten(W, q.k, (size_t)R.rows, w);
     flatten(H, q.k, (size_t)R.cols, h);
-    if (mf_ccdpp_train(&r, &t, w.data(), h.data(), &q, nullptr) != MF_OK) {
+    const int rc = mf_ccdpp_train(&r, &t, w.data(), h.data(), &q, nullptr);
+    mf_release_cached_memory(q.device);  // no device state left behind, like the reference's cudaDeviceReset (CCD_CUDA.cu:177)
+    if (rc != MF_OK) {
         std::fprintf(stderr, "CCD FAILED: %s\n", mf_last_error());
         return;
     }
@@ -84,7 +86,9 @@ void kernel_wrapper_als_NV(SparseMatrix& R, TestData& T, MatData& W, MatData& H,
     std::vector<float> w, h;  // W[i][t] -> w[i*k+t]
     flatten(W, (size_t)R.rows, q.k, w);
     flatten(H, (size_t)R.cols, q.k, h);
-    if (mf_als_train(&r, &t, w.data(), h.data(), &q, nullptr) != MF_OK) {
+    const int rc = mf_als_train(&r, &t, w.data(), h.data(), &q, nullptr);
+    mf_release_cached_memory(q.device);  // as above (ALS_CUDA.cu:196)
+    if (rc != MF_OK) {
         std::fprintf(stderr, "ALS FAILED: %s\n", mf_last_error());
         return;
     }

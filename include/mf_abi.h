@@ -147,6 +147,13 @@ int mf_ccdpp_train(const mf_ratings* R, const mf_testset* T, float* W, float* H,
 int mf_als_train(const mf_ratings* R, const mf_testset* T, float* W, float* H, const mf_params* params,
                  mf_iter_stats* stats);
 
+/* Device memory the library keeps cached between sessions of one process — the stream-ordered pool that holds a session's
+ * rating / layout arena and its scratch, so that a second training call of the process skips a multi-GB cudaMalloc and a
+ * cudaFree that was measured to stall for up to 0.9 s — goes back to the driver.  The reference leaves no device state
+ * behind (cudaDeviceReset, cuda_src/CCD_CUDA.cu:177, ALS_CUDA.cu:196): the two kernel_wrapper_* shims call this after
+ * training; a host that trains repeatedly does not.                                                                   */
+int mf_release_cached_memory(int device);
+
 /* ---- sessions: ratings, residual, factors resident in HBM ---- */
 int mf_session_create(const mf_ratings* R, const mf_testset* T, const mf_params* params, mf_session** out);
 int mf_session_destroy(mf_session* s);
