@@ -446,16 +446,11 @@ AlsGeometry als_geometry(int k) {
 template <int TS, int VW, int MAXREG>
 int launch_als(const AlsGeometry& G, const Side& s, const float* Y, float* X,
                int k, float lambda, int sm_count, cudaStream_t st) {
-    static size_t attr = 0;
-    if (G.smem > 48 * 1024 && G.smem > attr) {
+    // once per half-step (two host calls): shared-memory limit for this k, and all of the SM's configurable memory as
+    // shared memory — the CTA count per SM is what hides the serial phases
+    if (G.smem > 48 * 1024)
         MF_CUDA(cudaFuncSetAttribute(k_als_tile<TS, VW, MAXREG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.smem));
-        attr = G.smem;
-    }
-    static bool carveout = false;
-    if (!carveout) {  // all of the SM's configurable memory as shared memory: the CTA count per SM is what hides the serial phases
-        MF_CUDA(cudaFuncSetAttribute(k_als_tile<TS, VW, MAXREG>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        carveout = true;
-    }
+    MF_CUDA(cudaFuncSetAttribute(k_als_tile<TS, VW, MAXREG>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     int per_sm = 1;
     MF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_als_tile<TS, VW, MAXREG>, G.tps, G.smem));
     if (per_sm < 1) per_sm = 1;

@@ -877,12 +877,23 @@ __global__ void __launch_bounds__(256) k_direct_sweep(DirectSweepArgs a) {
     }
 }
 
+// kernel attributes are per device: remember per (template instance, device) whether they have been set
+struct PerDeviceOnce {
+    unsigned long long mask = 0;  // devices 0..63
+    bool need() {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+        if (mask >> dev & 1ull) return false;
+        mask |= 1ull << dev;
+        return true;
+    }
+};
+
 template <int MODE>
 int launch_panel(const PanelSweepArgs& a, int ncta, int threads, size_t smem, cudaStream_t st) {
-    static bool attr_set = false;  // per template instance
-    if (!attr_set) {
+    static PerDeviceOnce once;  // per template instance
+    if (once.need()) {
         MF_CUDA(cudaFuncSetAttribute(k_panel_sweep<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 256));
-        attr_set = true;
     }
     k_panel_sweep<MODE><<<ncta, threads, smem, st>>>(a);
     MF_CUDA(cudaGetLastError());
@@ -891,10 +902,9 @@ int launch_panel(const PanelSweepArgs& a, int ncta, int threads, size_t smem, cu
 
 template <int MODE>
 int launch_panel_tma(const PanelSweepArgs& a, int ncta, int threads, size_t smem, cudaStream_t st) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce once;
+    if (once.need()) {
         MF_CUDA(cudaFuncSetAttribute(k_panel_sweep_tma<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 256));
-        attr_set = true;
     }
     k_panel_sweep_tma<MODE><<<ncta, threads, smem, st>>>(a);
     MF_CUDA(cudaGetLastError());
@@ -903,10 +913,9 @@ int launch_panel_tma(const PanelSweepArgs& a, int ncta, int threads, size_t smem
 
 template <int MODE>
 int launch_panel_async(const PanelSweepArgs& a, int ncta, int threads, size_t smem, cudaStream_t st) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce once;
+    if (once.need()) {
         MF_CUDA(cudaFuncSetAttribute(k_panel_sweep_async<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 256));
-        attr_set = true;
     }
     k_panel_sweep_async<MODE><<<ncta, threads, smem, st>>>(a);
     MF_CUDA(cudaGetLastError());
