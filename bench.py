@@ -391,7 +391,7 @@ def run_b200_arm(args):
                 st = pkg.ccdpp_train(pinned, Wt.numpy(), Ht.numpy(), p2)
                 e2e_rmse = st[-1]["rmse"]
             else:
-                s2 = pkg.Session(pinned, p2, rank=rank, nranks=world, nccl_id=nccl_id_again(pkg, dist, dev, rank))
+                s2 = pkg.Session(pinned, p2, rank=rank, nranks=world, nccl_id=nccl_id)  # same id: the communicator is reused
                 s2.set_factors(Wt.numpy())
                 st = s2.iterate(E)
                 Wout, Hout = s2.get_factors()

@@ -588,6 +588,7 @@ int mf_release_cached_memory(int device) {
     MF_REQUIRE(device >= 0 && device < ndev, "device %d not present (%d CUDA devices)", device, ndev);
     MF_CUDA(cudaSetDevice(device));
     MF_CUDA(cudaDeviceSynchronize());
+    dist_release_cached(device);
     cudaMemPool_t pool;
     MF_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
     MF_CUDA(cudaMemPoolTrimTo(pool, 0));

@@ -69,6 +69,7 @@ namespace mf {
 int dist_unique_id(void* id128);
 int dist_create(Dist** out, int rank, int nranks, const void* id128, int device);
 int dist_destroy(Dist* d);
+void dist_release_cached(int device);  // destroys the communicators kept between sessions
 // optional NVLink peer-to-peer exchange (CUDA IPC); falls back to NCCL silently when unavailable
 int dist_setup_p2p(Dist* d, float* W, float* H, int64_t ldm, int64_t ldn, cudaStream_t st);
 unsigned long long* const* dist_peer_ll(const Dist* d, bool h);

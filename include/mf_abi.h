@@ -160,6 +160,8 @@ int mf_session_destroy(mf_session* s);
 /* multi-GPU: one session per rank/GPU; this rank keeps CSR row block + CSC column block `rank` of
  * `nranks` (nnz-balanced split) and all-gathers fresh factor blocks over NCCL.  nccl_unique_id is the
  * 128-byte ncclUniqueId every rank must share (rank 0: mf_dist_unique_id, then broadcast it).        */
+/* Sessions created with the SAME unique id (same rank, size, device) in one process share one NCCL communicator:
+ * ncclCommInitRank (0.5-1 s) is paid once; mf_release_cached_memory() destroys the cached communicators.        */
 int mf_dist_unique_id(void* id128);
 int mf_session_create_dist(const mf_ratings* R, const mf_testset* T, const mf_params* params, int rank, int nranks,
                            const void* nccl_unique_id, mf_session** out);
