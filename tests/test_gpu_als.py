@@ -11,7 +11,8 @@ from conftest import GOLDEN_ALS, rel_l2, sides
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("shape,k", [("ml100k", 10), ("small", 24), ("small", 3), ("small", 40), ("tiny", 100), ("small", 64)])
+@pytest.mark.parametrize("shape,k", [("ml100k", 10), ("small", 24), ("small", 3), ("small", 40), ("tiny", 100), ("small", 64),
+                                     ("small", 1), ("small", 23), ("tiny", 128), ("small", 7)])
 def test_half_step_parity(gpu, port, data_factory, shape, k):
     d = data_factory(shape)
     csr, csc, _ = sides(d)
