@@ -225,3 +225,23 @@ def test_rmse_kernel(gpu, port, data_factory):
         got = s.rmse()
     want = port.rmse(test[0], test[1], test[2], W, H, d["rows"], d["cols"], k, False)
     assert got == pytest.approx(want, rel=1e-12)
+
+
+def test_nmf_projection_extension(gpu, port, data_factory):
+    """mf_params.nmf_project = 1 (the -N option the reference parses and never uses): every solved coordinate is clamped at
+    zero in the finalize, so the factors stay non-negative; with the option off the same run has negative entries and is
+    the reference's arithmetic."""
+    d = data_factory("small")
+    k = 6
+    W0 = port.initial_col(k, d["rows"])
+    outs = []
+    for nmf in (0, 1):
+        with gpu.Session(d, gpu.make_params(k=k, lam=0.05, maxinner=2, nmf_project=nmf)) as s:
+            s.set_factors(W0)
+            st = s.iterate(2)
+            W, H = s.get_factors()
+            outs.append((W, H, st[-1]["rmse"]))
+    (W, H, r0), (Wn, Hn, r1) = outs
+    assert (W < 0).any() or (H < 0).any()
+    assert (Wn >= 0).all() and (Hn >= 0).all() and np.isfinite(r1)
+    assert not np.array_equal(Wn, W)
