@@ -5,12 +5,14 @@
 // updateH_overW_kernel (cuda_src/ALS_CUDA.cu:81-181), which give every row to ONE thread and
 // malloc() k*k floats per thread on the device heap.
 //
-// Here one CTA owns a segment (a user row or an item column) at a time; segments are visited longest-first
-// (degree-binned order) through an atomic queue.  Everything about a segment is one register-tiled computation on
+// Here one CTA owns a segment (a user row or an item column) at a time — or one part of a long segment, see AlsItem —
+// and takes its work from a list sorted longest-first through an atomic queue that runs one item ahead.  Everything
+// about a segment is one register-tiled computation on
 // the augmented matrix  M = [Y_O | r]^T [Y_O | r]  (+ lambda on the first k diagonal entries, lambda NOT scaled by
 // |O|, src/ALS.cpp:120-122):
 //   * the segment's factor rows Y[idx] are staged through shared memory in batches of 32 rows with asynchronous
-//     copies (cp.async, double-buffered), the rating r is stored as one more column behind the k factor columns;
+//     copies (cp.async, three buffers, one barrier per batch, one row per lane), the rating r is staged as one more
+//     column behind the k factor columns;
 //   * M is accumulated in registers as TS x TS tiles of the lower triangle (TS = 8, or 4 for small k), one tile per
 //     thread, the rows of a batch dealt to `ks` thread groups (split-K) whose partial tiles are added in a fixed
 //     order through shared memory: the Gram matrix A = M[0:k,0:k] and the right-hand side b = M[k,0:k] come out of
