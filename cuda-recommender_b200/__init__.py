@@ -71,7 +71,7 @@ ABI_SYMBOLS = [
     "mf_session_set_factors", "mf_session_get_factors", "mf_session_get_values",
     "mf_session_ccdpp_iterate", "mf_session_als_iterate", "mf_session_rmse", "mf_session_predict", "mf_session_kernel_times",
     "mf_session_last_seconds", "mf_session_ccd_solve", "mf_session_ccd_update", "mf_session_als_half",
-    "mf_build_csr_csc", "mf_degree_bins", "mf_partition", "mf_session_panel_layout",
+    "mf_build_csr_csc", "mf_degree_bins", "mf_partition", "mf_session_panel_layout", "mf_als_plan",
 ]
 
 _lib = None
@@ -112,6 +112,7 @@ def lib():
         L.mf_session_als_iterate.argtypes = [vp, C.c_int, vp]
         L.mf_session_rmse.argtypes = [vp, C.POINTER(C.c_double)]
         L.mf_release_cached_memory.argtypes = [C.c_int]
+        L.mf_als_plan.argtypes = [C.c_int64, vp, C.c_uint32, vp, C.POINTER(C.c_int64), C.POINTER(C.c_uint32)]
         L.mf_session_predict.argtypes = [vp, C.c_int64, vp, vp, vp]
         L.mf_session_kernel_times.argtypes = [vp, C.POINTER(mf_kernel_times)]
         L.mf_session_last_seconds.argtypes = [vp, C.POINTER(C.c_double)]
@@ -142,6 +143,16 @@ def device_count():
     n = C.c_int(0)
     _check(lib().mf_device_count(C.byref(n)))
     return n.value
+
+
+def als_plan(ptr, split=8192):
+    """The ALS work list for a host pointer array: (items[n, 4] = {segment, part, nparts, slot}, n_slots).  Host-only."""
+    ptr = np.ascontiguousarray(ptr, np.uint32)
+    n, slots = C.c_int64(0), C.c_uint32(0)
+    _check(lib().mf_als_plan(len(ptr) - 1, ptr.ctypes.data, int(split), None, C.byref(n), C.byref(slots)))
+    items = np.zeros((n.value, 4), np.uint32)
+    _check(lib().mf_als_plan(len(ptr) - 1, ptr.ctypes.data, int(split), items.ctypes.data, C.byref(n), C.byref(slots)))
+    return items, int(slots.value)
 
 
 def release_cached_memory(device=0):

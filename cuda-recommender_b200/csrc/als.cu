@@ -25,6 +25,7 @@
 // Shared-memory layout of a staged row / of a column of L: 4-float chunks; with TS = 8 the two chunks of tile t
 // sit at chunk positions t and nb + t, so that consecutive tiles read consecutive 16-byte words (no bank conflicts).
 #include <stdlib.h>
+#include <string.h>
 
 #include <algorithm>
 #include <vector>
@@ -490,25 +491,16 @@ int launch_als_ts(const AlsGeometry& G, const Side& s, const float* Y,
 
 }  // namespace
 
-// the work list of a side (items sorted longest-first, long segments split), built on first use and kept for the life
-// of the session; host-side: one download of the pointer array, one sort
-int als_prepare(Side& s, const AlsGeometry& G, cudaStream_t st) {
-    if (s.als_items || s.nseg <= 0) return MF_OK;
-    std::vector<uint32_t> hptr((size_t)s.nseg + 1);
-    MF_CUDA(cudaMemcpyAsync(hptr.data(), s.ptr, sizeof(uint32_t) * hptr.size(), cudaMemcpyDeviceToHost, st));
-    MF_CUDA(cudaStreamSynchronize(st));
-    uint32_t split = 8192;  // entries per part (~0.7 ms of Gram work at k = 100); measured flat from 4 K to 64 K on one GPU at
-                            // k = 40 / 100, 6 % better than 16 K at k = 10, and shorter tails when the shard is small
-    if (const char* e = getenv("MF_ALS_SPLIT")) {  // tuning / test knob
-        const long v = atol(e);
-        if (v >= kBatch) split = (uint32_t)v;
-    }
+// The work list of a half-step from the (host) pointer array: one item per segment, or `nparts` items for a segment with
+// more than `split` entries; parts have equal length plen = roundup32(ceil(deg / nparts)) — the rule the kernel re-derives
+// from (deg, nparts) — and the list is sorted longest-first (stable).  *slots = number of partial-tile slots needed.
+void als_plan(const uint32_t* hptr, int64_t nseg, uint32_t split, std::vector<AlsItem>& sorted, uint32_t* slots_out) {
     std::vector<AlsItem> items;
     std::vector<uint32_t> len;
-    items.reserve((size_t)s.nseg);
-    len.reserve((size_t)s.nseg);
+    items.reserve((size_t)nseg);
+    len.reserve((size_t)nseg);
     uint32_t slots = 0;
-    for (int64_t sg = 0; sg < s.nseg; ++sg) {
+    for (int64_t sg = 0; sg < nseg; ++sg) {
         const uint32_t deg = hptr[sg + 1] - hptr[sg];
         uint32_t nparts = deg > split ? (deg + split - 1) / split : 1;
         uint32_t plen = nparts > 1 ? ((deg + nparts - 1) / nparts + kBatch - 1) / kBatch * kBatch : deg;
@@ -525,8 +517,27 @@ int als_prepare(Side& s, const AlsGeometry& G, cudaStream_t st) {
     std::vector<uint32_t> perm(items.size());
     for (size_t i = 0; i < perm.size(); ++i) perm[i] = (uint32_t)i;
     std::stable_sort(perm.begin(), perm.end(), [&](uint32_t a, uint32_t b) { return len[a] > len[b]; });
-    std::vector<AlsItem> sorted(items.size());
+    sorted.resize(items.size());
     for (size_t i = 0; i < perm.size(); ++i) sorted[i] = items[perm[i]];
+    *slots_out = slots;
+}
+
+// the work list of a side (items sorted longest-first, long segments split), built on first use and kept for the life
+// of the session; host-side: one download of the pointer array, one sort
+int als_prepare(Side& s, const AlsGeometry& G, cudaStream_t st) {
+    if (s.als_items || s.nseg <= 0) return MF_OK;
+    std::vector<uint32_t> hptr((size_t)s.nseg + 1);
+    MF_CUDA(cudaMemcpyAsync(hptr.data(), s.ptr, sizeof(uint32_t) * hptr.size(), cudaMemcpyDeviceToHost, st));
+    MF_CUDA(cudaStreamSynchronize(st));
+    uint32_t split = 8192;  // entries per part (~0.7 ms of Gram work at k = 100); measured flat from 4 K to 64 K on one GPU at
+                            // k = 40 / 100, 6 % better than 16 K at k = 10, and shorter tails when the shard is small
+    if (const char* e = getenv("MF_ALS_SPLIT")) {  // tuning / test knob
+        const long v = atol(e);
+        if (v >= kBatch) split = (uint32_t)v;
+    }
+    std::vector<AlsItem> sorted;
+    uint32_t slots = 0;
+    als_plan(hptr.data(), s.nseg, split, sorted, &slots);
     s.als_nitems = (int64_t)sorted.size();
     AlsItem* d_items = nullptr;
     MF_TRY(dev_alloc(&d_items, sorted.size()));
@@ -551,6 +562,18 @@ int als_half_step(Side& s, const float* Y, float* X, int k, float lambda, int sm
     MF_CUDA(cudaMemsetAsync(s.als_queue, 0, sizeof(unsigned), st));
     if (G.TS == 8) return launch_als_ts<8>(G, s, Y, X, k, lambda, sm_count, st);
     return launch_als_ts<4>(G, s, Y, X, k, lambda, sm_count, st);
+}
+
+// host-only planner behind the C-ABI (include/mf_abi.h: mf_als_plan)
+int als_plan_host(const uint32_t* ptr, int64_t nseg, uint32_t split, uint32_t* items4, int64_t* n_items, uint32_t* n_slots) {
+    if (split < (uint32_t)kBatch) split = (uint32_t)kBatch;
+    std::vector<AlsItem> sorted;
+    uint32_t slots = 0;
+    als_plan(ptr, nseg, split, sorted, &slots);
+    if (n_items) *n_items = (int64_t)sorted.size();
+    if (n_slots) *n_slots = slots;
+    if (items4) memcpy(items4, sorted.data(), sizeof(AlsItem) * sorted.size());
+    return MF_OK;
 }
 
 }  // namespace mf

@@ -859,6 +859,11 @@ int mf_session_ccd_update(mf_session* s, int t, int add) {
     return MF_OK;
 }
 
+int mf_als_plan(int64_t nseg, const uint32_t* ptr, uint32_t split, uint32_t* items, int64_t* n_items, uint32_t* n_slots) {
+    MF_REQUIRE(nseg >= 0 && ptr != nullptr, "bad argument");
+    return als_plan_host(ptr, nseg, split, items, n_items, n_slots);
+}
+
 int mf_session_kernel_times(mf_session* s, mf_kernel_times* out) {
     MF_REQUIRE(s && out, "NULL argument");
     memset(out, 0, sizeof(*out));

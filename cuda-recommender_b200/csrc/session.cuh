@@ -86,4 +86,5 @@ int dist_allgather_blocks(Dist* d, float* vec, const std::vector<int64_t>& bound
 int dist_allreduce_sum_double(Dist* d, double* dev_value, cudaStream_t st);
 // als.cu
 int als_half_step(Side& s, const float* Y, float* X, int k, float lambda, int sm_count, cudaStream_t st);
+int als_plan_host(const uint32_t* ptr, int64_t nseg, uint32_t split, uint32_t* items4, int64_t* n_items, uint32_t* n_slots);
 }  // namespace mf

@@ -204,6 +204,11 @@ int mf_build_csr_csc(int64_t rows, int64_t cols, int64_t nnz, const uint32_t* co
 int mf_degree_bins(int64_t nseg, const uint32_t* ptr, uint64_t* seg_in_bin, uint64_t* nnz_in_bin, int device);
 /* nnz-balanced contiguous partition into P blocks: bound[p] = first segment with ptr[s] >= ceil(p*nnz/P). */
 int mf_partition(int64_t nseg, const uint32_t* ptr, int P, int64_t* bound, int device);
+/* The work list of an ALS half-step, as the session plans it from a HOST pointer array (host-only, no device needed): one
+ * item {segment, part, nparts, slot} per segment, or nparts items for a segment with more than `split` entries (parts of
+ * equal length, a multiple of 32; the library's default split is 8192), sorted longest-first.  items: NULL or room for
+ * 4 x (*n_items) uint32 (call twice); *n_slots = partial-tile slots the split segments need.                           */
+int mf_als_plan(int64_t nseg, const uint32_t* ptr, uint32_t split, uint32_t* items, int64_t* n_items, uint32_t* n_slots);
 /* the panel layout this session built for one side, copied out for inspection by the tests:
  * sizes first (any pointer NULL -> only *n_padded / *n_items / *n_panels are written).                 */
 int mf_session_panel_layout(mf_session* s, int side, int64_t* n_padded, int64_t* n_items, int64_t* n_panels,
