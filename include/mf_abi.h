@@ -151,7 +151,8 @@ int mf_als_train(const mf_ratings* R, const mf_testset* T, float* W, float* H, c
  * rating / layout arena and its scratch, so that a second training call of the process skips a multi-GB cudaMalloc and a
  * cudaFree that was measured to stall for up to 0.9 s — goes back to the driver.  The reference leaves no device state
  * behind (cudaDeviceReset, cuda_src/CCD_CUDA.cu:177, ALS_CUDA.cu:196): the two kernel_wrapper_* shims call this after
- * training; a host that trains repeatedly does not.                                                                   */
+ * training; a host that trains repeatedly does not.  Call it only while no session is open on `device` (it also destroys
+ * the NCCL communicators cached for that device).                                                                      */
 int mf_release_cached_memory(int device);
 
 /* ---- sessions: ratings, residual, factors resident in HBM ---- */
