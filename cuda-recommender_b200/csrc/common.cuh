@@ -75,6 +75,12 @@ static inline void tmp_free(void* p, cudaStream_t st) {
     if (p) cudaFreeAsync(p, st);
 }
 
+// upload.cu: host -> device copy ordered on `st`; a pageable host source is staged through page-locked bounce buffers by
+// several host threads (returns once the source has been read), anything else is one cudaMemcpyAsync
+int upload_bytes(void* dst, const void* src, size_t bytes, cudaStream_t st);
+bool host_pageable(const void* p);
+void upload_release_cached();
+
 static inline uint32_t ceil_div_u32(uint64_t a, uint64_t b) { return (uint32_t)((a + b - 1) / b); }
 
 // exclusive scan of n uint32 values into out[0..n] (out[n] = total); in and out may alias only if

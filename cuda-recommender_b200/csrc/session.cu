@@ -112,8 +112,8 @@ int upload_side(Side& sd, const std::vector<uint32_t>& ptr_full, int64_t s0, int
     MF_TRY(dev_alloc(&sd.val, (size_t)sd.nnz));
     MF_CUDA(cudaMemcpyAsync(sd.ptr, local.data(), sizeof(uint32_t) * local.size(), cudaMemcpyHostToDevice, st));
     if (sd.nnz > 0) {
-        MF_CUDA(cudaMemcpyAsync(sd.idx, idx + e0, sizeof(uint32_t) * (size_t)sd.nnz, cudaMemcpyDefault, st));
-        MF_CUDA(cudaMemcpyAsync(sd.val, val + e0, sizeof(float) * (size_t)sd.nnz, cudaMemcpyDefault, st));
+        MF_TRY(upload_bytes(sd.idx, idx + e0, sizeof(uint32_t) * (size_t)sd.nnz, st));
+        MF_TRY(upload_bytes(sd.val, val + e0, sizeof(float) * (size_t)sd.nnz, st));
     }
     if (!keep) MF_CUDA(cudaStreamSynchronize(st));  // `local` goes out of scope
     return MF_OK;
@@ -481,17 +481,23 @@ int create_impl(const mf_ratings* R, const mf_testset* T, const mf_params* param
         if ((rc = dev_alloc(&s->W, (size_t)s->k * s->ldm)) != MF_OK) return fail_up(rc);
         if ((rc = dev_alloc(&s->H, (size_t)s->k * s->ldn)) != MF_OK) return fail_up(rc);
         if ((rc = dev_alloc(&s->v_old, (size_t)s->k * s->ldn)) != MF_OK) return fail_up(rc);
-        cudaMemsetAsync(s->W, 0, sizeof(float) * (size_t)s->k * s->ldm, s->st);
-        cudaMemsetAsync(s->H, 0, sizeof(float) * (size_t)s->k * s->ldn, s->st);
-        cudaMemsetAsync(s->v_old, 0, sizeof(float) * (size_t)s->k * s->ldn, s->st);
+        if (cudaMemsetAsync(s->W, 0, sizeof(float) * (size_t)s->k * s->ldm, s->st) != cudaSuccess ||
+            cudaMemsetAsync(s->H, 0, sizeof(float) * (size_t)s->k * s->ldn, s->st) != cudaSuccess ||
+            cudaMemsetAsync(s->v_old, 0, sizeof(float) * (size_t)s->k * s->ldn, s->st) != cudaSuccess) {
+            set_error("cudaMemsetAsync of the factor matrices failed: %s", cudaGetErrorString(cudaGetLastError()));
+            return fail_up(MF_ERR_CUDA);
+        }
     } else {
         if ((rc = csr_arrived()) != MF_OK) return fail_up(rc);
         if (nranks > 1) arena_bind(nullptr);
         s->ldm = s->k; s->ldn = s->k;
         if ((rc = dev_alloc(&s->W, (size_t)s->rows * s->k)) != MF_OK) return fail_up(rc);
         if ((rc = dev_alloc(&s->H, (size_t)s->cols * s->k)) != MF_OK) return fail_up(rc);
-        cudaMemsetAsync(s->W, 0, sizeof(float) * (size_t)s->rows * s->k, s->st);
-        cudaMemsetAsync(s->H, 0, sizeof(float) * (size_t)s->cols * s->k, s->st);
+        if (cudaMemsetAsync(s->W, 0, sizeof(float) * (size_t)s->rows * s->k, s->st) != cudaSuccess ||
+            cudaMemsetAsync(s->H, 0, sizeof(float) * (size_t)s->cols * s->k, s->st) != cudaSuccess) {
+            set_error("cudaMemsetAsync of the factor matrices failed: %s", cudaGetErrorString(cudaGetLastError()));
+            return fail_up(MF_ERR_CUDA);
+        }
     }
 
     cudaStreamDestroy(st_up);
@@ -503,14 +509,14 @@ int create_impl(const mf_ratings* R, const mf_testset* T, const mf_params* param
         if ((rc = dev_alloc(&s->trow, (size_t)s->nt)) != MF_OK) return fail(rc);
         if ((rc = dev_alloc(&s->tcol, (size_t)s->nt)) != MF_OK) return fail(rc);
         if ((rc = dev_alloc(&s->tval, (size_t)s->nt)) != MF_OK) return fail(rc);
-        cudaMemcpyAsync(s->trow, T->row, sizeof(uint32_t) * (size_t)s->nt, cudaMemcpyDefault, s->st);
-        cudaMemcpyAsync(s->tcol, T->col, sizeof(uint32_t) * (size_t)s->nt, cudaMemcpyDefault, s->st);
-        cudaMemcpyAsync(s->tval, T->val, sizeof(float) * (size_t)s->nt, cudaMemcpyDefault, s->st);
+        if ((rc = upload_bytes(s->trow, T->row, sizeof(uint32_t) * (size_t)s->nt, s->st)) != MF_OK) return fail(rc);
+        if ((rc = upload_bytes(s->tcol, T->col, sizeof(uint32_t) * (size_t)s->nt, s->st)) != MF_OK) return fail(rc);
+        if ((rc = upload_bytes(s->tval, T->val, sizeof(float) * (size_t)s->nt, s->st)) != MF_OK) return fail(rc);
     }
     trace_mark("  test set");
     if ((rc = dev_alloc(&s->d_acc, rmse_scratch_doubles(s->sm_count))) != MF_OK) return fail(rc);
     if ((rc = dev_alloc(&s->d_gridbar, 1)) != MF_OK) return fail(rc);
-    cudaMemsetAsync(s->d_gridbar, 0, sizeof(unsigned), s->st);
+    if (cudaMemsetAsync(s->d_gridbar, 0, sizeof(unsigned), s->st) != cudaSuccess) { set_error("cudaMemsetAsync failed: %s", cudaGetErrorString(cudaGetLastError())); return fail(MF_ERR_CUDA); }
     // finalize inside the sweep kernel needs every CTA of a sweep resident at once (grid barrier): checked, not assumed
     s->fin_in_kernel = getenv("MF_SEPARATE_FINALIZE") == nullptr && s->panel &&
                        panel_sweep_grid_resident(std::max(s->csc.ncta, s->csr.ncta), kThreads, std::max(s->csc.panel_rows, s->csr.panel_rows), s->sm_count);
@@ -589,6 +595,7 @@ int mf_release_cached_memory(int device) {
     MF_CUDA(cudaSetDevice(device));
     MF_CUDA(cudaDeviceSynchronize());
     dist_release_cached(device);
+    upload_release_cached();
     cudaMemPool_t pool;
     MF_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
     MF_CUDA(cudaMemPoolTrimTo(pool, 0));
