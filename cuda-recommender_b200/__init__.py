@@ -60,7 +60,8 @@ class mf_kernel_times(C.Structure):
                 ("als_s", C.c_double), ("als_launches", C.c_int64), ("rmse_s", C.c_double), ("rmse_launches", C.c_int64),
                 ("collective_s", C.c_double), ("collective_launches", C.c_int64),
                 ("solve_bytes", C.c_int64), ("fused_bytes", C.c_int64), ("update_bytes", C.c_int64),
-                ("total_launches", C.c_int64)]
+                ("total_launches", C.c_int64),
+                ("persistent_s", C.c_double), ("persistent_launches", C.c_int64), ("persistent_bytes", C.c_int64)]
 
 
 # every symbol include/mf_abi.h declares (tests/test_abi_symbols.py checks header <-> library <-> this list)

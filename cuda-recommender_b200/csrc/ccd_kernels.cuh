@@ -58,6 +58,46 @@ struct PanelSweepArgs {
     SweepFinalize fin;    // register-ring pipeline only
 };
 
+// ---- persistent kernel (one cooperative launch per outer iteration, ccd_kernels.cu) ----
+struct PersistSide {
+    const uint16_t* idx16;
+    float* val;
+    const WorkItem* items;
+    const uint32_t* cta_item_ptr;
+    const uint32_t* panel_item_ptr;
+    int npanels;
+    uint32_t panel_rows;
+    int64_t gdim, seg_offset, nseg;
+    const uint32_t* slot_ptr;
+    const uint32_t* seg_ptr;
+    float2* partials;
+    int lanes;                           // finalize: 1 thread or 32 lanes per segment
+    // multi-GPU exchange of the vector this side solves (nullptr: single GPU)
+    unsigned long long* const* peer_ll;  // [nranks] LL receive buffers of every rank for the solved factor matrix
+    const unsigned long long* ll;        // this rank's receive buffer
+    int64_t dim;                         // full length of the solved vector
+};
+struct PersistArgs {
+    PersistSide csc, csr;
+    float *W, *H, *v_old;
+    int64_t ldm, ldn;
+    int k, T;
+    int add;        // 1 from the second outer iteration on (src/CCD.cpp:100)
+    int pending;    // rank whose subtraction is deferred at entry (-1: none)
+    float lambda;
+    int nmf;
+    unsigned* bar;        // grid barrier counter (monotonic)
+    unsigned bar_base;    // its value before this launch
+    unsigned* status;     // 0 = ok; set by a wait that timed out
+    int rank, nranks;
+    unsigned epoch_base;  // exchange epoch before this launch (phase n uses epoch_base + n)
+    unsigned long long* stamps;  // nullptr, or [1 + 2kT] %globaltimer at kernel start and after every phase
+};
+// smem: dynamic shared memory (the largest panel footprint of any phase).  Returns MF_ERR_UNSUPPORTED when the grid
+// cannot be co-resident / cooperative launch is unavailable (the caller then uses the per-launch path).
+int ccd_persistent_launch(const PersistArgs& a, int ncta, size_t smem, cudaStream_t st);
+bool ccd_persistent_supported(int ncta, size_t smem, int device);
+
 struct DirectSweepArgs {
     int64_t nseg;
     const uint32_t* ptr;
@@ -75,6 +115,7 @@ struct DirectSweepArgs {
 };
 
 int panel_timeout_report(char* buf, size_t n);  // 1 + message when a pipeline wait timed out since the last call
+int panel_sweep_threads();  // threads per CTA of the register-ring sweep kernels (per-launch and persistent)
 int panel_sweep_vectors(int mode);
 size_t panel_sweep_smem(int mode, int panel_rows);
 int panel_sweep(int mode, const PanelSweepArgs& a, int ncta, int threads, int chunk, int pipeline, cudaStream_t st);

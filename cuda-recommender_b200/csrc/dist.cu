@@ -238,6 +238,7 @@ float* const* dist_peer_H(const Dist* d) { return d->d_peerH; }
 unsigned* const* dist_peer_flags(const Dist* d) { return d->d_peerFlags; }
 unsigned* dist_flags(const Dist* d) { return d->flags; }
 unsigned dist_next_epoch(Dist* d) { return ++d->epoch; }
+unsigned dist_advance_epoch(Dist* d, unsigned n) { const unsigned e = d->epoch; d->epoch += n; return e; }
 unsigned long long* const* dist_peer_ll(const Dist* d, bool h) { return h ? d->d_peerLLH : d->d_peerLLW; }
 unsigned long long* dist_ll(const Dist* d, bool h) { return h ? d->llH : d->llW; }
 

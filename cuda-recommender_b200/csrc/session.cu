@@ -62,7 +62,6 @@ void FamilyTimer::destroy() {
 
 namespace {
 
-constexpr int kThreads = 1024;
 constexpr size_t kSmemMax = 227 * 1024 - 256;
 
 int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
@@ -182,7 +181,7 @@ int run_sweep(mf_session* s, Side& sd, int mode, const SweepVectors& v, float* o
         }
         if (sd.nitems > 0) {
             s->timer.start(family_of(mode));
-            MF_TRY(panel_sweep(mode, a, sd.ncta, kThreads, sd.chunk, s->prm.pipeline, s->st));
+            MF_TRY(panel_sweep(mode, a, sd.ncta, s->prm.pipeline == MF_PIPELINE_REGISTERS ? panel_sweep_threads() : 1024, sd.chunk, s->prm.pipeline, s->st));
             s->timer.stop();
         }
         if (solve) {
@@ -303,6 +302,87 @@ int ccd_rank_fused(mf_session* s, int t, bool add) {
     MF_CUDA(cudaMemcpyAsync(s->v_old + (int64_t)t * s->ldn, v, sizeof(float) * (size_t)s->ldn, cudaMemcpyDeviceToDevice, s->st));
     s->pending = t;
     return MF_OK;
+}
+
+// Device view of one side for the persistent kernel.
+PersistSide persist_side(mf_session* s, const Side& sd, bool solves_h) {
+    PersistSide p;
+    p.idx16 = sd.idx16; p.val = sd.pval; p.items = sd.items; p.cta_item_ptr = sd.cta_item_ptr; p.panel_item_ptr = sd.panel_item_ptr;
+    p.npanels = sd.npanels; p.panel_rows = (uint32_t)sd.panel_rows; p.gdim = sd.gdim; p.seg_offset = sd.seg_offset; p.nseg = sd.nseg;
+    p.slot_ptr = sd.slot_ptr; p.seg_ptr = sd.ptr; p.partials = sd.partials;
+    p.lanes = panel_finalize_lanes(sd.nseg, sd.nslots);
+    const bool push = fused_exchange(s);
+    p.peer_ll = push ? dist_peer_ll(s->dist, solves_h) : nullptr;
+    p.ll = push ? dist_ll(s->dist, solves_h) : nullptr;
+    p.dim = solves_h ? s->cols : s->rows;
+    return p;
+}
+
+// May this session run an outer iteration as one persistent launch?  (panel layout, fused schedule, register-ring
+// pipeline, co-resident grid with cooperative launch, and — multi-GPU — the peer-to-peer exchange)
+bool use_persistent(const mf_session* s) {
+    return s->persistent && s->panel && s->prm.schedule == MF_SCHEDULE_FUSED && s->prm.pipeline == MF_PIPELINE_REGISTERS &&
+           s->prm.maxinneriter >= 1 && (s->nranks == 1 || fused_exchange(s));
+}
+
+// one whole outer iteration (k ranks, fused schedule) as ONE cooperative launch — replaces the loop of
+// cuda_src/CCD_CUDA.cu:339-378.  Phase time stamps (%globaltimer at the grid barriers) feed the per-family times.
+int ccd_outer_persistent(mf_session* s, bool add, bool timing) {
+    const int k = s->k, T = s->prm.maxinneriter;
+    const unsigned nphase = (unsigned)(2 * k * T);
+    PersistArgs a;
+    a.csc = persist_side(s, s->csc, true);
+    a.csr = persist_side(s, s->csr, false);
+    a.W = s->W; a.H = s->H; a.v_old = s->v_old; a.ldm = s->ldm; a.ldn = s->ldn;
+    a.k = k; a.T = T; a.add = add ? 1 : 0; a.pending = s->pending;
+    a.lambda = s->prm.lambda; a.nmf = s->prm.nmf_project;
+    a.bar = s->d_gridbar; a.bar_base = s->gridbar_total; a.status = s->d_gridbar + 1;
+    a.rank = s->rank; a.nranks = s->nranks;
+    a.epoch_base = fused_exchange(s) ? dist_advance_epoch(s->dist, nphase) : 0u;
+    a.stamps = nullptr;
+    if (timing) {
+        if (!s->d_stamps) MF_TRY(dev_alloc(&s->d_stamps, (size_t)nphase + 1));
+        a.stamps = s->d_stamps;
+    }
+    const int ncta = s->csc.ncta;
+    s->timer.start(F_PERSIST);
+    MF_TRY(ccd_persistent_launch(a, ncta, s->persist_smem, s->st));
+    s->timer.stop();
+    s->gridbar_total += 2u * nphase * (unsigned)ncta;  // two grid barriers per phase (advanced only after a successful launch)
+    s->pending = k - 1;
+    if (timing) {
+        s->h_stamps.resize((size_t)nphase + 1);
+        MF_CUDA(cudaMemcpyAsync(s->h_stamps.data(), s->d_stamps, sizeof(unsigned long long) * ((size_t)nphase + 1), cudaMemcpyDeviceToHost, s->st));
+    }
+    return MF_OK;
+}
+
+// folds the phase stamps of the last persistent launch into the per-family times (call after the stream is synchronised)
+void fold_stamps(mf_session* s, bool add, bool had_pending) {
+    const int k = s->k, T = s->prm.maxinneriter;
+    if (s->h_stamps.size() != (size_t)(2 * k * T + 1)) return;
+    size_t n = 0;
+    for (int t = 0; t < k; ++t)
+        for (int it = 0; it < T; ++it)
+            for (int side = 0; side < 2; ++side, ++n) {
+                const bool fused = it == 0 && (add || t > 0 || had_pending);
+                const int fam = fused ? F_FUSED : F_SOLVE;
+                s->fam_seconds[fam] += (double)(s->h_stamps[n + 1] - s->h_stamps[n]) * 1e-9;
+                s->fam_launches[fam] += 1;
+            }
+    s->h_stamps.clear();
+}
+
+// after a synchronisation: did a device-side wait time out?  (persistent kernel; status word next to the barrier counter)
+int check_device_status(mf_session* s) {
+    if (!s->persistent) return MF_OK;
+    unsigned st = 0;
+    MF_CUDA(cudaMemcpy(&st, s->d_gridbar + 1, sizeof(unsigned), cudaMemcpyDeviceToHost));
+    if (st == 0) return MF_OK;
+    s->broken = true;
+    set_error("device-side wait timed out (%s): another kernel held SMs of this device, or a peer rank stopped; the session is unusable",
+              st == 1 ? "grid barrier" : "multi-GPU exchange");
+    return MF_ERR_STATE;
 }
 
 // the reference's launch order: add-back, T x (v-solve, u-solve), subtract — CCD_CUDA.cu:347-378
@@ -515,11 +595,18 @@ int create_impl(const mf_ratings* R, const mf_testset* T, const mf_params* param
     }
     trace_mark("  test set");
     if ((rc = dev_alloc(&s->d_acc, rmse_scratch_doubles(s->sm_count))) != MF_OK) return fail(rc);
-    if ((rc = dev_alloc(&s->d_gridbar, 1)) != MF_OK) return fail(rc);
-    if (cudaMemsetAsync(s->d_gridbar, 0, sizeof(unsigned), s->st) != cudaSuccess) { set_error("cudaMemsetAsync failed: %s", cudaGetErrorString(cudaGetLastError())); return fail(MF_ERR_CUDA); }
+    if ((rc = dev_alloc(&s->d_gridbar, 2)) != MF_OK) return fail(rc);
+    if (cudaMemsetAsync(s->d_gridbar, 0, 2 * sizeof(unsigned), s->st) != cudaSuccess) { set_error("cudaMemsetAsync failed: %s", cudaGetErrorString(cudaGetLastError())); return fail(MF_ERR_CUDA); }
     // finalize inside the sweep kernel needs every CTA of a sweep resident at once (grid barrier): checked, not assumed
     s->fin_in_kernel = getenv("MF_SEPARATE_FINALIZE") == nullptr && s->panel &&
-                       panel_sweep_grid_resident(std::max(s->csc.ncta, s->csr.ncta), kThreads, std::max(s->csc.panel_rows, s->csr.panel_rows), s->sm_count);
+                       panel_sweep_grid_resident(std::max(s->csc.ncta, s->csr.ncta), panel_sweep_threads(), std::max(s->csc.panel_rows, s->csr.panel_rows), s->sm_count);
+    // opt-in (MF_PERSISTENT=1): on one GPU the per-launch kernels are faster, because every phase of the persistent kernel
+    // runs with the shared-memory carve-out of the largest one (profiles/README.md, round 2)
+    if (ccd && s->panel && getenv("MF_PERSISTENT") != nullptr && atoi(getenv("MF_PERSISTENT")) != 0 && s->csc.ncta == s->csr.ncta) {
+        // the persistent kernel holds the largest panel footprint of any phase: CSC side up to 2 vectors, CSR side up to 3
+        s->persist_smem = std::max(panel_sweep_smem(kSolve | kSub | kAdd, s->csc.panel_rows), panel_sweep_smem(kSolve | kSub | kAdd | kAddSep, s->csr.panel_rows));
+        s->persistent = ccd_persistent_supported(s->csc.ncta, s->persist_smem, s->device);
+    }
     arena_bind(nullptr);
     if (nranks > 1) {
         if (!nccl_id) { set_error("multi-GPU session needs the shared ncclUniqueId"); return fail(MF_ERR_ARG); }
@@ -620,7 +707,7 @@ int mf_session_destroy(mf_session* s) {
     if (s->dist) dist_destroy(s->dist);
     side_free(s->csc);
     side_free(s->csr);
-    void* ptrs[] = {s->W, s->H, s->v_old, s->trow, s->tcol, s->tval, s->d_acc, s->d_gridbar};
+    void* ptrs[] = {s->W, s->H, s->v_old, s->trow, s->tcol, s->tval, s->d_acc, s->d_gridbar, s->d_stamps};
     for (void* p : ptrs)
         if (p) dev_free(p);
     arena_destroy(s->arena);
@@ -737,17 +824,24 @@ int mf_session_ccdpp_iterate(mf_session* s, int n_outer, mf_iter_stats* stats) {
     for (int f = 0; f < F_COUNT; ++f) { s->fam_seconds[f] = 0; s->fam_launches[f] = 0; }
     s->timer.launched = 0;
     double total = 0.0;
-    if (!stats) {
+    if (s->broken) { set_error("session is unusable after a device-side timeout"); return MF_ERR_STATE; }
+    const bool persist = use_persistent(s);
+    auto one_outer = [&](bool add) -> int {
+        MF_TRY(exchange_barrier(s));
+        if (persist) return ccd_outer_persistent(s, add, timing_on);
+        for (int t = 0; t < s->k; ++t) {
+            s->timer.enabled = timing_on && (t % tstride == 0);
+            if (s->prm.schedule == MF_SCHEDULE_REFERENCE) MF_TRY(ccd_rank_reference(s, t, add));
+            else MF_TRY(ccd_rank_fused(s, t, add));
+        }
+        s->timer.enabled = timing_on;
+        return MF_OK;
+    };
+    if (!stats && !persist) {
         // no per-iteration report wanted: one event pair around all n_outer iterations, one sync
         MF_CUDA(cudaEventRecord(s->ev_a, s->st));
         for (int it = 0; it < n_outer; ++it) {
-            const bool add = s->outer_done > 0;
-            MF_TRY(exchange_barrier(s));
-            for (int t = 0; t < s->k; ++t) {
-                s->timer.enabled = timing_on && (t % tstride == 0);
-                if (s->prm.schedule == MF_SCHEDULE_REFERENCE) MF_TRY(ccd_rank_reference(s, t, add));
-                else MF_TRY(ccd_rank_fused(s, t, add));
-            }
+            MF_TRY(one_outer(s->outer_done > 0));
             s->outer_done++;
         }
         MF_CUDA(cudaEventRecord(s->ev_b, s->st));
@@ -765,16 +859,11 @@ int mf_session_ccdpp_iterate(mf_session* s, int n_outer, mf_iter_stats* stats) {
     }
     for (int it = 0; it < n_outer; ++it) {
         const bool add = s->outer_done > 0;  // src/CCD.cpp:100: add-back only from the second outer iteration on
+        const bool had_pending = s->pending >= 0;
         double before[F_COUNT];
         memcpy(before, s->fam_seconds, sizeof(before));
         MF_CUDA(cudaEventRecord(s->ev_a, s->st));
-        MF_TRY(exchange_barrier(s));
-        for (int t = 0; t < s->k; ++t) {
-            s->timer.enabled = timing_on && (t % tstride == 0);
-            if (s->prm.schedule == MF_SCHEDULE_REFERENCE) MF_TRY(ccd_rank_reference(s, t, add));
-            else MF_TRY(ccd_rank_fused(s, t, add));
-        }
-        s->timer.enabled = timing_on;
+        MF_TRY(one_outer(add));
         MF_CUDA(cudaEventRecord(s->ev_b, s->st));
         MF_CUDA(cudaStreamSynchronize(s->st));
         float ms = 0.f;
@@ -782,6 +871,10 @@ int mf_session_ccdpp_iterate(mf_session* s, int n_outer, mf_iter_stats* stats) {
         total += ms * 1e-3;
         s->outer_done++;
         s->timer.collect(s->fam_seconds, s->fam_launches);
+        if (persist) {
+            MF_TRY(check_device_status(s));
+            if (timing_on) fold_stamps(s, add, had_pending);
+        }
         if (stats) {
             mf_iter_stats& o = stats[it];
             const double upd = s->fam_seconds[F_UPDATE] - before[F_UPDATE];
@@ -888,6 +981,13 @@ int mf_session_kernel_times(mf_session* s, mf_kernel_times* out) {
         out->update_bytes = (sweep_bytes(s, s->csc, kSub) + sweep_bytes(s, s->csr, kSub)) / 2;
     }
     out->total_launches = s->timer.launched;
+    out->persistent_s = s->fam_seconds[F_PERSIST]; out->persistent_launches = s->fam_launches[F_PERSIST];
+    if (s->prm.solver_type == MF_SOLVER_CCD && s->prm.maxinneriter >= 1) {
+        // one persistent launch = k ranks x [fused CSC, fused CSR, (T-1) x (solve CSC, solve CSR)]
+        const int64_t T = s->prm.maxinneriter;
+        out->persistent_bytes = (int64_t)s->k * (sweep_bytes(s, s->csc, kSolve | kSub | kAdd) + sweep_bytes(s, s->csr, kSolve | kSub | kAdd | kAddSep) +
+                                                (T - 1) * (sweep_bytes(s, s->csc, kSolve) + sweep_bytes(s, s->csr, kSolve)));
+    }
     return MF_OK;
 }
 

@@ -7,7 +7,7 @@
 
 namespace mf {
 
-enum Family { F_SOLVE = 0, F_FUSED, F_UPDATE, F_FINALIZE, F_ALS, F_RMSE, F_COLLECTIVE, F_COUNT };
+enum Family { F_SOLVE = 0, F_FUSED, F_UPDATE, F_FINALIZE, F_ALS, F_RMSE, F_COLLECTIVE, F_PERSIST, F_COUNT };
 
 // CUDA-event stopwatch per kernel family, on the session stream.  Events are pooled; durations are
 // read back after the stream has been synchronised (collect()).
@@ -51,9 +51,14 @@ struct mf_session {
     uint32_t *trow = nullptr, *tcol = nullptr;
     float* tval = nullptr;
     double* d_acc = nullptr;
-    unsigned* d_gridbar = nullptr;  // grid barrier counter of the in-kernel finalize (monotonic; gridbar_total = expected value)
+    unsigned* d_gridbar = nullptr;  // [0] grid barrier counter of the in-kernel finalize (monotonic; gridbar_total = expected value), [1] status word
     unsigned gridbar_total = 0;
     bool fin_in_kernel = true;
+    bool persistent = false;        // one cooperative launch per outer iteration (ccd_kernels.cu: k_ccd_persistent)
+    size_t persist_smem = 0;
+    unsigned long long* d_stamps = nullptr;  // [1 + 2kT] phase time stamps of the last persistent launch
+    std::vector<unsigned long long> h_stamps;
+    bool broken = false;            // a device-side wait timed out: the session refuses further work
     int outer_done = 0;
     int pending = -1;  // rank whose subtraction from the residual is still deferred (fused schedule)
     mf::FamilyTimer timer;
@@ -81,6 +86,7 @@ float* const* dist_peer_H(const Dist* d);
 unsigned* const* dist_peer_flags(const Dist* d);
 unsigned* dist_flags(const Dist* d);
 unsigned dist_next_epoch(Dist* d);
+unsigned dist_advance_epoch(Dist* d, unsigned n);  // returns the epoch before; the next n epochs belong to the caller
 // in-place all-gather of a full-length vector whose block r = [bound[r], bound[r+1]) was produced by rank r
 int dist_allgather_blocks(Dist* d, float* vec, const std::vector<int64_t>& bound, int64_t elems_per_unit, cudaStream_t st);
 int dist_allreduce_sum_double(Dist* d, double* dev_value, cudaStream_t st);

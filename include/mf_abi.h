@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define MF_ABI_VERSION 1
+#define MF_ABI_VERSION 2
 
 enum {
     MF_OK = 0,
@@ -125,6 +125,10 @@ typedef struct mf_kernel_times {
     double collective_s;   int64_t collective_launches;   /* NCCL all-gathers (multi-GPU)         */
     int64_t solve_bytes, fused_bytes, update_bytes;       /* HBM bytes one launch of the family must move */
     int64_t total_launches;  /* every kernel launched by the last iterate call, timed or not (sweeps, finalize, ALS, RMSE) */
+    /* CCD++ persistent kernel (one cooperative launch per outer iteration; solve_* / fused_* then hold the in-kernel
+     * phase times, %globaltimer stamps at the grid barriers, and *_launches count phases) */
+    double persistent_s;   int64_t persistent_launches;   /* CUDA events around the launches                           */
+    int64_t persistent_bytes;                              /* HBM bytes one launch must move: all 2kT phases             */
 } mf_kernel_times;
 
 typedef struct mf_session mf_session;

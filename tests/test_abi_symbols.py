@@ -21,7 +21,7 @@ def test_header_library_and_binding_agree(pkg):
     for name in declared:
         assert hasattr(lib, name), f"libmfb200.so does not export {name}"
     assert sorted(pkg.ABI_SYMBOLS) == declared
-    assert lib.mf_abi_version() == 1
+    assert lib.mf_abi_version() == 2
 
 
 def test_params_default_matches_reference_defaults(pkg):
@@ -38,7 +38,7 @@ def test_struct_sizes_match_header_layout(pkg):
     assert C.sizeof(pkg.mf_testset) == 8 + 3 * 8
     assert C.sizeof(pkg.mf_params) == 4 * 28
     assert C.sizeof(pkg.mf_iter_stats) == 32
-    assert C.sizeof(pkg.mf_kernel_times) == 14 * 8 + 4 * 8
+    assert C.sizeof(pkg.mf_kernel_times) == 14 * 8 + 4 * 8 + 3 * 8
 
 
 def test_no_cpu_fallback_without_gpu(pkg, data_factory):

@@ -245,3 +245,29 @@ def test_nmf_projection_extension(gpu, port, data_factory):
     assert (W < 0).any() or (H < 0).any()
     assert (Wn >= 0).all() and (Hn >= 0).all() and np.isfinite(r1)
     assert not np.array_equal(Wn, W)
+
+
+@pytest.mark.parametrize("shape,kw", [("ml100k", dict()), ("ml100k", dict(panel_rows=256, chunk=64)), ("small", dict(panel_rows=64, chunk=16)), ("tiny", dict())])
+@pytest.mark.parametrize("k,inner", [(5, 3), (1, 2), (3, 1)])
+def test_persistent_kernel_equals_per_launch_path_bitwise(gpu, port, data_factory, monkeypatch, shape, kw, k, inner):
+    """One cooperative launch per outer iteration (k_ccd_persistent) runs the same sweep body and the same finalize as the
+    per-launch kernels: identical factors, residual and RMSE, bit for bit, over several outer iterations (first iteration
+    without add-back, k = 1 where the subtracted rank is the rank being solved, T = 1 where the v_old copy shares a phase
+    with its last reader)."""
+    d = data_factory(shape)
+    W0 = port.initial_col(k, d["rows"])
+    outs = []
+    for no_persistent in (False, True):
+        if no_persistent:
+            monkeypatch.delenv("MF_PERSISTENT", raising=False)
+        else:
+            monkeypatch.setenv("MF_PERSISTENT", "1")
+        with gpu.Session(d, gpu.make_params(k=k, lam=0.05, maxinner=inner, **kw)) as s:
+            s.set_factors(W0)
+            st = s.iterate(2)
+            st += s.iterate(2)
+            kt = s.kernel_times()
+            assert (kt["persistent_launches"] > 0) == (not no_persistent)
+            outs.append(s.get_factors() + s.get_values() + (np.array([x["rmse"] for x in st]),))
+    for a, b in zip(*outs):
+        assert np.array_equal(a, b)
