@@ -74,7 +74,7 @@ def parse_args():
     ap.add_argument("--panel-rows", type=int, default=0)
     ap.add_argument("--chunk", type=int, default=0)
     ap.add_argument("--pad", type=int, default=0)
-    ap.add_argument("--pipeline", default="registers", choices=["registers", "async", "tma"])
+    ap.add_argument("--pipeline", default="registers", choices=["registers", "async", "tma", "stream"])
     ap.add_argument("--timing-stride", type=int, default=8, help="per-launch CUDA events on every n-th rank only")
     return ap.parse_args()
 
@@ -356,7 +356,7 @@ def run_leg(ctx, pkg, dg, args, workload, headline):
                              schedule=pkg.SCHEDULE_REFERENCE if args.schedule == "reference" else pkg.SCHEDULE_FUSED,
                              layout=pkg.LAYOUT_DIRECT if args.layout == "direct" else pkg.LAYOUT_PANEL,
                              panel_rows=args.panel_rows, chunk=args.chunk, no_launch_timing=int(args.no_launch_timing),
-                             pipeline={"registers": 0, "async": 1, "tma": 2}[args.pipeline], timing_stride=args.timing_stride, pad_entries=args.pad)
+                             pipeline={"registers": 0, "async": 1, "tma": 2, "stream": 3}[args.pipeline], timing_stride=args.timing_stride, pad_entries=args.pad)
     nccl_id = ctx.shared_nccl_id(pkg)
 
     # factors exactly as the reference seeds them (tools.cpp:165-173): libc srand(0)/rand()

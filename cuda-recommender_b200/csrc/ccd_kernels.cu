@@ -162,6 +162,8 @@ struct LaunchView {
     __device__ __forceinline__ const float* s_add() const { return a.s_add; }
     __device__ __forceinline__ const float* s_old() const { return a.s_old; }
     __device__ __forceinline__ float2* partials() const { return a.partials; }
+    __device__ __forceinline__ uint32_t pf_dist() const { return a.pf_dist; }
+    __device__ __forceinline__ uint32_t npad() const { return a.npad; }
 };
 
 // Streams the (up to four) items of a batch through the 8-lane groups of a warp: a lane owns 4 consecutive
@@ -342,6 +344,11 @@ __device__ __forceinline__ bool ll_unpack_entries(const unsigned long long* ll, 
     return ok;
 }
 
+// L2 prefetch of a stretch of the rating stream (TMA engine, no shared memory involved): `bytes` a multiple of 16
+__device__ __forceinline__ void l2_prefetch(const void* p, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
 // One CTA's share of a sweep: the work items [ib, ie) of the list, starting in panel p (the panel that holds item ib).
 // smem: the staged panel vectors; s_ctr: a shared-memory counter the warps pull batches from.
 template <int MODE, class Args>
@@ -396,6 +403,17 @@ __device__ __forceinline__ void sweep_cta_range(const Args& a, float* smem, unsi
 
                 const uint32_t len = d.y;
                 const uint32_t lane_off = 4u * (uint32_t)sl;     // this lane's 4 entries inside a 32-entry step
+                // The storage is in work-list order, so what this CTA will read pf_dist entries from now is simply this
+                // item's stretch shifted by pf_dist: one lane per item asks the L2 for it (the per-lane loads of the
+                // register ring then hit L2 instead of paying the DRAM latency under load).
+                if (a.pf_dist() != 0u && sl == 0 && len != 0u) {
+                    const uint32_t q = d.x + a.pf_dist();
+                    if (q < a.npad()) {
+                        const uint32_t n = q + len <= a.npad() ? len : a.npad() - q;  // multiples of 8 entries
+                        l2_prefetch(a.idx16() + q, n * 2u);
+                        l2_prefetch(a.val() + q, n * 4u);
+                    }
+                }
                 float s_add = 0.0f, s_old = 0.0f;
                 if (len != 0u) {
                     // L2 loads: the finalize of this very launch rewrites the vector s_add points into (after the grid
@@ -559,6 +577,8 @@ struct PersistView {
     __device__ __forceinline__ const float* s_add() const { return persist_shared().vec.s_add; }
     __device__ __forceinline__ const float* s_old() const { return persist_shared().vec.s_old; }
     __device__ __forceinline__ float2* partials() const { return sw().partials; }
+    __device__ __forceinline__ uint32_t pf_dist() const { return 0u; }
+    __device__ __forceinline__ uint32_t npad() const { return 0u; }
 };
 
 // Inlined into the phase loop.  Everything a sweep derives from the thread index is derived from `tid + zero`, where
@@ -1070,6 +1090,295 @@ __global__ void __launch_bounds__(1024, 1) k_panel_sweep_async(PanelSweepArgs a)
     }
 }
 
+// =============================================================================================
+// STREAM pipeline (MF_PIPELINE_STREAM): the ratings reach the SM as a few large TMA bulk copies instead of per-lane
+// loads.  The padded entries are stored in work-list order (layout.cuh), so the items [ib, ie) a CTA walks are ONE
+// contiguous stretch [cta_start_ptr[b], cta_start_ptr[b+1]) of the index and value arrays.  The first kFeeders warps
+// are producers (one issuing lane each): the stretch is cut into tiles of kTile entries, and tile t goes into stage
+// t % NST of a shared-memory ring with two cp.async.bulk copies (indices, values; completion counted in bytes on the
+// stage's `full` mbarrier), issued by producer warp t % kFeeders.  The kConsumerWarps other warps
+// consume the items (one item per warp at a time, 128-entry steps, a lane owns 4 consecutive entries) reading indices and
+// values from the ring: the HBM stream is decoupled from the arithmetic, the bytes in flight per SM are bounded by the
+// ring (up to 96 KB) instead of by registers x warps or by what L1 is left beside the staged panels, and an item need
+// not start on a 128-byte line any more (padding granularity 8 instead of 32 entries).
+//   full[s]      producer -> consumers: expect_tx + complete_tx of the two copies
+//   consumed[s]  entries of the stage's current tile already consumed; the warp that completes the tile resets
+//                it and arrives on empty[s] (count 1), which lets the producer refill the stage
+//   s_armed[s]   1 + the tile stage s is armed for: a consumer may only issue its parity wait on full[s] for tile t once
+//                t has been armed (a parity wait issued a whole ring round early would alias the previous round)
+// A ring of RING = NST * kTile entries is addressed with a mask (RING is a power of two); items never straddle more than
+// two tiles (chunk <= kTile) and a lane's 4 entries never straddle the wrap (everything is a multiple of 8 entries).
+// =============================================================================================
+// Consumer warps: few on purpose.  The entries of the items being processed (4 per warp) are pinned in the ring until
+// their tile has been consumed completely; with 31 consumer warps that window (124 items x ~150 entries) is larger than
+// the ring itself, nothing is prefetched and the kernel runs at half the speed of the register ring (measured, round 2).
+#ifndef MF_STREAM_WARPS
+#define MF_STREAM_WARPS 24
+#endif
+// Producer warps: several, one issuing lane each.  Measured (scripts/ubench/bulk_stream.cu, B200): one thread completes a
+// [wait empty, expect_tx, cp.async.bulk] round every ~280 ns whatever the copy size (2-8 KB), i.e. 6 KB tiles from one
+// producer are 21 GB/s per SM = 3.2 TB/s per GPU; the rounds of different warps overlap perfectly (4 warps: 48 GB/s per
+// SM = 7.1 TB/s, HBM-bound).
+// A stage must be served by the same producer warp in every ring round — a warp is never a round ahead of itself,
+// while another warp could be, and its parity wait on empty[s] would then alias an older phase (measured: 3 or 6
+// producers on a 16-stage ring corrupt the ring) — so the producer count is a power of two, capped by the stage count.
+#ifndef MF_STREAM_PRODUCERS
+#define MF_STREAM_PRODUCERS 4
+#endif
+namespace stream {
+constexpr uint32_t kTile = 1024;  // entries per stage: 2 KB of indices + 4 KB of values
+constexpr uint32_t kFeeders = MF_STREAM_PRODUCERS;
+constexpr uint32_t kConsumerWarps = MF_STREAM_WARPS;
+constexpr uint32_t kConsumers = 32u * kConsumerWarps;
+constexpr uint32_t kThreads = kConsumers + 32u * kFeeders;
+static_assert((kFeeders & (kFeeders - 1u)) == 0u && kFeeders >= 1u && kFeeders <= 16u, "producer warps: a power of two");
+static_assert(kThreads <= 1024u, "too many warps");
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kConsumers) : "memory"); }
+
+// One panel of a factor vector -> shared memory as ONE bulk copy issued by consumer thread 0 (completion on `bar`);
+// the copy moves the panel's valid entries rounded up to 4 (factor rows are padded to 32 entries, so it stays inside the
+// allocation); stage_panel_tail then zeroes everything from `cnt` to `stride`.
+__device__ __forceinline__ uint32_t stage_panel_bytes(uint32_t cnt) { return ((cnt + 3u) & ~3u) * 4u; }
+__device__ __forceinline__ void stage_panel_tail(float* __restrict__ sm, uint32_t cnt, uint32_t stride, uint32_t ctid) {
+    for (uint32_t i = cnt + ctid; i < stride; i += kConsumers) sm[i] = 0.0f;
+}
+}  // namespace stream
+
+template <int MODE>
+__global__ void __launch_bounds__(stream::kThreads, 1) k_panel_sweep_stream(PanelSweepArgs a) {
+    using namespace tma;
+    using namespace stream;
+    constexpr bool SUB = MODE & kSub, ADD = MODE & kAdd, SOLVE = MODE & kSolve, ADDSEP = MODE & kAddSep;
+    constexpr bool WRITE = SUB || ADD;
+    extern __shared__ __align__(128) unsigned char smraw[];
+    __shared__ volatile unsigned s_armed[16];  // per stage: 1 + the tile the stage is armed for (0: none yet)
+
+    const uint32_t RING = a.ring_entries, NST = RING / kTile, rmask = RING - 1u;
+    float* ring_v = reinterpret_cast<float*>(smraw);
+    uint16_t* ring_i = reinterpret_cast<uint16_t*>(smraw + (size_t)RING * 4u);
+    const uint32_t ring_v_u32 = smem_u32(ring_v), ring_i_u32 = smem_u32(ring_i);
+    const uint32_t full_u32 = ring_i_u32 + RING * 2u;     // full[s]  at full_u32 + 8*s
+    const uint32_t empty_u32 = full_u32 + NST * 8u;       // empty[s] at empty_u32 + 8*s
+    unsigned* consumed = reinterpret_cast<unsigned*>(smraw + (size_t)RING * 6u + (size_t)NST * 16u);
+    const uint32_t vec_bar = full_u32 + NST * 20u;        // completion of the staged factor panels (one phase per panel)
+    float* smem = reinterpret_cast<float*>(smraw + (((size_t)RING * 6u + (size_t)NST * 20u + 8u + 127u) & ~(size_t)127u));
+
+    const uint32_t PR = a.panel_rows;
+    const uint32_t stride = PR + 8;  // 8 zeroed floats behind each panel: the padding slot
+    constexpr bool NEEDNEW = SOLVE || (ADD && !ADDSEP);
+    float* sm_new = smem;
+    float* sm_add = smem;
+    float* sm_old = smem;
+    {
+        int n = 0;
+        if (NEEDNEW) { sm_new = smem + n * stride; ++n; }
+        if (ADD) { if (ADDSEP) { sm_add = smem + n * stride; ++n; } else sm_add = sm_new; }
+        if (SUB) { sm_old = smem + n * stride; ++n; }
+    }
+    const float* g_add = ADDSEP ? a.g_add : a.g_new;
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint4* __restrict__ items = reinterpret_cast<const uint4*>(a.items);
+
+    if (threadIdx.x == 0) {
+        for (uint32_t st = 0; st < NST; ++st) {
+            mbar_init(full_u32 + 8u * st, 1u);
+            mbar_init(empty_u32 + 8u * st, 1u);
+            consumed[st] = 0u;
+            s_armed[st] = 0u;
+        }
+        mbar_init(vec_bar, 1u);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    uint32_t ib = a.cta_item_ptr[blockIdx.x];
+    const uint32_t ie = a.cta_item_ptr[blockIdx.x + 1];
+    const uint32_t stream0 = a.cta_start_ptr[blockIdx.x], stream1 = a.cta_start_ptr[blockIdx.x + 1];
+    int p = first_panel(a.panel_item_ptr, a.npanels, ib);  // (contains a CTA-wide barrier: the mbarriers are initialised)
+    const uint32_t total = stream1 - stream0;
+
+    if (warp < (int)kFeeders) {
+        // ---------------- producers: warp w moves tiles w, w + kFeeders, ... ----------------
+        const uint32_t nfeed = kFeeders < NST ? kFeeders : NST;
+        if (lane == 0 && (uint32_t)warp < nfeed) {
+            const uint32_t ntiles = (total + kTile - 1u) / kTile;
+            for (uint32_t t = (uint32_t)warp; t < ntiles; t += nfeed) {
+                const uint32_t st = t & (NST - 1u), round = t / NST;
+                if (round > 0u) mbar_wait(empty_u32 + 8u * st, (round - 1u) & 1u);  // the stage's previous tile has been consumed
+                const uint32_t n = total - t * kTile < kTile ? total - t * kTile : kTile;
+                const uint32_t bar = full_u32 + 8u * st;
+                mbar_expect_tx(bar, n * 6u);
+                bulk_g2s(ring_i_u32 + st * kTile * 2u, a.idx16 + stream0 + t * kTile, n * 2u, bar);
+                bulk_g2s(ring_v_u32 + st * kTile * 4u, a.val + stream0 + t * kTile, n * 4u, bar);
+                __threadfence_block();
+                s_armed[st] = t + 1u;
+            }
+        }
+        __syncwarp();
+    } else {
+        // ---------------- consumers ----------------
+        const unsigned ctid = threadIdx.x - 32u * kFeeders;
+        uint32_t vec_phase = 0;
+        while (ib < ie && p < a.npanels) {
+            const uint32_t pend = a.panel_item_ptr[p + 1];
+            const uint32_t pe = ie < pend ? ie : pend;
+            if (pe > ib) {
+                consumer_sync();  // every consumer warp is done with the previous panel and counter
+                const int64_t base = (int64_t)p * PR;
+                const uint32_t cnt = (uint32_t)((a.gdim - base) < (int64_t)PR ? (a.gdim - base) : (int64_t)PR);
+                if (ctid == 0) {
+                    constexpr uint32_t nvec = (NEEDNEW ? 1u : 0u) + ((ADD && ADDSEP) ? 1u : 0u) + (SUB ? 1u : 0u);
+                    const uint32_t nb = stage_panel_bytes(cnt);
+                    // the generic-proxy reads of the previous panel (ordered by the barrier above) precede these async-proxy writes
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    mbar_expect_tx(vec_bar, nvec * nb);
+                    if (NEEDNEW) bulk_g2s(smem_u32(sm_new), a.g_new + base, nb, vec_bar);
+                    if (ADD && ADDSEP) bulk_g2s(smem_u32(sm_add), g_add + base, nb, vec_bar);
+                    if (SUB) bulk_g2s(smem_u32(sm_old), a.g_old + base, nb, vec_bar);
+                }
+                mbar_wait(vec_bar, vec_phase & 1u);
+                ++vec_phase;
+                if (NEEDNEW) stage_panel_tail(sm_new, cnt, stride, ctid);
+                if (ADD && ADDSEP) stage_panel_tail(sm_add, cnt, stride, ctid);
+                if (SUB) stage_panel_tail(sm_old, cnt, stride, ctid);
+                consumer_sync();
+
+                // One item per warp at a time (static round-robin over the consumer warps: neighbours in the list have
+                // nearly the same length).  What the consumers hold pinned in the ring is then kConsumerWarps items
+                // (~150 entries each) instead of four per warp: with 8-lane groups the pinned window was as large as the
+                // ring and nothing was prefetched (measured: the warps spent 40 % of their time waiting for tiles).
+                // Lane l owns entries 128 s + 4 l .. + 3 of step s; the item's sums are lane-serial over the steps, then an
+                // xor-butterfly over the 32 lanes: a fixed tree of the item alone (not the 8-lane tree of the other
+                // pipelines: results agree with them to rounding, not bit for bit).
+                // Descriptors are fetched kDepth items ahead, the per-segment scalars of the fused modes one item ahead; the
+                // item loop is unrolled kDepth times so that every load in flight has a register of its own (rotating the
+                // descriptors through moves makes each move wait for the load it copies: prefetch distance zero, measured).
+                constexpr uint32_t kDepth = 4;
+                const uint32_t cw = (uint32_t)warp - kFeeders;
+                const uint32_t lane_off = 4u * (uint32_t)lane;
+                uint4 dq[kDepth];  // {start, len, seg, slot}; len 0 = no item
+                float sa[kDepth], so[kDepth];
+                uint32_t i0 = ib + cw;
+#pragma unroll
+                for (uint32_t u = 0; u < kDepth; ++u) {
+                    dq[u] = make_uint4(0u, 0u, 0u, 0u);
+                    sa[u] = 0.0f; so[u] = 0.0f;
+                    if (i0 + u * kConsumerWarps < pe) dq[u] = __ldg(items + i0 + u * kConsumerWarps);
+                }
+                if (dq[0].y != 0u) {
+                    if (ADD) sa[0] = __ldcg(a.s_add + a.seg_offset + dq[0].z);
+                    if (SUB) so[0] = __ldcg(a.s_old + a.seg_offset + dq[0].z);
+                }
+                for (; i0 < pe; i0 += kDepth * kConsumerWarps) {
+#pragma unroll
+                    for (uint32_t u = 0; u < kDepth; ++u) {
+                        const uint4 d = dq[u];
+                        if (d.y == 0u) break;  // past the end of the range (warp-uniform)
+                        const float s_add = sa[u], s_old = so[u];
+                        dq[u] = make_uint4(0u, 0u, 0u, 0u);
+                        if (i0 + (u + kDepth) * kConsumerWarps < pe) dq[u] = __ldg(items + i0 + (u + kDepth) * kConsumerWarps);
+                        {
+                            const uint32_t n = (u + 1u) % kDepth;  // the next item's scalars (its descriptor arrived long ago)
+                            sa[n] = 0.0f; so[n] = 0.0f;
+                            if (dq[n].y != 0u) {
+                                if (ADD) sa[n] = __ldcg(a.s_add + a.seg_offset + dq[n].z);
+                                if (SUB) so[n] = __ldcg(a.s_old + a.seg_offset + dq[n].z);
+                            }
+                        }
+                        const uint32_t len = d.y;
+                        const uint32_t rel = d.x - stream0;
+                        const uint32_t t0 = rel / kTile, t1 = (rel + len - 1u) / kTile;
+                        {   // (a stage stays armed for tile t until t has been consumed completely — which includes this item)
+                            uint32_t spins = 0;
+                            while (s_armed[t0 & (NST - 1u)] != t0 + 1u)  // the producer has not armed the stage for this tile yet
+                                if (++spins > kSpinLimit) __trap();
+                            mbar_wait(full_u32 + 8u * (t0 & (NST - 1u)), (t0 / NST) & 1u);
+                            if (t1 != t0) {
+                                while (s_armed[t1 & (NST - 1u)] != t1 + 1u)
+                                    if (++spins > kSpinLimit) __trap();
+                                mbar_wait(full_u32 + 8u * (t1 & (NST - 1u)), (t1 / NST) & 1u);
+                            }
+                        }
+                        float* gval = a.val + d.x + lane_off;
+                        const uint32_t r0 = rel + lane_off;
+                        float g = 0.0f, h = 0.0f;
+#pragma unroll 1
+                        for (uint32_t o = 0; o < len; o += 128u) {
+                            if (o + lane_off < len) {
+                                const uint32_t pos = (r0 + o) & rmask;
+                                Step e;
+                                e.i = *reinterpret_cast<const uint2*>(ring_i + pos);
+                                e.v = *reinterpret_cast<const float4*>(ring_v + pos);
+                                calc4<MODE>(e, sm_new, sm_add, sm_old, s_add, s_old, g, h);
+                                if (WRITE) __stcs(reinterpret_cast<float4*>(gval + o), e.v);
+                            }
+                        }
+                        __syncwarp();  // every lane has read its entries out of the ring
+                        if (lane == 0) {
+                            // hand the entries back: the warp that completes a tile lets the producer refill the stage
+                            // (no fence: a warp's shared-memory loads and this atomic are processed in order, the __syncwarp
+                            // covers the other lanes, and a fence here would also wait for the descriptor loads in flight)
+                            const uint32_t in0 = (t0 + 1u) * kTile - rel < len ? (t0 + 1u) * kTile - rel : len;
+                            {
+                                const uint32_t st = t0 & (NST - 1u);
+                                const uint32_t tile_total = total - t0 * kTile < kTile ? total - t0 * kTile : kTile;
+                                if (atomicAdd(&consumed[st], in0) + in0 == tile_total) {
+                                    consumed[st] = 0u;
+                                    mbar_arrive(empty_u32 + 8u * st);
+                                }
+                            }
+                            if (t1 != t0) {
+                                const uint32_t st = t1 & (NST - 1u), in1 = len - in0;
+                                const uint32_t tile_total = total - t1 * kTile < kTile ? total - t1 * kTile : kTile;
+                                if (atomicAdd(&consumed[st], in1) + in1 == tile_total) {
+                                    consumed[st] = 0u;
+                                    mbar_arrive(empty_u32 + 8u * st);
+                                }
+                            }
+                        }
+                        if (SOLVE) {
+#pragma unroll
+                            for (int q = 1; q < 32; q <<= 1) {
+                                g += __shfl_xor_sync(kFull, g, q);
+                                h += __shfl_xor_sync(kFull, h, q);
+                            }
+                            if (lane == 0) a.partials[d.w] = make_float2(g, h);
+                        }
+                    }
+                }
+            }
+            ib = pe;
+            ++p;
+        }
+    }
+    if (SOLVE && a.fin.enabled) {
+        // grid-wide barrier (monotonic counter; every CTA of the launch is resident), then the CTAs share the segments
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            atomicAdd(a.fin.bar, 1u);
+            unsigned v, spins = 0;
+            unsigned long long t0 = 0;
+            for (;;) {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(a.fin.bar) : "memory");
+                if ((int)(v - a.fin.bar_target) >= 0) break;
+                if ((++spins & 0x3fffu) == 0u) {
+                    const unsigned long long now = global_ns();
+                    if (t0 == 0) t0 = now;
+                    if (now - t0 > kWaitLimitNs) __trap();
+                }
+            }
+        }
+        __syncthreads();
+        if (a.fin.lanes == 32)
+            finalize_segments<32>(a.fin.nseg, a.fin.slot_ptr, a.partials, a.fin.seg_ptr, a.fin.lambda, a.fin.nmf, a.fin.out,
+                                  a.fin.peer_ll, a.fin.vec_off, a.fin.rank, a.fin.nranks, a.fin.epoch);
+        else
+            finalize_segments<1>(a.fin.nseg, a.fin.slot_ptr, a.partials, a.fin.seg_ptr, a.fin.lambda, a.fin.nmf, a.fin.out,
+                                 a.fin.peer_ll, a.fin.vec_off, a.fin.rank, a.fin.nranks, a.fin.epoch);
+        if (a.fin.ll != nullptr) ll_unpack_entries(a.fin.ll, a.fin.vec, a.fin.dim, a.fin.own_lo, a.fin.own_hi, a.fin.epoch);
+    }
+}
+
 template <int LANES>
 __global__ void __launch_bounds__(256) k_finalize(int64_t nseg, const uint32_t* __restrict__ slot_ptr,
                                                   const float2* __restrict__ partials, const uint32_t* __restrict__ seg_ptr,
@@ -1200,6 +1509,17 @@ int launch_panel_async(const PanelSweepArgs& a, int ncta, int threads, size_t sm
 }
 
 template <int MODE>
+int launch_panel_stream(const PanelSweepArgs& a, int ncta, int threads, size_t smem, cudaStream_t st) {
+    static PerDeviceOnce once;
+    if (once.need()) {
+        MF_CUDA(cudaFuncSetAttribute(k_panel_sweep_stream<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 256));
+    }
+    k_panel_sweep_stream<MODE><<<ncta, stream::kThreads, smem, st>>>(a);
+    MF_CUDA(cudaGetLastError());
+    return MF_OK;
+}
+
+template <int MODE>
 int launch_direct(const DirectSweepArgs& a, int sm_count, cudaStream_t st) {
     int64_t blocks = (a.nseg + 7) / 8;
     int64_t cap = (int64_t)sm_count * 32;
@@ -1260,6 +1580,18 @@ size_t panel_sweep_smem(int mode, int panel_rows) {
     return (size_t)panel_sweep_vectors(mode) * (size_t)(panel_rows + 8) * sizeof(float);
 }
 
+// STREAM pipeline: the ring gets what the staged vectors leave: the largest power of two of entries (6 bytes each), at
+// most 16 tiles, at least 2 tiles and at least two work items
+static size_t stream_overhead(uint32_t ring) { return ((size_t)ring * 6u + (size_t)(ring / stream::kTile) * 20u + 8u + 127u) & ~(size_t)127u; }
+uint32_t panel_stream_ring(int mode, int panel_rows, int chunk) {
+    const size_t cap = 227 * 1024 - 256, vec = panel_sweep_smem(mode, panel_rows);
+    if (chunk > (int)stream::kTile) return 0;
+    for (uint32_t ring = 16u * stream::kTile; ring >= 2u * stream::kTile; ring >>= 1)
+        if (stream_overhead(ring) + vec <= cap) return ring;
+    return 0;
+}
+size_t panel_stream_smem(int mode, int panel_rows, uint32_t ring) { return stream_overhead(ring) + panel_sweep_smem(mode, panel_rows); }
+
 int panel_sweep(int mode, const PanelSweepArgs& a_in, int ncta, int threads, int chunk, int pipeline, cudaStream_t st) {
     PanelSweepArgs a = a_in;
     const size_t vec = panel_sweep_smem(mode, (int)a.panel_rows);
@@ -1268,17 +1600,6 @@ int panel_sweep(int mode, const PanelSweepArgs& a_in, int ncta, int threads, int
         set_error("panel sweep mode %d needs %zu bytes of shared memory (panel_rows=%u)", mode, vec, a.panel_rows);
         return MF_ERR_ARG;
     }
-    if (pipeline != MF_PIPELINE_REGISTERS && chunk <= (int)tma::kChunkMax) {  // experimental slot-ring pipelines
-        // the slot ring gets whatever shared memory the panel vectors leave (at most 64 slots); per slot: data, two
-        // mbarriers, one round word
-        const size_t vec_al = (vec + 127) & ~(size_t)127;
-        const size_t per_slot = tma::kSlotBytes + 16 + 4;
-        size_t ns = (cap - vec_al) / per_slot;
-        if (ns > 64) ns = 64;
-        if (ns >= 40) {  // fewer slots could deadlock the producers against their own un-signalled batches
-            a.nslots = (uint32_t)ns;
-            a.fin.enabled = 0;
-            const size_t smem = vec_al + ns * per_slot;
 #define MF_DISPATCH(LAUNCH)                                                                                         \
     switch (mode) {                                                                                                 \
         case kSolve: return LAUNCH<kSolve>(a, ncta, threads, smem, st);                                             \
@@ -1291,11 +1612,32 @@ int panel_sweep(int mode, const PanelSweepArgs& a_in, int ncta, int threads, int
         case kSub | kAdd | kAddSep | kSolve: return LAUNCH<kSub | kAdd | kAddSep | kSolve>(a, ncta, threads, smem, st); \
         default: set_error("panel sweep: unsupported mode %d", mode); return MF_ERR_ARG;                            \
     }
+    if (pipeline == MF_PIPELINE_STREAM) {
+        const uint32_t ring = panel_stream_ring(mode, (int)a.panel_rows, chunk);
+        if (ring == 0) {
+            set_error("stream pipeline: no room for the ring beside %d staged vectors of %u entries (chunk %d)", panel_sweep_vectors(mode), a.panel_rows, chunk);
+            return MF_ERR_ARG;
+        }
+        a.ring_entries = ring;
+        const size_t smem = panel_stream_smem(mode, (int)a.panel_rows, ring);
+        MF_DISPATCH(launch_panel_stream)
+    }
+    if (pipeline != MF_PIPELINE_REGISTERS && chunk <= (int)tma::kChunkMax) {  // experimental slot-ring pipelines
+        // the slot ring gets whatever shared memory the panel vectors leave (at most 64 slots); per slot: data, two
+        // mbarriers, one round word
+        const size_t vec_al = (vec + 127) & ~(size_t)127;
+        const size_t per_slot = tma::kSlotBytes + 16 + 4;
+        size_t ns = (cap - vec_al) / per_slot;
+        if (ns > 64) ns = 64;
+        if (ns >= 40) {  // fewer slots could deadlock the producers against their own un-signalled batches
+            a.nslots = (uint32_t)ns;
+            a.fin.enabled = 0;
+            const size_t smem = vec_al + ns * per_slot;
             if (pipeline == MF_PIPELINE_TMA_BULK) { MF_DISPATCH(launch_panel_tma) }
             MF_DISPATCH(launch_panel_async)
-#undef MF_DISPATCH
         }
     }
+#undef MF_DISPATCH
     const size_t smem = vec;
     switch (mode) {
         case kSolve: return launch_panel<kSolve>(a, ncta, threads, smem, st);

@@ -55,6 +55,10 @@ struct PanelSweepArgs {
     const float* s_old;   // per-segment factor of the rank being subtracted
     float2* partials;
     uint32_t nslots;      // TMA pipeline: shared-memory slots of the ring (set by panel_sweep)
+    const uint32_t* cta_start_ptr;  // STREAM pipeline: [ncta+1] first padded entry of every CTA's item range
+    uint32_t ring_entries;          // STREAM pipeline: entries of the shared-memory ring (set by panel_sweep)
+    uint32_t pf_dist;               // register ring: L2 prefetch distance in entries (0: off)
+    uint32_t npad;                  // padded entries of the copy
     SweepFinalize fin;    // register-ring pipeline only
 };
 
@@ -118,6 +122,8 @@ int panel_timeout_report(char* buf, size_t n);  // 1 + message when a pipeline w
 int panel_sweep_threads();  // threads per CTA of the register-ring sweep kernels (per-launch and persistent)
 int panel_sweep_vectors(int mode);
 size_t panel_sweep_smem(int mode, int panel_rows);
+uint32_t panel_stream_ring(int mode, int panel_rows, int chunk);  // STREAM pipeline: ring entries that fit beside the staged vectors (0: none)
+size_t panel_stream_smem(int mode, int panel_rows, uint32_t ring);
 int panel_sweep(int mode, const PanelSweepArgs& a, int ncta, int threads, int chunk, int pipeline, cudaStream_t st);
 // multi-GPU: the finalize kernel also sends the solved block to every peer (LL protocol) or, as a barrier, only
 // publishes the epoch in the peers' flag words

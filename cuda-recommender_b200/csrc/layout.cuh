@@ -11,10 +11,13 @@
 // PANEL layout (the B200 layout): the gather dimension is cut into panels of
 // `panel_rows` factor entries so that one panel of the factor vector sits in shared memory while
 // the ratings that reference it stream past.  Every segment is cut at the panel boundaries into
-// pieces (panel p, segment s); storage is panel-major, pieces in segment order inside a panel, each
-// piece padded to a multiple of `pad` entries (default 32: every item then starts on a 64-byte boundary of
-// the index array and a 128-byte boundary of the value array — measured −13 % on the outer iteration, the
-// streams of an 8-lane group stop straddling DRAM atoms and L2 sectors).  Indices are stored panel-local in 16 bits, pre-multiplied
+// pieces (panel p, segment s), each piece padded to a multiple of `pad` entries and cut into work items of at
+// most `chunk` entries; storage is in WORK-LIST order ("stream order"): panel-major, and inside a panel in the
+// degree-binned, dealt order of the work items (below), item i starting where items 0..i-1 end — so the items
+// a CTA walks are one contiguous stretch of the arrays, which the STREAM pipeline fetches with large TMA bulk
+// copies.  `pad`: 8 for the STREAM pipeline (alignment no longer matters: the bulk copies are contiguous);
+// 32 for the register-ring pipeline (every item then starts on a 64-byte boundary of the index array and a
+// 128-byte boundary of the value array — measured −13 % there).  Indices are stored panel-local in 16 bits, pre-multiplied
 // by 4 (the byte offset of the factor entry inside the staged panel, so panel_rows <= 16376); padding
 // entries carry the offset of a zeroed shared-memory slot (index panel_rows) and val = 0, so they add
 // nothing to g, h or the residual.
@@ -60,7 +63,9 @@ struct Side {
     uint32_t* slot_ptr = nullptr;     // [nseg+1]
     float2* partials = nullptr;       // [nslots]
     uint32_t* cta_item_ptr = nullptr; // [ncta+1] equal-cost contiguous item ranges
+    uint32_t* cta_start_ptr = nullptr; // [ncta+1] first padded entry of each range (= items[cta_item_ptr[j]].start; npad at the end)
     uint32_t* panel_item_ptr = nullptr; // [npanels+1]
+    uint32_t* item_perm = nullptr;      // [nitems] position in `items` of the j-th item in piece order (item_ptr numbering)
     int ncta = 0;
     bool sorted = true;
     // ALS work list (als.cu, built on first use): items sorted longest-first, long segments split into parts

@@ -54,13 +54,11 @@ __global__ void k_seg_items(int64_t nseg, int npanels, const uint32_t* __restric
     seg_items[s] = n;
 }
 
-// one warp per piece: copy + pad the entries, emit the work items
-__global__ void k_fill(int64_t nseg, int npanels, uint32_t panel_rows, uint32_t chunk,
-                       const uint32_t* __restrict__ ptr, const uint32_t* __restrict__ idx,
-                       const float* __restrict__ val, const uint32_t* __restrict__ piece_first,
-                       const uint32_t* __restrict__ piece_ptr, const uint32_t* __restrict__ item_ptr,
-                       const uint32_t* __restrict__ slot_ptr, uint16_t* __restrict__ idx16,
-                       float* __restrict__ pval, WorkItem* __restrict__ items, uint32_t* __restrict__ item_cost) {
+// one warp per piece: emit the piece's work items (provisional start = the piece-order position; the storage
+// position is assigned after the items have been put in work-list order, k_item_set_start)
+__global__ void k_items(int64_t nseg, int npanels, uint32_t chunk, const uint32_t* __restrict__ piece_ptr,
+                        const uint32_t* __restrict__ item_ptr, const uint32_t* __restrict__ slot_ptr,
+                        WorkItem* __restrict__ items, uint32_t* __restrict__ item_cost) {
     const int lane = threadIdx.x & 31;
     int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -71,16 +69,6 @@ __global__ void k_fill(int64_t nseg, int npanels, uint32_t panel_rows, uint32_t 
         if (pd == 0) continue;
         int p = (int)(q / nseg);
         int64_t s = q - (int64_t)p * nseg;
-        uint32_t src0 = piece_first[q];
-        uint32_t src1 = (p == npanels - 1) ? ptr[s + 1] : piece_first[q + nseg];
-        uint32_t cnt = src1 - src0;
-        uint32_t base = (uint32_t)p * panel_rows;
-        for (uint32_t e = lane; e < pd; e += 32) {
-            bool real = e < cnt;
-            // stored pre-multiplied by 4: the byte offset of the factor entry inside the shared-memory panel
-            idx16[dst0 + e] = (uint16_t)((real ? idx[src0 + e] - base : panel_rows) << 2);
-            pval[dst0 + e] = real ? val[src0 + e] : 0.0f;
-        }
         // slots of segment s are ordered (panel, chunk): count the items of the earlier panels
         uint32_t before = 0;
         for (int pp = lane; pp < p; pp += 32) {
@@ -100,6 +88,53 @@ __global__ void k_fill(int64_t nseg, int npanels, uint32_t panel_rows, uint32_t 
             w.slot = slot0 + j;
             items[it0 + j] = w;
             item_cost[it0 + j] = w.len / kPad + kCost0;
+        }
+    }
+}
+
+// STREAM order (layout.cuh): the padded entries are stored in WORK-LIST order — item i of the final list starts at
+// the sum of the lengths of the items before it — so that the range of items a CTA walks is one contiguous stretch of
+// the index and value arrays (fetched with a few large bulk copies instead of one gather per item).
+__global__ void k_item_len(int64_t nitems, const WorkItem* __restrict__ items, uint32_t* __restrict__ len) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nitems) len[i] = items[i].len;
+}
+__global__ void k_item_set_start(int64_t nitems, const uint32_t* __restrict__ start, WorkItem* __restrict__ items) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nitems) items[i].start = start[i];
+}
+
+// one warp per piece: copy + pad the entries of each of its work items to the item's place in the stream
+// (perm[original item] = position in the final list)
+__global__ void k_fill_entries(int64_t nseg, int npanels, uint32_t panel_rows, uint32_t chunk,
+                               const uint32_t* __restrict__ ptr, const uint32_t* __restrict__ idx,
+                               const float* __restrict__ val, const uint32_t* __restrict__ piece_first,
+                               const uint32_t* __restrict__ piece_ptr, const uint32_t* __restrict__ item_ptr,
+                               const uint32_t* __restrict__ perm, const WorkItem* __restrict__ items,
+                               uint16_t* __restrict__ idx16, float* __restrict__ pval) {
+    const int lane = threadIdx.x & 31;
+    int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    int64_t Q = nseg * npanels;
+    for (int64_t q = warp; q < Q; q += nwarps) {
+        uint32_t pd = piece_ptr[q + 1] - piece_ptr[q];
+        if (pd == 0) continue;
+        int p = (int)(q / nseg);
+        int64_t s = q - (int64_t)p * nseg;
+        uint32_t src0 = piece_first[q];
+        uint32_t src1 = (p == npanels - 1) ? ptr[s + 1] : piece_first[q + nseg];
+        uint32_t cnt = src1 - src0;
+        uint32_t base = (uint32_t)p * panel_rows;
+        uint32_t it0 = item_ptr[q], nit = item_ptr[q + 1] - it0;
+        for (uint32_t j = 0; j < nit; ++j) {
+            const uint32_t dst0 = items[perm[it0 + j]].start;
+            const uint32_t e0 = j * chunk, e1 = e0 + chunk < pd ? e0 + chunk : pd;
+            for (uint32_t e = e0 + lane; e < e1; e += 32) {
+                bool real = e < cnt;
+                // stored pre-multiplied by 4: the byte offset of the factor entry inside the shared-memory panel
+                idx16[dst0 + e - e0] = (uint16_t)((real ? idx[src0 + e] - base : panel_rows) << 2);
+                pval[dst0 + e - e0] = real ? val[src0 + e] : 0.0f;
+            }
         }
     }
 }
@@ -135,7 +170,8 @@ __global__ void k_item_bin_count(int64_t nitems, int npanels, uint32_t nbins, co
 }
 __global__ void k_item_bin_scatter(int64_t nitems, int npanels, uint32_t nbins, const uint32_t* __restrict__ panel_item_ptr,
                                    const WorkItem* __restrict__ items, const uint32_t* __restrict__ bin_ptr,
-                                   uint32_t* __restrict__ bin_cursor, WorkItem* __restrict__ sorted, uint32_t* __restrict__ cost) {
+                                   uint32_t* __restrict__ bin_cursor, WorkItem* __restrict__ sorted, uint32_t* __restrict__ cost,
+                                   uint32_t* __restrict__ perm) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nitems) return;
     const WorkItem w = items[i];
@@ -146,6 +182,7 @@ __global__ void k_item_bin_scatter(int64_t nitems, int npanels, uint32_t nbins, 
     const uint32_t dst = pbeg + deal_position(rank - pbeg, panel_item_ptr[p + 1] - pbeg);
     sorted[dst] = w;
     cost[dst] = w.len / kPad + kCost0;
+    perm[i] = dst;
 }
 
 __global__ void k_panel_item_ptr(int64_t nseg, int npanels, const uint32_t* __restrict__ item_ptr,
@@ -165,26 +202,42 @@ __global__ void k_cta_ranges(int ncta, int64_t nitems, const uint32_t* __restric
     cta_item_ptr[j] = lower_bound_u32(cost_prefix, 0, (uint32_t)nitems, target);
 }
 
-// one warp per piece: value copy between the panel order and the caller's order
+// first padded entry of every CTA's item range (STREAM pipeline: a CTA's items are one contiguous stretch)
+__global__ void k_cta_starts(int ncta, int64_t nitems, uint32_t npad, const uint32_t* __restrict__ cta_item_ptr,
+                             const WorkItem* __restrict__ items, uint32_t* __restrict__ cta_start_ptr) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j > ncta) return;
+    const uint32_t i = cta_item_ptr[j];
+    cta_start_ptr[j] = i < (uint32_t)nitems ? items[i].start : npad;
+}
+
+// one warp per piece: value copy between the stream order and the caller's order
 template <bool TO_RAW>
-__global__ void k_copy_values(int64_t nseg, int npanels, const uint32_t* __restrict__ ptr,
+__global__ void k_copy_values(int64_t nseg, int npanels, uint32_t chunk, const uint32_t* __restrict__ ptr,
                               const uint32_t* __restrict__ piece_first, const uint32_t* __restrict__ piece_ptr,
-                              float* __restrict__ pval, float* __restrict__ raw) {
+                              const uint32_t* __restrict__ item_ptr, const uint32_t* __restrict__ perm,
+                              const WorkItem* __restrict__ items, float* __restrict__ pval, float* __restrict__ raw) {
     const int lane = threadIdx.x & 31;
     int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     int64_t Q = nseg * npanels;
     for (int64_t q = warp; q < Q; q += nwarps) {
-        uint32_t dst0 = piece_ptr[q];
-        if (piece_ptr[q + 1] == dst0) continue;
+        if (piece_ptr[q + 1] == piece_ptr[q]) continue;
         int p = (int)(q / nseg);
         int64_t s = q - (int64_t)p * nseg;
         uint32_t src0 = piece_first[q];
         uint32_t src1 = (p == npanels - 1) ? ptr[s + 1] : piece_first[q + nseg];
         uint32_t cnt = src1 - src0;
-        for (uint32_t e = lane; e < cnt; e += 32) {
-            if (TO_RAW) raw[src0 + e] = pval[dst0 + e];
-            else pval[dst0 + e] = raw[src0 + e];
+        uint32_t it0 = item_ptr[q], nit = item_ptr[q + 1] - it0;
+        for (uint32_t j = 0; j < nit; ++j) {
+            const uint32_t e0 = j * chunk;
+            if (e0 >= cnt) break;
+            const uint32_t dst0 = items[perm[it0 + j]].start;
+            const uint32_t e1 = e0 + chunk < cnt ? e0 + chunk : cnt;
+            for (uint32_t e = e0 + lane; e < e1; e += 32) {
+                if (TO_RAW) raw[src0 + e] = pval[dst0 + e - e0];
+                else pval[dst0 + e - e0] = raw[src0 + e];
+            }
         }
     }
 }
@@ -245,7 +298,7 @@ inline unsigned grid_for(int64_t n, int block) { return (unsigned)((n + block - 
 
 int side_free(Side& s) {
     void* ptrs[] = {s.ptr, s.idx, s.val, s.piece_ptr, s.piece_first, s.item_ptr, s.idx16, s.pval, s.items,
-                    s.slot_ptr, s.partials, s.cta_item_ptr, s.panel_item_ptr, s.als_items, s.als_queue, s.als_counters, s.als_partial};
+                    s.slot_ptr, s.partials, s.cta_item_ptr, s.cta_start_ptr, s.panel_item_ptr, s.item_perm, s.als_items, s.als_queue, s.als_counters, s.als_partial};
     for (void* p : ptrs)
         if (p) dev_free(p);
     s = Side();
@@ -291,6 +344,7 @@ int side_build_panels(Side& s, int panel_rows, int chunk, int ncta, cudaStream_t
     MF_TRY(dev_alloc(&s.slot_ptr, (size_t)s.nseg + 1));
     MF_TRY(dev_alloc(&s.panel_item_ptr, (size_t)s.npanels + 1));
     MF_TRY(dev_alloc(&s.cta_item_ptr, (size_t)ncta + 1));
+    MF_TRY(dev_alloc(&s.cta_start_ptr, (size_t)ncta + 1));
     size_t tmp_n = scan_tmp_elems((size_t)(Q > s.nseg ? Q : s.nseg));
     MF_TRY(tmp_alloc(&tmp, tmp_n, st));
 
@@ -324,12 +378,9 @@ int side_build_panels(Side& s, int panel_rows, int chunk, int ncta, cudaStream_t
     MF_TRY(tmp_alloc(&cost, (size_t)s.nitems, st));
     MF_TRY(tmp_alloc(&cost_prefix, (size_t)s.nitems + 1, st));
     trace_mark("    layout: big allocations");
-    if (Q > 0) {
-        int64_t warps = Q < 148 * 64 * 8 ? Q : 148 * 64 * 8;
-        k_fill<<<grid_for(warps * 32, 256), 256, 0, st>>>(s.nseg, s.npanels, (uint32_t)panel_rows, (uint32_t)chunk, s.ptr,
-                                                         s.idx, s.val, s.piece_first, s.piece_ptr, s.item_ptr, s.slot_ptr,
-                                                         s.idx16, s.pval, s.items, cost);
-    }
+    const int64_t fill_warps = Q < 148 * 64 * 8 ? Q : 148 * 64 * 8;
+    if (Q > 0)
+        k_items<<<grid_for(fill_warps * 32, 256), 256, 0, st>>>(s.nseg, s.npanels, (uint32_t)chunk, s.piece_ptr, s.item_ptr, s.slot_ptr, s.items, cost);
     MF_CUDA(cudaGetLastError());
     k_panel_item_ptr<<<grid_for(s.npanels + 1, 128), 128, 0, st>>>(s.nseg, s.npanels, s.item_ptr, s.panel_item_ptr);
     MF_CUDA(cudaGetLastError());
@@ -343,21 +394,44 @@ int side_build_panels(Side& s, int panel_rows, int chunk, int ncta, cudaStream_t
         MF_TRY(tmp_alloc(&bin_ptr, nb + 1, st));
         MF_TRY(tmp_alloc(&tmp2, scan_tmp_elems(nb), st));
         MF_TRY(dev_alloc(&sorted, (size_t)s.nitems));
+        MF_TRY(dev_alloc(&s.item_perm, (size_t)s.nitems));
         MF_CUDA(cudaMemsetAsync(bin_count, 0, sizeof(uint32_t) * nb, st));
         k_item_bin_count<<<grid_for(s.nitems, 256), 256, 0, st>>>(s.nitems, s.npanels, nbins, s.panel_item_ptr, s.items, bin_count);
         MF_CUDA(cudaGetLastError());
         MF_TRY(exclusive_scan_u32(bin_count, bin_ptr, nb, tmp2, st));
         MF_CUDA(cudaMemsetAsync(bin_count, 0, sizeof(uint32_t) * nb, st));
         k_item_bin_scatter<<<grid_for(s.nitems, 256), 256, 0, st>>>(s.nitems, s.npanels, nbins, s.panel_item_ptr, s.items, bin_ptr,
-                                                                   bin_count, sorted, cost);
+                                                                   bin_count, sorted, cost, s.item_perm);
         MF_CUDA(cudaGetLastError());
         MF_CUDA(cudaStreamSynchronize(st));
         dev_free(s.items);
         s.items = sorted;
         tmp_free(bin_count, st); tmp_free(bin_ptr, st); tmp_free(tmp2, st);
+        // stream order: an item's entries start where the items before it in the list end
+        uint32_t *len = nullptr, *start = nullptr, *tmp3 = nullptr;
+        MF_TRY(tmp_alloc(&len, (size_t)s.nitems, st));
+        MF_TRY(tmp_alloc(&start, (size_t)s.nitems + 1, st));
+        MF_TRY(tmp_alloc(&tmp3, scan_tmp_elems((size_t)s.nitems), st));
+        k_item_len<<<grid_for(s.nitems, 256), 256, 0, st>>>(s.nitems, s.items, len);
+        MF_CUDA(cudaGetLastError());
+        MF_TRY(exclusive_scan_u32(len, start, (size_t)s.nitems, tmp3, st));
+        k_item_set_start<<<grid_for(s.nitems, 256), 256, 0, st>>>(s.nitems, start, s.items);
+        MF_CUDA(cudaGetLastError());
+        k_fill_entries<<<grid_for(fill_warps * 32, 256), 256, 0, st>>>(s.nseg, s.npanels, (uint32_t)panel_rows, (uint32_t)chunk, s.ptr, s.idx,
+                                                                      s.val, s.piece_first, s.piece_ptr, s.item_ptr, s.item_perm, s.items,
+                                                                      s.idx16, s.pval);
+        MF_CUDA(cudaGetLastError());
+        tmp_free(len, st); tmp_free(start, st); tmp_free(tmp3, st);
     }
-    MF_TRY(exclusive_scan_u32(cost, cost_prefix, (size_t)s.nitems, tmp, st));
+    {   // (the scratch of the piece scans is sized for Q elements; a copy with long pieces has more items than pieces)
+        uint32_t* tmp_cost = nullptr;
+        MF_TRY(tmp_alloc(&tmp_cost, scan_tmp_elems((size_t)s.nitems), st));
+        MF_TRY(exclusive_scan_u32(cost, cost_prefix, (size_t)s.nitems, tmp_cost, st));
+        tmp_free(tmp_cost, st);
+    }
     k_cta_ranges<<<grid_for(ncta + 1, 128), 128, 0, st>>>(ncta, s.nitems, cost_prefix, s.cta_item_ptr);
+    MF_CUDA(cudaGetLastError());
+    k_cta_starts<<<grid_for(ncta + 1, 128), 128, 0, st>>>(ncta, s.nitems, (uint32_t)s.npad, s.cta_item_ptr, s.items, s.cta_start_ptr);
     MF_CUDA(cudaGetLastError());
     MF_CUDA(cudaStreamSynchronize(st));
     trace_mark("    layout: fill + order + ranges");
@@ -369,8 +443,8 @@ int side_panel_to_raw(const Side& s, float* dst_raw, cudaStream_t st) {
     int64_t Q = s.nseg * s.npanels;
     if (Q == 0 || s.nnz == 0) return MF_OK;
     int64_t warps = Q < 148 * 64 * 8 ? Q : 148 * 64 * 8;
-    k_copy_values<true><<<grid_for(warps * 32, 256), 256, 0, st>>>(s.nseg, s.npanels, s.ptr, s.piece_first, s.piece_ptr,
-                                                                  s.pval, dst_raw);
+    k_copy_values<true><<<grid_for(warps * 32, 256), 256, 0, st>>>(s.nseg, s.npanels, (uint32_t)s.chunk, s.ptr, s.piece_first, s.piece_ptr,
+                                                                  s.item_ptr, s.item_perm, s.items, s.pval, dst_raw);
     MF_CUDA(cudaGetLastError());
     return MF_OK;
 }
@@ -379,8 +453,8 @@ int side_raw_to_panel(Side& s, const float* src_raw, cudaStream_t st) {
     int64_t Q = s.nseg * s.npanels;
     if (Q == 0 || s.nnz == 0) return MF_OK;
     int64_t warps = Q < 148 * 64 * 8 ? Q : 148 * 64 * 8;
-    k_copy_values<false><<<grid_for(warps * 32, 256), 256, 0, st>>>(s.nseg, s.npanels, s.ptr, s.piece_first, s.piece_ptr,
-                                                                   s.pval, const_cast<float*>(src_raw));
+    k_copy_values<false><<<grid_for(warps * 32, 256), 256, 0, st>>>(s.nseg, s.npanels, (uint32_t)s.chunk, s.ptr, s.piece_first, s.piece_ptr,
+                                                                   s.item_ptr, s.item_perm, s.items, s.pval, const_cast<float*>(src_raw));
     MF_CUDA(cudaGetLastError());
     return MF_OK;
 }

@@ -153,6 +153,8 @@ int run_sweep(mf_session* s, Side& sd, int mode, const SweepVectors& v, float* o
         a.g_new = v.g_new; a.g_add = v.g_add; a.g_old = v.g_old; a.s_add = v.s_add; a.s_old = v.s_old;
         a.partials = sd.partials;
         a.nslots = 0;
+        a.cta_start_ptr = sd.cta_start_ptr; a.ring_entries = 0;
+        a.pf_dist = s->pf_dist; a.npad = (uint32_t)sd.npad;
         a.fin.enabled = 0;
         const bool solve = (mode & kSolve) != 0;
         const bool is_h = push && out >= s->H && out < s->H + (int64_t)s->k * s->ldn;
@@ -165,7 +167,8 @@ int run_sweep(mf_session* s, Side& sd, int mode, const SweepVectors& v, float* o
             fp.rank = s->rank; fp.nranks = s->nranks; fp.epoch = dist_next_epoch(s->dist); fp.barrier = 0;
         }
         // finalize inside the sweep kernel (grid barrier, register-ring pipeline) unless switched off
-        const bool in_kernel = solve && sd.nitems > 0 && s->fin_in_kernel && s->prm.pipeline == MF_PIPELINE_REGISTERS;
+        const bool in_kernel = solve && sd.nitems > 0 && s->fin_in_kernel &&
+                               (s->prm.pipeline == MF_PIPELINE_REGISTERS || s->prm.pipeline == MF_PIPELINE_STREAM);
         if (in_kernel) {
             SweepFinalize& f = a.fin;
             f.enabled = 1;
@@ -450,6 +453,11 @@ int create_impl(const mf_ratings* R, const mf_testset* T, const mf_params* param
 
     mf_session* s = new mf_session();
     s->prm = *params;
+    if (const char* e = getenv("MF_L2_PREFETCH")) s->pf_dist = (uint32_t)(atoi(e) / 8 * 8);
+    if (const char* e = getenv("MF_PIPELINE")) {  // A/B switch for runs that do not set mf_params.pipeline themselves
+        if (!strcmp(e, "stream")) s->prm.pipeline = MF_PIPELINE_STREAM;
+        else if (!strcmp(e, "registers")) s->prm.pipeline = MF_PIPELINE_REGISTERS;
+    }
     s->device = params->device;
     s->rank = rank;
     s->nranks = nranks;
@@ -524,6 +532,8 @@ int create_impl(const mf_ratings* R, const mf_testset* T, const mf_params* param
             // almost no L1 for the rating streams and the updating sweeps slow down by 30-60 %; 12-16 K entries
             // (48-64 KB per vector) is the sweet spot on B200.  Hard cap 16376: idx16 stores index*4.
             int cap_c = std::min(panel_cap(2), 16376), cap_r = std::min(panel_cap(3), 16376);
+            // STREAM pipeline: the ring of rating tiles (16 K entries, 96 KB) lives beside the staged vectors
+            if (s->prm.pipeline == MF_PIPELINE_STREAM) cap_r = std::min(cap_r, 11112);
             const int want = params->panel_rows > 0 ? params->panel_rows / 8 * 8 : 16376;
             cap_c = std::min(cap_c, want);
             cap_r = std::min(cap_r, want);
@@ -534,6 +544,7 @@ int create_impl(const mf_ratings* R, const mf_testset* T, const mf_params* param
             // Yahoo-Music shape: ~6 entries per piece; measured 2.55 s -> 2.04 s per outer iteration with 16)
             auto pick_pad = [&](const Side& sd, int pr) {
                 if (params->pad_entries > 0) return (int)params->pad_entries;
+                if (s->prm.pipeline == MF_PIPELINE_STREAM) return 8;  // contiguous bulk copies: items need no line alignment
                 const int64_t npan = (sd.gdim + pr - 1) / pr;
                 const int64_t pieces = std::max<int64_t>(1, std::min<int64_t>(sd.nseg * npan, std::max<int64_t>(sd.nnz, 1)));
                 return sd.nnz / pieces < 24 ? 16 : 32;

@@ -56,6 +56,7 @@ struct mf_session {
     bool fin_in_kernel = true;
     bool persistent = false;        // one cooperative launch per outer iteration (ccd_kernels.cu: k_ccd_persistent)
     size_t persist_smem = 0;
+    uint32_t pf_dist = 0;  // register-ring sweeps: L2 prefetch distance in entries (0: off)
     unsigned long long* d_stamps = nullptr;  // [1 + 2kT] phase time stamps of the last persistent launch
     std::vector<unsigned long long> h_stamps;
     bool broken = false;            // a device-side wait timed out: the session refuses further work

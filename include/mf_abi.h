@@ -53,7 +53,7 @@ enum { MF_LAYOUT_PANEL = 0, MF_LAYOUT_DIRECT = 1 };          /* HBM layout of th
 /* how the panel sweep feeds its warps: a per-lane register ring (default, fastest measured), or —
  * kept for comparison — producer warps with cp.async / one bulk-copy (TMA) descriptor per work item into a
  * shared-memory slot ring guarded by mbarriers */
-enum { MF_PIPELINE_REGISTERS = 0, MF_PIPELINE_ASYNC = 1, MF_PIPELINE_TMA_BULK = 2 };
+enum { MF_PIPELINE_REGISTERS = 0, MF_PIPELINE_ASYNC = 1, MF_PIPELINE_TMA_BULK = 2, MF_PIPELINE_STREAM = 3 };
 enum { MF_SIDE_CSC = 0, MF_SIDE_CSR = 1 };                   /* CSC: columns solve v / H;  CSR: rows solve u / W */
 
 /* Paired CSR + CSC of the same ratings — src/pmf_util.h:34-149 (SparseMatrix). */

@@ -71,16 +71,29 @@ def panel_layout(ptr, idx, val, gdim, panel_rows, chunk, pad=32):
                 items=np.array(items, np.uint32).reshape(-1, 4), item_panel=np.array(item_panel, np.int64))
 
 
-def check_items(got_items, want):
-    """The GPU lists the same work items, re-ordered inside every panel (length-ranked, then dealt into lanes)."""
-    w = want["items"]
-    assert got_items.shape == w.shape
-    if len(w) == 0:
+def check_layout(got, want):
+    """The GPU lists the same work items, re-ordered inside every panel (length-ranked, then dealt into lanes; the order
+    among equal lengths is arbitrary), and stores the padded entries in that WORK-LIST order (STREAM order, layout.cuh):
+    item i starts where items 0..i-1 end.  Bit-exact check: same set of items per panel (keyed by their slot), every item
+    holds exactly the reference's padded entries, starts are the exclusive prefix sums of the lengths."""
+    gi, wi = got["items"], want["items"]
+    assert gi.shape == wi.shape
+    assert got["n_padded"] == want["n_padded"] and len(got["idx16"]) >= want["n_padded"]
+    if len(wi) == 0:
         return
-    assert np.array_equal(got_items[np.argsort(got_items[:, 0])], w[np.argsort(w[:, 0])])
+    lens = gi[:, 1].astype(np.int64)
+    assert np.array_equal(gi[:, 0].astype(np.int64), np.concatenate([[0], np.cumsum(lens)[:-1]]))
+    assert int(lens.sum()) == want["n_padded"]
+    by_slot = {int(r[3]): r for r in wi}
+    assert len(by_slot) == len(wi)
+    for g in gi:
+        w = by_slot[int(g[3])]
+        assert int(g[1]) == int(w[1]) and int(g[2]) == int(w[2])
+        a, b, n = int(g[0]), int(w[0]), int(g[1])
+        assert np.array_equal(got["idx16"][a:a + n], want["idx16"][b:b + n])
+        assert np.array_equal(got["val"][a:a + n], want["val"][b:b + n])
     counts = np.bincount(want["item_panel"], minlength=want["n_panels"])
     lo = 0
     for c in counts:
-        seg_got, seg_want = got_items[lo:lo + c], w[lo:lo + c]
-        assert set(seg_got[:, 0].tolist()) == set(seg_want[:, 0].tolist())  # same panel membership
+        assert set(gi[lo:lo + c, 3].tolist()) == set(wi[lo:lo + c, 3].tolist())  # same panel membership
         lo += c

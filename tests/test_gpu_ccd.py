@@ -112,22 +112,51 @@ def test_fused_schedule_equals_reference_schedule_bitwise(gpu, port, data_factor
 
 
 def test_all_pipelines_bitwise_equal(gpu, port, data_factory):
-    """The three ways of feeding the sweep (cp.async producer warps or one bulk-copy descriptor per item into a
-    shared-memory slot ring, or a register ring) use the same reduction tree: identical factors and residual,
-    for several panel / chunk geometries."""
+    """The three 8-lane-group ways of feeding the sweep (a register ring; cp.async producer warps or one bulk-copy
+    descriptor per item into a shared-memory slot ring) use the same reduction tree: identical factors and residual, for
+    several panel / chunk geometries.  The STREAM pipeline (large TMA bulk copies of the contiguous stream into a tile
+    ring, one item per warp) has its own fixed tree (32 lanes per item) and pads pieces to 8 instead of 32 entries: it
+    agrees with the others to rounding, and with itself bit for bit."""
     for shape, kw in (("ml100k", dict()), ("ml100k", dict(panel_rows=256, chunk=64)), ("small", dict(panel_rows=64, chunk=16))):
         d = data_factory(shape)
         k = 5
         W0 = port.initial_col(k, d["rows"])
         outs = []
-        for pipeline in (0, 1, 2):
+        for pipeline in (0, 1, 2, 3, 3):
             with gpu.Session(d, gpu.make_params(k=k, lam=0.05, maxinner=2, pipeline=pipeline, **kw)) as s:
                 s.set_factors(W0)
                 s.iterate(3)
                 outs.append(s.get_factors() + s.get_values())
-        for other in outs[1:]:
+        for other in outs[1:3]:
             for a, b in zip(outs[0], other):
                 assert np.array_equal(a, b)
+        for a, b in zip(outs[3], outs[4]):
+            assert np.array_equal(a, b)
+        for a, b in zip(outs[0], outs[3]):
+            assert np.linalg.norm(a - b) <= 2e-5 * np.linalg.norm(a)
+
+
+def test_stream_pipeline_step_parity_and_schedules(gpu, port, data_factory):
+    """STREAM pipeline: one solve sweep against the oracle on identical inputs (<= 5e-5), residual updates bit-exact,
+    fused schedule == reference launch order bit for bit."""
+    for shape, kw in (("ml100k", dict()), ("small", dict(panel_rows=64, chunk=16)), ("tiny", dict())):
+        d = data_factory(shape)
+        k, lam = 4, 0.05
+        W0 = port.initial_col(k, d["rows"])
+        outs = []
+        for schedule in (0, 1):
+            with gpu.Session(d, gpu.make_params(k=k, lam=lam, maxinner=3, pipeline=3, schedule=schedule, **kw)) as s:
+                s.set_factors(W0)
+                st = s.iterate(3)
+                outs.append(s.get_factors() + s.get_values() + (np.array([x["rmse"] for x in st]),))
+        for a, b in zip(*outs):
+            assert np.array_equal(a, b)
+        want = port.ccdpp(d["rows"], d["cols"], (d["csr_ptr"], d["csr_idx"], d["csr_val"]), (d["csc_ptr"], d["csc_idx"], d["csc_val"]),
+                          W0, k, lam, 3, 3, test=(d["test_row"], d["test_col"], d["test_val"]))
+        W, H = outs[0][0], outs[0][1]
+        assert np.linalg.norm(W - want["W"]) <= 2e-4 * np.linalg.norm(want["W"])
+        assert np.linalg.norm(H - want["H"]) <= 2e-4 * np.linalg.norm(want["H"])
+        assert np.abs(outs[0][-1] - np.array(want["rmse"])).max() < 1e-4
 
 
 def test_panel_geometry_does_not_change_residual_and_barely_factors(gpu, port, data_factory):
