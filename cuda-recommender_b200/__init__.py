@@ -47,7 +47,7 @@ class mf_params(C.Structure):
                 ("verbose", C.c_int32), ("do_nmf", C.c_int32), ("nBlocks", C.c_uint32), ("nThreadsPerBlock", C.c_uint32),
                 ("device", C.c_int32), ("schedule", C.c_int32), ("layout", C.c_int32), ("quiet", C.c_int32),
                 ("panel_rows", C.c_int32), ("chunk", C.c_int32), ("nmf_project", C.c_int32),
-                ("no_launch_timing", C.c_int32), ("pipeline", C.c_int32), ("timing_stride", C.c_int32), ("pad_entries", C.c_int32), ("reserved", C.c_int32 * 5)]
+                ("no_launch_timing", C.c_int32), ("pipeline", C.c_int32), ("timing_stride", C.c_int32), ("pad_entries", C.c_int32), ("early_stop", C.c_int32), ("reserved", C.c_int32 * 4)]
 
 
 class mf_iter_stats(C.Structure):
@@ -71,6 +71,7 @@ ABI_SYMBOLS = [
     "mf_session_create", "mf_session_destroy", "mf_dist_unique_id", "mf_session_create_dist",
     "mf_session_set_factors", "mf_session_get_factors", "mf_session_get_values",
     "mf_session_ccdpp_iterate", "mf_session_als_iterate", "mf_session_rmse", "mf_session_predict", "mf_session_kernel_times",
+    "mf_session_rank_stats", "mf_predict_pairs",
     "mf_session_last_seconds", "mf_session_ccd_solve", "mf_session_ccd_update", "mf_session_als_half",
     "mf_build_csr_csc", "mf_degree_bins", "mf_partition", "mf_session_panel_layout", "mf_als_plan",
 ]
@@ -124,6 +125,8 @@ def lib():
         L.mf_degree_bins.argtypes = [C.c_int64, vp, vp, vp, C.c_int]
         L.mf_partition.argtypes = [C.c_int64, vp, C.c_int, vp, C.c_int]
         L.mf_session_panel_layout.argtypes = [vp, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64), vp, vp, vp]
+        L.mf_session_rank_stats.argtypes = [vp, vp, vp, vp]
+        L.mf_predict_pairs.argtypes = [vp, vp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, vp, vp, vp, C.c_int]
         _lib = L
     return _lib
 
@@ -201,13 +204,17 @@ class Ratings:
 
 
 def make_params(solver=SOLVER_CCD, k=10, lam=0.1, maxiter=5, maxinner=1, device=0, schedule=SCHEDULE_FUSED,
-                layout=LAYOUT_PANEL, quiet=True, panel_rows=0, chunk=0, nmf_project=0, no_launch_timing=0, pipeline=0, timing_stride=0, pad_entries=0):
+                layout=LAYOUT_PANEL, quiet=True, panel_rows=0, chunk=0, nmf_project=0, no_launch_timing=0, pipeline=0, timing_stride=0, pad_entries=0,
+                eps=None, do_predict=0, verbose=0, do_nmf=0, early_stop=0):
     p = mf_params()
     lib().mf_params_default(C.byref(p))
     p.solver_type, p.k, p.lambda_, p.maxiter, p.maxinneriter = solver, k, lam, maxiter, maxinner
     p.device, p.schedule, p.layout, p.quiet = device, schedule, layout, int(quiet)
     p.panel_rows, p.chunk, p.nmf_project, p.no_launch_timing = panel_rows, chunk, nmf_project, no_launch_timing
     p.pipeline, p.timing_stride, p.pad_entries = pipeline, timing_stride, pad_entries
+    p.do_predict, p.verbose, p.do_nmf, p.early_stop = do_predict, verbose, do_nmf, early_stop
+    if eps is not None:
+        p.eps = eps
     return p
 
 
@@ -311,6 +318,18 @@ class Session:
         _check(lib().mf_session_predict(self.h, len(row), row.ctypes.data, col.ctypes.data, out.ctypes.data))
         return out
 
+    def rank_stats(self):
+        """Per-rank report of the last CCD++ outer iteration (mf_session_rank_stats): dict of seconds / rmse (None unless the
+        session was created with verbose and do_predict) and inner_iters."""
+        k = self.k
+        inner = np.zeros(k, np.int32)
+        sec = np.zeros(k, np.float64)
+        rm = np.zeros(k, np.float64)
+        if lib().mf_session_rank_stats(self.h, sec.ctypes.data, rm.ctypes.data, inner.ctypes.data) != 0:
+            _check(lib().mf_session_rank_stats(self.h, None, None, inner.ctypes.data))
+            return dict(seconds=None, rmse=None, inner_iters=inner)
+        return dict(seconds=sec, rmse=rm, inner_iters=inner)
+
     def last_seconds(self):
         r = C.c_double()
         _check(lib().mf_session_last_seconds(self.h, C.byref(r)))
@@ -339,6 +358,18 @@ class Session:
         _check(lib().mf_session_panel_layout(self.h, side, C.byref(npad), C.byref(nit), C.byref(npan),
                                              idx16.ctypes.data, val.ctypes.data, items.ctypes.data))
         return dict(n_padded=npad.value, n_items=nit.value, n_panels=npan.value, idx16=idx16, val=val, items=items)
+
+
+def predict_pairs(W, H, row, col, device=0):
+    """Predict-only path for a saved model (mf_predict_pairs): W [rows, k], H [cols, k] row-major -> float64 predictions."""
+    W = np.ascontiguousarray(W, np.float32)
+    H = np.ascontiguousarray(H, np.float32)
+    row = np.ascontiguousarray(row, np.uint32)
+    col = np.ascontiguousarray(col, np.uint32)
+    out = np.zeros(len(row), np.float64)
+    _check(lib().mf_predict_pairs(W.ctypes.data, H.ctypes.data, W.shape[0], H.shape[0], W.shape[1], len(row), row.ctypes.data,
+                              col.ctypes.data, out.ctypes.data, device))
+    return out
 
 
 def nccl_unique_id():

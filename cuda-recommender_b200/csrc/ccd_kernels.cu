@@ -237,26 +237,41 @@ struct PushArgs {
 // grid-stride over segments, four segments per thread and round with their metadata loads issued together (the
 // finalize is a chain of dependent L2 round trips: pointers -> slots -> result); `partials` is read through L2
 // (written by other CTAs of the same launch when the finalize runs inside the sweep kernel)
+// segment metadata of a thread's first finalize round (layout data: it can be fetched before the grid barrier, which
+// takes one dependent L2 round trip out of every solving sweep)
+struct FinalizeMeta {
+    uint32_t deg[4], lo[4], hi[4];
+};
+template <int LANES>
+__device__ __forceinline__ void finalize_load_meta(int64_t nseg, const uint32_t* __restrict__ slot_ptr, const uint32_t* __restrict__ seg_ptr,
+                                                   int64_t t0, FinalizeMeta& m) {
+    const int64_t total = nseg * LANES, stride = (int64_t)gridDim.x * blockDim.x;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int64_t tid = t0 + u * stride;
+        m.deg[u] = 0u; m.lo[u] = 0u; m.hi[u] = 0u;
+        if (tid < total) {
+            const int64_t s = tid / LANES;
+            m.deg[u] = seg_ptr[s + 1] - seg_ptr[s];
+            m.lo[u] = slot_ptr[s];
+            m.hi[u] = slot_ptr[s + 1];
+        }
+    }
+}
+
 template <int LANES>
 __device__ __forceinline__ void finalize_segments(int64_t nseg, const uint32_t* __restrict__ slot_ptr, const float2* partials,
                                                   const uint32_t* __restrict__ seg_ptr, float lambda, int nmf,
                                                   float* __restrict__ out, unsigned long long* const* peer_ll, int64_t vec_off,
-                                                  int rank, int nranks, unsigned epoch) {
+                                                  int rank, int nranks, unsigned epoch, const FinalizeMeta* first = nullptr) {
     constexpr int U = 4;
     const int64_t total = nseg * LANES, stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t0 < total; t0 += U * stride) {
-        uint32_t deg[U], lo[U], hi[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int64_t tid = t0 + u * stride;
-            deg[u] = 0u; lo[u] = 0u; hi[u] = 0u;
-            if (tid < total) {
-                const int64_t s = tid / LANES;
-                deg[u] = seg_ptr[s + 1] - seg_ptr[s];
-                lo[u] = slot_ptr[s];
-                hi[u] = slot_ptr[s + 1];
-            }
-        }
+    const int64_t tfirst = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (int64_t t0 = tfirst; t0 < total; t0 += U * stride) {
+        FinalizeMeta m;
+        if (first != nullptr && t0 == tfirst) m = *first;
+        else finalize_load_meta<LANES>(nseg, slot_ptr, seg_ptr, t0, m);
+        uint32_t (&deg)[U] = m.deg, (&lo)[U] = m.lo, (&hi)[U] = m.hi;
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int64_t tid = t0 + u * stride;
@@ -353,7 +368,7 @@ __device__ __forceinline__ void l2_prefetch(const void* p, uint32_t bytes) {
 // smem: the staged panel vectors; s_ctr: a shared-memory counter the warps pull batches from.
 template <int MODE, class Args>
 __device__ __forceinline__ void sweep_cta_range(const Args& a, float* smem, unsigned* s_ctr, uint32_t ib, uint32_t ie, int p, const unsigned tid,
-                                                const unsigned nthr) {
+                                                const unsigned nthr, uint32_t pend_first = 0xffffffffu) {
     constexpr bool SUB = MODE & kSub, ADD = MODE & kAdd, SOLVE = MODE & kSolve, ADDSEP = MODE & kAddSep;
     const uint32_t PR = a.panel_rows();
     const uint32_t stride = PR + 8;  // 8 zeroed floats behind each panel: the padding slot idx16 == PR
@@ -374,8 +389,10 @@ __device__ __forceinline__ void sweep_cta_range(const Args& a, float* smem, unsi
     const int grp = lane >> 3, sl = lane & 7;
     const uint4* __restrict__ items = reinterpret_cast<const uint4*>(a.items());
 
+    bool first = pend_first != 0xffffffffu;  // the end of the first panel may have been fetched by the caller
     while (ib < ie && p < a.npanels()) {
-        const uint32_t pend = a.panel_item_ptr()[p + 1];
+        const uint32_t pend = first ? pend_first : a.panel_item_ptr()[p + 1];
+        first = false;
         const uint32_t pe = ie < pend ? ie : pend;
         if (pe > ib) {
             __syncthreads();  // every warp is done with the previous panel and counter
@@ -443,16 +460,31 @@ __device__ __forceinline__ void sweep_cta_range(const Args& a, float* smem, unsi
     }
 }
 
+// Programmatic dependent launch (sweeps follow one another in the stream, each depending on the one before): the kernel
+// lets its successor be scheduled at once (its CTAs take an SM as soon as one of ours leaves) and the successor runs its
+// prologue — item range, first panel: layout data no sweep writes — before it waits for our completion and memory flush.
+// What that removes from the 2kT dependent launches of an outer iteration is the launch gap and the prologue's dependent
+// L2 round trips.  Both instructions are no-ops when the launch does not carry the attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 template <int MODE>
 __global__ void __launch_bounds__(kSweepThreads, 1) k_panel_sweep(PanelSweepArgs a) {
     constexpr bool SOLVE = MODE & kSolve;
     extern __shared__ __align__(16) float smem[];
     __shared__ unsigned s_ctr;
+    pdl_launch_dependents();
     const uint32_t ib = a.cta_item_ptr[blockIdx.x];
     const uint32_t ie = a.cta_item_ptr[blockIdx.x + 1];
     const int p = first_panel(a.panel_item_ptr, a.npanels, ib);
-    sweep_cta_range<MODE>(LaunchView{a}, smem, &s_ctr, ib, ie, p, threadIdx.x, blockDim.x);
+    const uint32_t pend0 = p < a.npanels ? a.panel_item_ptr[p + 1] : 0u;
+    pdl_wait();  // everything below reads what the previous sweep wrote (factor vectors, residual) or writes what it read
+    sweep_cta_range<MODE>(LaunchView{a}, smem, &s_ctr, ib, ie, p, threadIdx.x, blockDim.x, pend0);
     if (SOLVE && a.fin.enabled) {
+        // the first finalize round's segment metadata is on its way while the grid assembles at the barrier
+        FinalizeMeta meta;
+        if (a.fin.lanes == 32) finalize_load_meta<32>(a.fin.nseg, a.fin.slot_ptr, a.fin.seg_ptr, (int64_t)blockIdx.x * blockDim.x + threadIdx.x, meta);
+        else finalize_load_meta<1>(a.fin.nseg, a.fin.slot_ptr, a.fin.seg_ptr, (int64_t)blockIdx.x * blockDim.x + threadIdx.x, meta);
         // grid-wide barrier (monotonic counter; every CTA of the launch is resident), then the CTAs share the segments
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -473,10 +505,10 @@ __global__ void __launch_bounds__(kSweepThreads, 1) k_panel_sweep(PanelSweepArgs
         __syncthreads();
         if (a.fin.lanes == 32)
             finalize_segments<32>(a.fin.nseg, a.fin.slot_ptr, a.partials, a.fin.seg_ptr, a.fin.lambda, a.fin.nmf, a.fin.out,
-                                  a.fin.peer_ll, a.fin.vec_off, a.fin.rank, a.fin.nranks, a.fin.epoch);
+                                  a.fin.peer_ll, a.fin.vec_off, a.fin.rank, a.fin.nranks, a.fin.epoch, &meta);
         else
             finalize_segments<1>(a.fin.nseg, a.fin.slot_ptr, a.partials, a.fin.seg_ptr, a.fin.lambda, a.fin.nmf, a.fin.out,
-                                 a.fin.peer_ll, a.fin.vec_off, a.fin.rank, a.fin.nranks, a.fin.epoch);
+                                 a.fin.peer_ll, a.fin.vec_off, a.fin.rank, a.fin.nranks, a.fin.epoch, &meta);
         if (a.fin.ll != nullptr) ll_unpack_entries(a.fin.ll, a.fin.vec, a.fin.dim, a.fin.own_lo, a.fin.own_hi, a.fin.epoch);
     }
 }
@@ -1481,7 +1513,18 @@ int launch_panel(const PanelSweepArgs& a, int ncta, int threads, size_t smem, cu
     if (once.need()) {
         MF_CUDA(cudaFuncSetAttribute(k_panel_sweep<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 256));
     }
-    k_panel_sweep<MODE><<<ncta, threads, smem, st>>>(a);
+    static const bool pdl = getenv("MF_NO_PDL") == nullptr;
+    if (pdl) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)ncta); cfg.blockDim = dim3((unsigned)threads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        MF_CUDA(cudaLaunchKernelEx(&cfg, k_panel_sweep<MODE>, a));
+    } else {
+        k_panel_sweep<MODE><<<ncta, threads, smem, st>>>(a);
+    }
     MF_CUDA(cudaGetLastError());
     return MF_OK;
 }

@@ -271,6 +271,54 @@ int flush_pending(mf_session* s) {
     return MF_OK;
 }
 
+// ---- optional per-rank work (both inert in the reference) ----
+// rank start: remember u_t (and v_t, which the fused schedule keeps anyway) for the incremental test RMSE
+int rank_begin(mf_session* s, int t) {
+    if (!s->rank_report) return MF_OK;
+    MF_CUDA(cudaEventRecord(s->rank_ev[t], s->st));
+    MF_CUDA(cudaMemcpyAsync(s->u_prev, s->W + (int64_t)t * s->ldm, sizeof(float) * (size_t)s->ldm, cudaMemcpyDeviceToDevice, s->st));
+    MF_CUDA(cudaMemcpyAsync(s->v_old + (int64_t)t * s->ldn, s->H + (int64_t)t * s->ldn, sizeof(float) * (size_t)s->ldn, cudaMemcpyDeviceToDevice, s->st));
+    return MF_OK;
+}
+// rank end (before v_old[t] is refreshed): calrmse_r1 with the rank's old and new vectors — src/CCD.cpp:144-146
+int rank_end(mf_session* s, int t) {
+    if (!s->rank_report) return MF_OK;
+    s->timer.start(F_RMSE);
+    MF_TRY(rmse_r1_accumulate(s->nt, s->trow, s->tcol, s->tres, s->W + (int64_t)t * s->ldm, s->H + (int64_t)t * s->ldn, s->u_prev,
+                              s->v_old + (int64_t)t * s->ldn, s->d_acc, s->sm_count, s->st));
+    s->timer.stop();
+    MF_CUDA(cudaMemcpyAsync(s->d_rank_acc + t, s->d_acc, sizeof(double), cudaMemcpyDeviceToDevice, s->st));
+    MF_CUDA(cudaEventRecord(s->rank_ev[t + 1], s->st));
+    return MF_OK;
+}
+// -e stop rule of CCDR1 (restated in oracle/mf_oracle.c, orc_ccdpp_ex): the function decrease of an inner iteration is the
+// sum over both sweeps of (lambda*deg + h)(old - new)^2; the rank's inner iterations end after the one whose decrease is
+// below eps * (largest decrease seen so far); the very first inner iteration of a run never enters the maximum.
+int stop_rule_before(mf_session* s, const float* vec, int64_t n) {
+    if (!s->early_stop) return MF_OK;
+    MF_CUDA(cudaMemcpyAsync(s->vec_prev, vec, sizeof(float) * (size_t)n, cudaMemcpyDeviceToDevice, s->st));
+    return MF_OK;
+}
+int stop_rule_after(mf_session* s, const Side& sd, const float* vec, int which) {
+    if (!s->early_stop) return MF_OK;
+    MF_TRY(fundec_accumulate(sd.nseg, sd.ptr, sd.slot_ptr, sd.partials, s->prm.lambda, s->vec_prev + sd.seg_offset, vec + sd.seg_offset,
+                             s->d_acc, s->sm_count, s->st));
+    MF_CUDA(cudaMemcpyAsync(s->d_rank_acc + s->k + which, s->d_acc, sizeof(double), cudaMemcpyDeviceToDevice, s->st));
+    return MF_OK;
+}
+// true: stop the rank's inner iterations now (one host synchronisation per inner iteration: the rule is opt-in)
+int stop_rule_decide(mf_session* s, int t, int it, bool* stop) {
+    *stop = false;
+    if (!s->early_stop) return MF_OK;
+    double f[2] = {0, 0};
+    MF_CUDA(cudaMemcpyAsync(f, s->d_rank_acc + s->k, 2 * sizeof(double), cudaMemcpyDeviceToHost, s->st));
+    MF_CUDA(cudaStreamSynchronize(s->st));
+    const double cur = f[0] + f[1];
+    if (cur < s->fundec_max * (double)s->prm.eps) { *stop = true; return MF_OK; }
+    if (!(s->outer_done == 0 && t == 0 && it == 0)) s->fundec_max = std::max(s->fundec_max, cur);
+    return MF_OK;
+}
+
 // one rank of one outer iteration, fused schedule: the deferred subtraction of the
 // previous rank and this rank's add-back ride on the first solve sweep of each copy.
 int ccd_rank_fused(mf_session* s, int t, bool add) {
@@ -282,24 +330,39 @@ int ccd_rank_fused(mf_session* s, int t, bool add) {
     const float* u_sub = sub >= 0 ? s->W + (int64_t)sub * s->ldm : nullptr;
     const float* v_sub = sub >= 0 ? s->H + (int64_t)sub * s->ldn : nullptr;
     const float* v_prev_iter = s->v_old + (int64_t)t * s->ldn;  // v_t as the previous outer iteration left it
+    MF_TRY(rank_begin(s, t));
+    bool stop = false;
     {   // CSC: [subtract `sub`] [add back t with the old (u_t, v_t)] solve v_t against u_t
         SweepVectors a;
         a.g_new = u; a.g_old = u_sub; a.s_add = v; a.s_old = v_sub;
+        MF_TRY(stop_rule_before(s, v, s->ldn));
         MF_TRY(solve_v(s, t, kSolve | (sub >= 0 ? kSub : 0) | (add ? kAdd : 0), a));
+        MF_TRY(stop_rule_after(s, s->csc, v, 0));
     }
     {   // CSR: [subtract `sub`] [add back t with the old v_t (saved) and old u_t] solve u_t against the new v_t
         SweepVectors a;
         a.g_new = v; a.g_add = v_prev_iter; a.s_add = u; a.s_old = u_sub;
         a.g_old = (sub == t) ? v_prev_iter : v_sub;  // k == 1: the subtracted rank's v was just overwritten
+        MF_TRY(stop_rule_before(s, u, s->ldm));
         MF_TRY(solve_u(s, t, kSolve | (sub >= 0 ? kSub : 0) | (add ? (kAdd | kAddSep) : 0), a));
+        MF_TRY(stop_rule_after(s, s->csr, u, 1));
     }
-    for (int it = 1; it < T; ++it) {
+    MF_TRY(stop_rule_decide(s, t, 0, &stop));
+    int done = 1;
+    for (int it = 1; it < T && !stop; ++it, ++done) {
         SweepVectors a, b;
         a.g_new = u;
+        MF_TRY(stop_rule_before(s, v, s->ldn));
         MF_TRY(solve_v(s, t, kSolve, a));
+        MF_TRY(stop_rule_after(s, s->csc, v, 0));
         b.g_new = v;
+        MF_TRY(stop_rule_before(s, u, s->ldm));
         MF_TRY(solve_u(s, t, kSolve, b));
+        MF_TRY(stop_rule_after(s, s->csr, u, 1));
+        MF_TRY(stop_rule_decide(s, t, it, &stop));
     }
+    if (!s->rank_inner.empty()) s->rank_inner[t] = done;
+    MF_TRY(rank_end(s, t));
     // keep v_t for the next outer iteration's add-back on the CSR copy (taken now: no rank writes H[t] again
     // before that, so the copy can never race with a peer's push)
     MF_CUDA(cudaMemcpyAsync(s->v_old + (int64_t)t * s->ldn, v, sizeof(float) * (size_t)s->ldn, cudaMemcpyDeviceToDevice, s->st));
@@ -324,7 +387,7 @@ PersistSide persist_side(mf_session* s, const Side& sd, bool solves_h) {
 // May this session run an outer iteration as one persistent launch?  (panel layout, fused schedule, register-ring
 // pipeline, co-resident grid with cooperative launch, and — multi-GPU — the peer-to-peer exchange)
 bool use_persistent(const mf_session* s) {
-    return s->persistent && s->panel && s->prm.schedule == MF_SCHEDULE_FUSED && s->prm.pipeline == MF_PIPELINE_REGISTERS &&
+    return s->persistent && !s->rank_report && !s->early_stop && s->panel && s->prm.schedule == MF_SCHEDULE_FUSED && s->prm.pipeline == MF_PIPELINE_REGISTERS &&
            s->prm.maxinneriter >= 1 && (s->nranks == 1 || fused_exchange(s));
 }
 
@@ -393,14 +456,24 @@ int ccd_rank_reference(mf_session* s, int t, bool add) {
     const int T = s->prm.maxinneriter;
     float* u = s->W + (int64_t)t * s->ldm;
     float* v = s->H + (int64_t)t * s->ldn;
+    MF_TRY(rank_begin(s, t));
     if (add) MF_TRY(update_both(s, t, true));
-    for (int it = 0; it < T; ++it) {
+    bool stop = false;
+    int done = 0;
+    for (int it = 0; it < T && !stop; ++it, ++done) {
         SweepVectors a, b;
         a.g_new = u;
+        MF_TRY(stop_rule_before(s, v, s->ldn));
         MF_TRY(solve_v(s, t, kSolve, a));
+        MF_TRY(stop_rule_after(s, s->csc, v, 0));
         b.g_new = v;
+        MF_TRY(stop_rule_before(s, u, s->ldm));
         MF_TRY(solve_u(s, t, kSolve, b));
+        MF_TRY(stop_rule_after(s, s->csr, u, 1));
+        MF_TRY(stop_rule_decide(s, t, it, &stop));
     }
+    if (!s->rank_inner.empty()) s->rank_inner[t] = done;
+    MF_TRY(rank_end(s, t));
     return update_both(s, t, false);
 }
 
@@ -604,6 +677,28 @@ int create_impl(const mf_ratings* R, const mf_testset* T, const mf_params* param
         if ((rc = upload_bytes(s->tcol, T->col, sizeof(uint32_t) * (size_t)s->nt, s->st)) != MF_OK) return fail(rc);
         if ((rc = upload_bytes(s->tval, T->val, sizeof(float) * (size_t)s->nt, s->st)) != MF_OK) return fail(rc);
     }
+    if (ccd) {
+        if (s->prm.do_nmf) s->prm.nmf_project = 1;  // -N: the clamp of the finalize (inert in the reference, src/pmf.h:36)
+        s->rank_inner.assign((size_t)s->k, 0);
+        s->early_stop = s->prm.early_stop != 0;
+        if (s->early_stop && (nranks > 1 || !s->panel)) {
+            set_error("early_stop needs a single-GPU session with the panel layout");
+            return fail(MF_ERR_UNSUPPORTED);
+        }
+        s->rank_report = s->prm.verbose != 0 && s->prm.do_predict != 0 && s->nt > 0;
+        if (s->rank_report) {
+            if ((rc = dev_alloc(&s->tres, (size_t)s->nt)) != MF_OK) return fail(rc);
+            if ((rc = dev_alloc(&s->u_prev, (size_t)s->ldm)) != MF_OK) return fail(rc);
+            // the reference's calrmse_r1 starts from the raw test ratings: training starts at H = 0 (src/CCD.cpp:63-67)
+            if (cudaMemcpyAsync(s->tres, s->tval, sizeof(float) * (size_t)s->nt, cudaMemcpyDeviceToDevice, s->st) != cudaSuccess) { set_error("cudaMemcpyAsync failed"); return fail(MF_ERR_CUDA); }
+            s->rank_ev.resize((size_t)s->k + 1);
+            for (auto& e : s->rank_ev) cudaEventCreate(&e);
+            s->rank_seconds.assign((size_t)s->k, 0.0);
+            s->rank_rmse.assign((size_t)s->k, 0.0);
+        }
+        if (s->early_stop && (rc = dev_alloc(&s->vec_prev, (size_t)std::max(s->ldm, s->ldn))) != MF_OK) return fail(rc);
+        if ((s->rank_report || s->early_stop) && (rc = dev_alloc(&s->d_rank_acc, (size_t)s->k + 2)) != MF_OK) return fail(rc);
+    }
     trace_mark("  test set");
     if ((rc = dev_alloc(&s->d_acc, rmse_scratch_doubles(s->sm_count))) != MF_OK) return fail(rc);
     if ((rc = dev_alloc(&s->d_gridbar, 2)) != MF_OK) return fail(rc);
@@ -718,7 +813,8 @@ int mf_session_destroy(mf_session* s) {
     if (s->dist) dist_destroy(s->dist);
     side_free(s->csc);
     side_free(s->csr);
-    void* ptrs[] = {s->W, s->H, s->v_old, s->trow, s->tcol, s->tval, s->d_acc, s->d_gridbar, s->d_stamps};
+    for (auto& e : s->rank_ev) cudaEventDestroy(e);
+    void* ptrs[] = {s->W, s->H, s->v_old, s->trow, s->tcol, s->tval, s->d_acc, s->d_gridbar, s->d_stamps, s->tres, s->u_prev, s->vec_prev, s->d_rank_acc};
     for (void* p : ptrs)
         if (p) dev_free(p);
     arena_destroy(s->arena);
@@ -825,6 +921,54 @@ int mf_session_predict(mf_session* s, int64_t n, const uint32_t* row, const uint
     return rc;
 }
 
+int mf_session_rank_stats(mf_session* s, double* seconds, double* rmse, int32_t* inner_iters) {
+    MF_REQUIRE(s, "NULL argument");
+    if (s->prm.solver_type != MF_SOLVER_CCD) { set_error("not a CCD++ session"); return MF_ERR_STATE; }
+    if ((seconds || rmse) && !s->rank_report) { set_error("per-rank report is off (needs verbose, do_predict and a test set)"); return MF_ERR_STATE; }
+    for (int t = 0; t < s->k; ++t) {
+        if (seconds) seconds[t] = s->rank_seconds[t];
+        if (rmse) rmse[t] = s->rank_rmse[t];
+        if (inner_iters) inner_iters[t] = s->rank_inner[t];
+    }
+    return MF_OK;
+}
+
+int mf_predict_pairs(const float* W, const float* H, int64_t rows, int64_t cols, int64_t k, int64_t n, const uint32_t* row,
+                     const uint32_t* col, double* out, int device) {
+    MF_REQUIRE(W && H && rows > 0 && cols > 0 && k > 0 && n >= 0 && (n == 0 || (row && col && out)), "mf_predict_pairs: bad argument");
+    if (n == 0) return MF_OK;
+    int ndev = 0, sms = 0;
+    MF_CUDA(cudaGetDeviceCount(&ndev));
+    MF_REQUIRE(device >= 0 && device < ndev, "device %d not present (%d CUDA devices)", device, ndev);
+    MF_CUDA(cudaSetDevice(device));
+    MF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    for (int64_t e = 0; e < n; ++e)  // host pairs: the model's shape bounds them (a bad pair would read past the factors)
+        MF_REQUIRE(row[e] < (uint64_t)rows && col[e] < (uint64_t)cols, "pair %lld (%u, %u) is outside the %lld x %lld model", (long long)e, row[e], col[e], (long long)rows, (long long)cols);
+    float *dW = nullptr, *dH = nullptr;
+    uint32_t *d_row = nullptr, *d_col = nullptr;
+    double* d_out = nullptr;
+    int rc = dev_alloc(&dW, (size_t)rows * k);
+    if (rc == MF_OK) rc = dev_alloc(&dH, (size_t)cols * k);
+    if (rc == MF_OK) rc = dev_alloc(&d_row, (size_t)n);
+    if (rc == MF_OK) rc = dev_alloc(&d_col, (size_t)n);
+    if (rc == MF_OK) rc = dev_alloc(&d_out, (size_t)n);
+    auto cuda_ok = [&](cudaError_t e) {
+        if (e != cudaSuccess && rc == MF_OK) { set_error("mf_predict_pairs: %s", cudaGetErrorString(e)); rc = MF_ERR_CUDA; }
+    };
+    if (rc == MF_OK) {
+        cuda_ok(cudaMemcpy(dW, W, sizeof(float) * (size_t)rows * k, cudaMemcpyHostToDevice));
+        cuda_ok(cudaMemcpy(dH, H, sizeof(float) * (size_t)cols * k, cudaMemcpyHostToDevice));
+        cuda_ok(cudaMemcpy(d_row, row, sizeof(uint32_t) * (size_t)n, cudaMemcpyHostToDevice));
+        cuda_ok(cudaMemcpy(d_col, col, sizeof(uint32_t) * (size_t)n, cudaMemcpyHostToDevice));
+    }
+    if (rc == MF_OK) rc = predict_pairs(n, d_row, d_col, dW, dH, (int)k, 1, k, 1, k, d_out, sms, nullptr);
+    if (rc == MF_OK) cuda_ok(cudaMemcpy(out, d_out, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost));
+    void* ptrs[] = {dW, dH, d_row, d_col, d_out};
+    for (void* p : ptrs)
+        if (p) dev_free(p);
+    return rc;
+}
+
 int mf_session_ccdpp_iterate(mf_session* s, int n_outer, mf_iter_stats* stats) {
     MF_REQUIRE(s && n_outer >= 0, "bad argument");
     if (s->prm.solver_type != MF_SOLVER_CCD) { set_error("not a CCD++ session"); return MF_ERR_STATE; }
@@ -848,7 +992,7 @@ int mf_session_ccdpp_iterate(mf_session* s, int n_outer, mf_iter_stats* stats) {
         s->timer.enabled = timing_on;
         return MF_OK;
     };
-    if (!stats && !persist) {
+    if (!stats && !persist && !s->rank_report) {
         // no per-iteration report wanted: one event pair around all n_outer iterations, one sync
         MF_CUDA(cudaEventRecord(s->ev_a, s->st));
         for (int it = 0; it < n_outer; ++it) {
@@ -882,6 +1026,16 @@ int mf_session_ccdpp_iterate(mf_session* s, int n_outer, mf_iter_stats* stats) {
         total += ms * 1e-3;
         s->outer_done++;
         s->timer.collect(s->fam_seconds, s->fam_launches);
+        if (s->rank_report) {
+            std::vector<double> acc((size_t)s->k);
+            MF_CUDA(cudaMemcpy(acc.data(), s->d_rank_acc, sizeof(double) * (size_t)s->k, cudaMemcpyDeviceToHost));
+            for (int t = 0; t < s->k; ++t) {
+                float rms = 0.f;
+                cudaEventElapsedTime(&rms, s->rank_ev[t], s->rank_ev[t + 1]);
+                s->rank_seconds[t] = rms * 1e-3;
+                s->rank_rmse[t] = sqrt(acc[t] / (double)s->nt);
+            }
+        }
         if (persist) {
             MF_TRY(check_device_status(s));
             if (timing_on) fold_stamps(s, add, had_pending);
@@ -1042,6 +1196,16 @@ static int train_impl(const mf_ratings* R, const mf_testset* T, float* W, float*
         rank_acc += st.rank_time;
         upd_acc += st.update_time;
         if (stats) stats[it] = st;
+        if (!p.quiet && solver == MF_SOLVER_CCD && p.verbose) {
+            // the per-rank lines of the reference's (commented-out) verbose block, src/CCD.cpp:141-148
+            std::vector<double> sec((size_t)p.k), rm((size_t)p.k);
+            const bool have = mf_session_rank_stats(s, sec.data(), rm.data(), nullptr) == MF_OK;
+            for (unsigned t = 0; have && t < p.k; ++t) {
+                printf("iter %d rank %d time %f", it + 1, (int)t + 1, sec[t]);
+                if (p.do_predict) printf(" rmse %f", rm[t]);
+                printf("\n");
+            }
+        }
         if (!p.quiet) {
             if (solver == MF_SOLVER_CCD)  // line format of CCD_CUDA.cu:405
                 printf("[-INFO-] iteration num %d \trank_time %.4lf|%.4lf s \tupdate_time %.4lf|%.4lfs \tRMSE=%lf time:%fs\n",

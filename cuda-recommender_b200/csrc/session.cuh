@@ -60,6 +60,17 @@ struct mf_session {
     unsigned long long* d_stamps = nullptr;  // [1 + 2kT] phase time stamps of the last persistent launch
     std::vector<unsigned long long> h_stamps;
     bool broken = false;            // a device-side wait timed out: the session refuses further work
+    // ---- optional per-rank reporting and the -e stop rule (CCD++) ----
+    bool rank_report = false;       // verbose && do_predict: per-rank time and incremental test RMSE (src/CCD.cpp:141-148)
+    bool early_stop = false;        // mf_params.early_stop: inner iterations end when the function decrease falls under eps * max
+    float* tres = nullptr;          // [nt] test residual of calrmse_r1 (src/tools.cpp:260-270)
+    float* u_prev = nullptr;        // [ldm] u_t as it was when the rank started
+    float* vec_prev = nullptr;      // [max(ldm, ldn)] the vector a solve sweep is about to overwrite (stop rule)
+    double* d_rank_acc = nullptr;   // [k] sum of squared test residuals after each rank; [k .. k+1] function decrease of the two sweeps
+    std::vector<cudaEvent_t> rank_ev;          // k+1 events (rank_report)
+    std::vector<double> rank_seconds, rank_rmse;  // last outer iteration
+    std::vector<int> rank_inner;               // inner iterations run per rank in the last outer iteration
+    double fundec_max = 0.0;
     int outer_done = 0;
     int pending = -1;  // rank whose subtraction from the residual is still deferred (fused schedule)
     mf::FamilyTimer timer;

@@ -33,7 +33,11 @@ void exit_with_help() {
         "    -device id : CUDA device ordinal (default 0)\n"
         "    -schedule s : 0 fused sweeps (default), 1 the reference's launch order\n"
         "    -layout l : 0 shared-memory panel layout (default), 1 caller-order arrays\n"
-        "    -save : write W then H to <data_dir>/model (row-major, the reference's save_mat_t format)\n");
+        "    -save : write W then H to <data_dir>/model (row-major, the reference's save_mat_t format)\n"
+        "    -load : predict only: read <data_dir>/model, write one prediction per test rating to <data_dir>/output\n"
+        "            and print the test RMSE (the reference's calculate_rmse_from_file)\n"
+        "  (-e switches the stop rule on: a rank's inner iterations end once the function decrease is below eps x the\n"
+        "   largest seen; -N 1 clamps factors at 0; -q 1 -p 1 prints time and test RMSE after every rank)\n");
     std::exit(EXIT_FAILURE);
 }
 
@@ -47,6 +51,7 @@ parameter parse_command_line(int argc, char** argv) {
         {"-OMP", [](parameter& p) { p.enable_omp = true; }},
         {"-ALS", [](parameter& p) { p.solver_type = solvertype::ALS; }},
         {"-save", [](parameter&) { g_save_model = true; }},
+        {"-load", [](parameter& p) { p.load_model = true; }},
     };
     const std::map<std::string, std::function<void(parameter&, const char*)>> valued = {
         {"-nBlocks", [](parameter& p, const char* v) { p.nBlocks = std::atoi(v); }},
@@ -59,7 +64,7 @@ parameter parse_command_line(int argc, char** argv) {
         {"-l", [](parameter& p, const char* v) { p.lambda = (float)std::atof(v); }},
         {"-t", [](parameter& p, const char* v) { p.maxiter = std::atoi(v); }},
         {"-T", [](parameter& p, const char* v) { p.maxinneriter = std::atoi(v); }},
-        {"-e", [](parameter& p, const char* v) { p.eps = (float)std::atof(v); }},
+        {"-e", [](parameter& p, const char* v) { p.eps = (float)std::atof(v); p.early_stop = 1; }},
         {"-p", [](parameter& p, const char* v) { p.do_predict = std::atoi(v); }},
         {"-q", [](parameter& p, const char* v) { p.verbose = std::atoi(v); }},
         {"-N", [](parameter& p, const char* v) { p.do_nmf = (std::atoi(v) == 1); }},

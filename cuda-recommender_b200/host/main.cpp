@@ -9,9 +9,12 @@
 //   * the dataset directory is not written to unless -save is given (the reference always truncates
 //     <dir>/model and <dir>/output, src/extras.cpp:11-21).
 #include <chrono>
+#include <cmath>
 #include <cstdio>
 #include <iostream>
+#include <vector>
 
+#include "../../include/mf_abi.h"
 #include "extras.h"
 
 void kernel_wrapper_ccdpp_NV(SparseMatrix& R, TestData& T, MatData& W, MatData& H, parameter& parameters);
@@ -22,6 +25,43 @@ extern bool g_save_model;
 namespace {
 double now_s() { return std::chrono::duration<double>(std::chrono::high_resolution_clock::now().time_since_epoch()).count(); }
 const char* kRule = "------------------------------------------------------------";
+
+// -load: the reference's calculate_rmse_from_file (src/extras.cpp:143-180; its call is commented out of main.cpp:146-149)
+// on the GPU: W then H from <dir>/model (load_mat_t, both row-major rows x k as -save writes them), one prediction per
+// test rating through the C-ABI's predict-only entry point, "%lf" lines to <dir>/output, the same final line.
+int predict_from_model(const parameter& param, TestData& T) {
+    const double t0 = now_s();
+    const std::string model = std::string(param.src_dir) + "/model", output = std::string(param.src_dir) + "/output";
+    FILE* mfp = std::fopen(model.c_str(), "rb");
+    if (!mfp) { std::fprintf(stderr, "can't open model file %s\n", model.c_str()); return EXIT_FAILURE; }
+    MatData W = load_mat_t(mfp, true);
+    MatData H = load_mat_t(mfp, true);
+    std::fclose(mfp);
+    const size_t rank = W[0].size();
+    if (rank == 0 || H[0].size() != rank) { std::fprintf(stderr, "Matrix is empty!\n"); return EXIT_FAILURE; }
+    if (T.nnz == 0) return EXIT_FAILURE;  // num_insts == 0, src/extras.cpp:173
+    std::vector<float> w(W.size() * rank), h(H.size() * rank);
+    for (size_t i = 0; i < W.size(); ++i) std::copy(W[i].begin(), W[i].end(), w.begin() + i * rank);
+    for (size_t j = 0; j < H.size(); ++j) std::copy(H[j].begin(), H[j].end(), h.begin() + j * rank);
+    std::vector<double> pred((size_t)T.nnz);
+    if (mf_predict_pairs(w.data(), h.data(), (int64_t)W.size(), (int64_t)H.size(), (int64_t)rank, (int64_t)T.nnz, T.getTestRow(),
+                         T.getTestCol(), pred.data(), param.device) != MF_OK) {
+        std::fprintf(stderr, "PREDICT FAILED: %s\n", mf_last_error());
+        return EXIT_FAILURE;
+    }
+    FILE* ofp = std::fopen(output.c_str(), "w");
+    if (!ofp) { std::fprintf(stderr, "can't open output file %s\n", output.c_str()); return EXIT_FAILURE; }
+    double rmse = 0;
+    for (long e = 0; e < T.nnz; ++e) {
+        const double d = pred[e] - (double)T.getTestVal()[e];
+        rmse += d * d;
+        std::fprintf(ofp, "%lf\n", pred[e]);
+    }
+    std::fclose(ofp);
+    rmse = std::sqrt(rmse / (double)T.nnz);
+    std::printf("[FINAL INFO] Test RMSE = %f. Calculated in %lfs\n", rmse, now_s() - t0);
+    return EXIT_SUCCESS;
+}
 }  // namespace
 
 int main(int argc, char* argv[]) {
@@ -36,6 +76,13 @@ int main(int argc, char* argv[]) {
     load(param.src_dir, R, T);
     std::printf("[info] Loading rating data time: %lf s.\n", now_s() - t0);
     std::puts(kRule);
+
+    if (param.load_model) {
+        const int rc = predict_from_model(param, T);
+        std::puts(kRule);
+        std::cout << "Total Time: " << now_s() - t_begin << " s.\n";
+        return rc;
+    }
 
     const bool ifALS = param.solver_type == solvertype::ALS;
     std::puts(ifALS ? "[info] Picked Version: ALS!" : "[info] Picked Version: CCD!");

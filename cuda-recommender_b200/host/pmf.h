@@ -19,10 +19,10 @@ public:
     int maxiter = 5;                 // outer iterations                   (-t)
     int maxinneriter = 1;            // CCD++ inner iterations             (-T)
     float lambda = 0.1f;             // regulariser                        (-l)
-    float eps = 1e-3f;               // parsed, unused by either solver    (-e)
-    int do_predict = 0;              //                                    (-p)
-    int verbose = 0;                 //                                    (-q)
-    int do_nmf = 0;                  // parsed, unused by either solver    (-N)
+    float eps = 1e-3f;               // stop rule of CCDR1; acts only when -e is given (early_stop), inert in the reference (-e)
+    int do_predict = 0;              // prediction output + per-rank RMSE  (-p)
+    int verbose = 0;                 // per-rank report lines              (-q)
+    int do_nmf = 0;                  // non-negative factors: solved coordinates clamped at 0; inert in the reference (-N)
     bool enable_cuda = false;        //                                    (-CUDA)
     bool enable_omp = false;         //                                    (-OMP)
     unsigned nBlocks = 32;           // accepted for compatibility; launch geometry is chosen by the library
@@ -33,6 +33,8 @@ public:
     int device = 0;                  // CUDA device ordinal                (-device)
     int schedule = 0;                // 0 fused, 1 reference launch order  (-schedule)
     int layout = 0;                  // 0 panel, 1 direct                  (-layout)
+    int early_stop = 0;              // 1 when -e was given on the command line: the eps rule is active
+    bool load_model = false;         // predict-only: read <dir>/model, write <dir>/output       (-load)
 
     parameter() { std::snprintf(src_dir, sizeof(src_dir), "../data/simple"); }
 };

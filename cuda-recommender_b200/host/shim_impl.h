@@ -38,6 +38,10 @@ template <typename P>
 auto ext_layout(const P& p, int) -> decltype(p.layout) { return p.layout; }
 template <typename P>
 int ext_layout(const P&, long) { return 0; }
+template <typename P>
+auto ext_early_stop(const P& p, int) -> decltype(p.early_stop) { return p.early_stop; }
+template <typename P>
+int ext_early_stop(const P&, long) { return 0; }
 
 mf_params to_abi(const parameter& p, int solver) {
     mf_params q;
@@ -48,6 +52,7 @@ mf_params to_abi(const parameter& p, int solver) {
     q.nBlocks = p.nBlocks; q.nThreadsPerBlock = p.nThreadsPerBlock;
     // the reference's parameter class has no such members; this build's host/pmf.h does
     q.device = ext_device(p, 0); q.schedule = ext_schedule(p, 0); q.layout = ext_layout(p, 0);
+    q.early_stop = ext_early_stop(p, 0);  // the reference's -e stays inert (its main.cpp cannot set this)
     return q;
 }
 

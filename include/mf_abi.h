@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define MF_ABI_VERSION 2
+#define MF_ABI_VERSION 3
 
 enum {
     MF_OK = 0,
@@ -83,10 +83,10 @@ typedef struct mf_params {
     int32_t maxiter;           /* outer iterations       pmf.h:13 */
     int32_t maxinneriter;      /* CCD++ inner iterations pmf.h:14 */
     float lambda;              /*                        pmf.h:15 */
-    float eps;                 /* parsed, inert (as ref) pmf.h:16 */
-    int32_t do_predict;        /* parsed, inert          pmf.h:17 */
-    int32_t verbose;           /* parsed, inert          pmf.h:18 */
-    int32_t do_nmf;            /* parsed, inert (as ref) pmf.h:19 */
+    float eps;                 /* used only with early_stop = 1 (inert in the reference) pmf.h:16 */
+    int32_t do_predict;        /* with verbose: per-rank incremental test RMSE (the reference's commented-out block, CCD.cpp:141-148) pmf.h:17 */
+    int32_t verbose;           /* per-rank report lines "iter %d rank %d time %f [rmse %f]"  pmf.h:18 */
+    int32_t do_nmf;            /* 1: solved coordinates are clamped at 0 (inert in the reference; same as nmf_project) pmf.h:19 */
     uint32_t nBlocks;          /* accepted, ignored: geometry comes from the work partition  pmf.h:22 */
     uint32_t nThreadsPerBlock; /* accepted, ignored      pmf.h:23 */
     /* ---- extensions (zero = default) ---- */
@@ -101,7 +101,10 @@ typedef struct mf_params {
     int32_t pipeline;          /* MF_PIPELINE_* */
     int32_t timing_stride;     /* CCD++: per-launch events only on every timing_stride-th rank (0/1 = every rank) */
     int32_t pad_entries;       /* 0 = default (32): pieces are padded to a multiple of this many entries (8, 16, 32, 64) */
-    int32_t reserved[5];
+    int32_t early_stop;        /* 1: the -e rule of CCDR1 is active (single GPU, panel layout): the inner iterations of a rank end
+                                * after the one whose function decrease is below eps * (largest decrease seen so far); 0 (default):
+                                * eps is inert, exactly like the reference */
+    int32_t reserved[4];
 } mf_params;
 
 /* One line of the reference's per-iteration report (CCD_CUDA.cu:405, ALS_CUDA.cu:360). */
@@ -184,6 +187,16 @@ int mf_session_rmse(mf_session* s, double* rmse);
  * FP32 products summed in rank order in FP64 — the loop body of calculate_rmse_from_file, src/extras.cpp:165-168
  * (and of dot(), src/tools.cpp:184-198) — so the doubles are bit-identical to the CPU path's on the same factors. */
 int mf_session_predict(mf_session* s, int64_t n, const uint32_t* row, const uint32_t* col, double* out);
+/* CCD++, last outer iteration, k entries each (any pointer may be NULL): device seconds per rank and the incremental test
+ * RMSE after each rank — the reference's verbose block, src/CCD.cpp:141-148 with calrmse_r1, src/tools.cpp:260-270; both
+ * need verbose != 0, do_predict != 0 and a test set — and the inner iterations run per rank (< maxinneriter only with
+ * early_stop). */
+int mf_session_rank_stats(mf_session* s, double* seconds, double* rmse, int32_t* inner_iters);
+/* Predict-only path (no session): out[e] = w_row[e] . h_col[e] for a SAVED model, W [rows][k] and H [cols][k] row-major
+ * as save_mat_t / load_mat_t hold them (src/tools.cpp:90-153); host pointers; same arithmetic as mf_session_predict —
+ * the loop body of calculate_rmse_from_file, src/extras.cpp:143-180. */
+int mf_predict_pairs(const float* W, const float* H, int64_t rows, int64_t cols, int64_t k, int64_t n, const uint32_t* row,
+                     const uint32_t* col, double* out, int device);
 int mf_session_kernel_times(mf_session* s, mf_kernel_times* out);
 /* device seconds of the last iterate call, CUDA events on the session stream (RMSE excluded) */
 int mf_session_last_seconds(mf_session* s, double* seconds);

@@ -42,6 +42,11 @@ def lib():
         L.orc_ccdpp.argtypes = [C.c_long, C.c_long, u32p, u32p, f32p, u32p, u32p, f32p, f32p, f32p,
                                 C.c_long, C.c_float, C.c_int, C.c_int,
                                 C.c_long, u32p, u32p, f32p, f64p, C.c_int, C.c_int]
+        L.orc_ccdpp_ex.argtypes = [C.c_long, C.c_long, u32p, u32p, f32p, u32p, u32p, f32p, f32p, f32p,
+                                   C.c_long, C.c_float, C.c_int, C.c_int,
+                                   C.c_long, u32p, u32p, f32p, f64p, f64p, C.c_int, C.c_int, C.c_float,
+                                   np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")]
+        L.orc_ccdpp_ex.restype = None
         L.orc_als_half_step.argtypes = [C.c_long, u32p, u32p, f32p, f32p, f32p, C.c_long, C.c_float]
         L.orc_als_half_step.restype = C.c_long
         L.orc_als_half_step_f64.argtypes = L.orc_als_half_step.argtypes
@@ -124,6 +129,25 @@ def ccdpp(rows, cols, csr, csc, W, k, lam, maxiter, maxinner, test=None, f64acc=
                     Wf.reshape(-1), Hf.reshape(-1), k, lam, maxiter, maxinner,
                     nt, trow, tcol, tval, r, int(f64acc), threads)
     return dict(W=Wf, H=Hf, rmse=r[:maxiter], csr_val=csr_val, csc_val=csc_val)
+
+
+def ccdpp_ex(rows, cols, csr, csc, W, k, lam, maxiter, maxinner, test=None, nmf=False, early_stop=False, eps=1e-3):
+    """CCD++ with the options the reference parses but never acts on switched on (orc_ccdpp_ex): per-rank incremental
+    test RMSE (calrmse_r1), the non-negativity clamp and the -e stop rule.  Returns the dict of ccdpp plus
+    rank_rmse [maxiter, k] and inner_done [maxiter, k]."""
+    csr_ptr, csr_idx, csr_val = _u32(csr[0]), _u32(csr[1]), _f32(csr[2]).copy()
+    csc_ptr, csc_idx, csc_val = _u32(csc[0]), _u32(csc[1]), _f32(csc[2]).copy()
+    Wf = _f32(W).reshape(k, rows).copy()
+    Hf = np.zeros((k, cols), np.float32)
+    nt, trow, tcol, tval = _test_arrays(test)
+    r = np.zeros(max(maxiter, 1), np.float64)
+    rr = np.zeros(max(maxiter, 1) * k, np.float64)
+    done = np.zeros(max(maxiter, 1) * k, np.int32)
+    lib().orc_ccdpp_ex(rows, cols, csr_ptr, csr_idx, csr_val, csc_ptr, csc_idx, csc_val,
+                       Wf.reshape(-1), Hf.reshape(-1), k, lam, maxiter, maxinner,
+                       nt, trow, tcol, tval, r, rr, int(nmf), int(early_stop), eps, done)
+    return dict(W=Wf, H=Hf, rmse=r[:maxiter], csr_val=csr_val, csc_val=csc_val,
+                rank_rmse=rr.reshape(-1, k)[:maxiter], inner_done=done.reshape(-1, k)[:maxiter])
 
 
 def als_half_step(ptr, idx, val, Y, k, lam, f64=False):

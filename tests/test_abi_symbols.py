@@ -21,7 +21,7 @@ def test_header_library_and_binding_agree(pkg):
     for name in declared:
         assert hasattr(lib, name), f"libmfb200.so does not export {name}"
     assert sorted(pkg.ABI_SYMBOLS) == declared
-    assert lib.mf_abi_version() == 2
+    assert lib.mf_abi_version() == 3
 
 
 def test_params_default_matches_reference_defaults(pkg):

@@ -44,3 +44,23 @@ def test_f64_yardstick_is_close_to_reference(golden, port):
     relW = np.linalg.norm(hi["W"] - z["W_iter1"]) / np.linalg.norm(z["W_iter1"])
     relH = np.linalg.norm(hi["H"] - z["H_iter1"]) / np.linalg.norm(z["H_iter1"])
     assert relW < 1e-4 and relH < 1e-4
+
+
+def test_ccdpp_ex_with_options_off_is_ccdpp(port, data_factory):
+    """orc_ccdpp_ex (the checker of the §8 f4 options) with every option off is the pinned restatement, bit for bit; its
+    per-rank incremental RMSE ends every outer iteration on the iteration's RMSE (calrmse_r1 vs calrmse: FP32 drift only)."""
+    from conftest import sides
+    d = data_factory("ml100k")
+    csr, csc, test = sides(d)
+    k = 4
+    W0 = port.initial_col(k, d["rows"])
+    a = port.ccdpp(d["rows"], d["cols"], csr, csc, W0, k, 0.05, 3, 2, test=test)
+    b = port.ccdpp_ex(d["rows"], d["cols"], csr, csc, W0, k, 0.05, 3, 2, test=test)
+    for key in ("W", "H", "rmse", "csr_val", "csc_val"):
+        assert np.array_equal(a[key], b[key])
+    assert np.abs(b["rank_rmse"][:, -1] - b["rmse"]).max() < 1e-5
+    assert (b["inner_done"] == 2).all()
+    c = port.ccdpp_ex(d["rows"], d["cols"], csr, csc, W0, k, 0.05, 3, 6, test=test, early_stop=True, eps=1e-2)
+    assert c["inner_done"].sum() < 3 * k * 6 and c["inner_done"].min() >= 1
+    n = port.ccdpp_ex(d["rows"], d["cols"], csr, csc, W0 - 0.05, k, 0.05, 2, 2, test=test, nmf=True)
+    assert (n["W"] >= 0).all() and (n["H"] >= 0).all()
