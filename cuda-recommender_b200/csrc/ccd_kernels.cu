@@ -359,6 +359,35 @@ __device__ __forceinline__ bool ll_unpack_entries(const unsigned long long* ll, 
     return ok;
 }
 
+// Grid-wide barrier on a monotonic counter (every CTA of the launch is resident: one CTA per SM, checked with the occupancy
+// API at session creation, or enforced by a cooperative launch).  Bounded: a wait that does not complete (the device is
+// shared with another grid-barrier kernel, a lost peer) records a code in the session's status word and the kernel
+// returns; the host then reports MF_ERR_STATE — no trap, the CUDA context stays usable.
+__device__ __forceinline__ bool grid_barrier(unsigned* bar, unsigned target, unsigned* status, int* s_abort) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(bar, 1u);
+        unsigned v, spins = 0;
+        unsigned long long t0 = 0;
+        for (;;) {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+            if ((int)(v - target) >= 0) break;
+            if ((++spins & 0x3fffu) == 0u) {
+                const unsigned long long now = global_ns();
+                if (t0 == 0) t0 = now;
+                if (now - t0 > kWaitLimitNs || status_peek(status) != 0u) {
+                    atomicCAS(status, 0u, kStatusBarrierTimeout);
+                    *s_abort = 1;
+                    break;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    return *s_abort == 0;
+}
+
 // L2 prefetch of a stretch of the rating stream (TMA engine, no shared memory involved): `bytes` a multiple of 16
 __device__ __forceinline__ void l2_prefetch(const void* p, uint32_t bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
@@ -486,30 +515,16 @@ __global__ void __launch_bounds__(kSweepThreads, 1) k_panel_sweep(PanelSweepArgs
         if (a.fin.lanes == 32) finalize_load_meta<32>(a.fin.nseg, a.fin.slot_ptr, a.fin.seg_ptr, (int64_t)blockIdx.x * blockDim.x + threadIdx.x, meta);
         else finalize_load_meta<1>(a.fin.nseg, a.fin.slot_ptr, a.fin.seg_ptr, (int64_t)blockIdx.x * blockDim.x + threadIdx.x, meta);
         // grid-wide barrier (monotonic counter; every CTA of the launch is resident), then the CTAs share the segments
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            __threadfence();
-            atomicAdd(a.fin.bar, 1u);
-            unsigned v, spins = 0;
-            unsigned long long t0 = 0;
-            for (;;) {
-                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(a.fin.bar) : "memory");
-                if ((int)(v - a.fin.bar_target) >= 0) break;
-                if ((++spins & 0x3fffu) == 0u) {
-                    const unsigned long long now = global_ns();
-                    if (t0 == 0) t0 = now;
-                    if (now - t0 > kWaitLimitNs) __trap();
-                }
-            }
-        }
-        __syncthreads();
+        __shared__ int s_abort;
+        if (threadIdx.x == 0) s_abort = 0;
+        if (!grid_barrier(a.fin.bar, a.fin.bar_target, a.fin.status, &s_abort)) return;
         if (a.fin.lanes == 32)
             finalize_segments<32>(a.fin.nseg, a.fin.slot_ptr, a.partials, a.fin.seg_ptr, a.fin.lambda, a.fin.nmf, a.fin.out,
                                   a.fin.peer_ll, a.fin.vec_off, a.fin.rank, a.fin.nranks, a.fin.epoch, &meta);
         else
             finalize_segments<1>(a.fin.nseg, a.fin.slot_ptr, a.partials, a.fin.seg_ptr, a.fin.lambda, a.fin.nmf, a.fin.out,
                                  a.fin.peer_ll, a.fin.vec_off, a.fin.rank, a.fin.nranks, a.fin.epoch, &meta);
-        if (a.fin.ll != nullptr) ll_unpack_entries(a.fin.ll, a.fin.vec, a.fin.dim, a.fin.own_lo, a.fin.own_hi, a.fin.epoch);
+        if (a.fin.ll != nullptr) ll_unpack_entries(a.fin.ll, a.fin.vec, a.fin.dim, a.fin.own_lo, a.fin.own_hi, a.fin.epoch, a.fin.status);
     }
 }
 
@@ -524,31 +539,6 @@ __global__ void __launch_bounds__(kSweepThreads, 1) k_panel_sweep(PanelSweepArgs
 // item ranges and first panels of both copies are read once per launch, and a phase boundary costs two grid barriers.
 // The copy of v_t for the next outer iteration's add-back (v_old) rides on the last finalize of the rank.
 // =============================================================================================
-__device__ __forceinline__ bool grid_barrier(unsigned* bar, unsigned target, unsigned* status, int* s_abort) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        atomicAdd(bar, 1u);
-        unsigned v, spins = 0;
-        unsigned long long t0 = 0;
-        for (;;) {
-            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
-            if ((int)(v - target) >= 0) break;
-            if ((++spins & 0x3fffu) == 0u) {
-                const unsigned long long now = global_ns();
-                if (t0 == 0) t0 = now;
-                if (now - t0 > kWaitLimitNs || status_peek(status) != 0u) {
-                    atomicCAS(status, 0u, kStatusBarrierTimeout);
-                    *s_abort = 1;
-                    break;
-                }
-            }
-        }
-    }
-    __syncthreads();
-    return *s_abort == 0;
-}
-
 // The launch's arguments live in __constant__ memory (written by the host right before the launch): every device
 // function reads them as constant-bank operands, no registers.  That matters because the phases are OUT-OF-LINE calls:
 // with the sweep bodies inlined into the phase loop the compiler hoisted their loop-invariant address arithmetic out of
@@ -1384,30 +1374,16 @@ __global__ void __launch_bounds__(stream::kThreads, 1) k_panel_sweep_stream(Pane
     }
     if (SOLVE && a.fin.enabled) {
         // grid-wide barrier (monotonic counter; every CTA of the launch is resident), then the CTAs share the segments
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            __threadfence();
-            atomicAdd(a.fin.bar, 1u);
-            unsigned v, spins = 0;
-            unsigned long long t0 = 0;
-            for (;;) {
-                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(a.fin.bar) : "memory");
-                if ((int)(v - a.fin.bar_target) >= 0) break;
-                if ((++spins & 0x3fffu) == 0u) {
-                    const unsigned long long now = global_ns();
-                    if (t0 == 0) t0 = now;
-                    if (now - t0 > kWaitLimitNs) __trap();
-                }
-            }
-        }
-        __syncthreads();
+        __shared__ int s_abort;
+        if (threadIdx.x == 0) s_abort = 0;
+        if (!grid_barrier(a.fin.bar, a.fin.bar_target, a.fin.status, &s_abort)) return;
         if (a.fin.lanes == 32)
             finalize_segments<32>(a.fin.nseg, a.fin.slot_ptr, a.partials, a.fin.seg_ptr, a.fin.lambda, a.fin.nmf, a.fin.out,
                                   a.fin.peer_ll, a.fin.vec_off, a.fin.rank, a.fin.nranks, a.fin.epoch);
         else
             finalize_segments<1>(a.fin.nseg, a.fin.slot_ptr, a.partials, a.fin.seg_ptr, a.fin.lambda, a.fin.nmf, a.fin.out,
                                  a.fin.peer_ll, a.fin.vec_off, a.fin.rank, a.fin.nranks, a.fin.epoch);
-        if (a.fin.ll != nullptr) ll_unpack_entries(a.fin.ll, a.fin.vec, a.fin.dim, a.fin.own_lo, a.fin.own_hi, a.fin.epoch);
+        if (a.fin.ll != nullptr) ll_unpack_entries(a.fin.ll, a.fin.vec, a.fin.dim, a.fin.own_lo, a.fin.own_hi, a.fin.epoch, a.fin.status);
     }
 }
 

@@ -27,6 +27,7 @@ struct SweepFinalize {
     float* out;                          // this shard's block of the factor vector
     unsigned* bar;                       // grid barrier counter (monotonic)
     unsigned bar_target;                 // value of *bar once every CTA of this launch has arrived
+    unsigned* status;                    // session status word: a wait that times out records a code here and the kernel returns
     unsigned long long* const* peer_ll;  // multi-GPU push (nullptr: none), as FinalizePush
     int64_t vec_off;
     int rank, nranks;

@@ -93,8 +93,6 @@ struct Dist {
     // peer-to-peer exchange over NVLink (CUDA IPC mappings of every peer's factor buffers and flag words)
     bool p2p = false;
     std::vector<void*> opened;      // mappings to close
-    float** d_peerW = nullptr;      // [nranks] device array: W of every rank (own entry = own pointer)
-    float** d_peerH = nullptr;
     unsigned** d_peerFlags = nullptr;  // [nranks] device array: flag words of every rank
     unsigned* flags = nullptr;      // [nranks + 1] own flag words (flags[r] written by rank r) + block ticket
     unsigned long long* llW = nullptr;  // own low-latency receive buffers: one (value, epoch) word per factor entry
@@ -142,8 +140,16 @@ int dist_create(Dist** out, int rank, int nranks, const void* id128, int device)
 int dist_destroy(Dist* d) {
     if (!d) return MF_OK;
     for (void* p : d->opened) cudaIpcCloseMemHandle(p);
-    if (d->d_peerW) dev_free(d->d_peerW);
-    if (d->d_peerH) dev_free(d->d_peerH);
+    if (d->p2p && d->comm) {
+        // the exporter must not free a buffer a peer still has mapped (CUDA IPC: undefined behaviour): every rank has closed
+        // its imports above before any rank frees its exports below — a one-byte all-gather is the barrier (p2p is agreed
+        // across the ranks, so they all come here)
+        char* d_b = nullptr;
+        if (dev_alloc(&d_b, (size_t)d->nranks) == MF_OK) {
+            if (g_api.AllGather(d_b + d->rank, d_b, 1, ncclInt8, d->comm, nullptr) == ncclSuccess) cudaStreamSynchronize(nullptr);
+            dev_free(d_b);
+        }
+    }
     if (d->d_peerFlags) dev_free(d->d_peerFlags);
     if (d->flags) dev_free(d->flags);
     if (d->llW) dev_free(d->llW);
@@ -165,29 +171,32 @@ void dist_release_cached(int device) {
     }
 }
 
-// Maps every peer's W, H and flag words into this process (CUDA IPC over NVLink / NVSwitch) so that the finalize
-// kernel can store a freshly solved block straight into the peers' factor buffers (ccd_kernels.cu: k_finalize
-// push epilogue + k_exchange_wait).  The 64-byte IPC handles travel through one ncclAllGather.  Any failure
-// leaves p2p off and the NCCL broadcast path in use.
+// Maps every peer's low-latency receive buffers and flag words into this process (CUDA IPC over NVLink / NVSwitch) so that
+// the finalize can store a freshly solved block straight into the peers (ccd_kernels.cu).  The 64-byte IPC handles travel
+// through one ncclAllGather, and whether the peer-to-peer path is used at all is AGREED across the ranks: every rank takes
+// part in both collectives below whatever happened to it locally (MF_NO_P2P, no IPC support, a mapping that failed), and
+// the path is switched on only when every rank succeeded — a rank that silently stayed on NCCL while its peers pushed
+// LL words would hang the job.
 int dist_setup_p2p(Dist* d, float* W, float* H, int64_t ldm, int64_t ldn, cudaStream_t st) {
+    (void)W; (void)H;
     if (!d || d->nranks <= 1) return MF_OK;
-    if (getenv("MF_NO_P2P")) return MF_OK;
     const int P = d->nranks;
-    struct Handles { cudaIpcMemHandle_t w, h, f, lw, lh; };
-    static_assert(sizeof(Handles) == 320, "five 64-byte handles");
-    MF_TRY(dev_alloc(&d->flags, (size_t)P + 1));
-    MF_CUDA(cudaMemsetAsync(d->flags, 0, sizeof(unsigned) * ((size_t)P + 1), st));
-    MF_TRY(dev_alloc(&d->llW, (size_t)ldm));
-    MF_TRY(dev_alloc(&d->llH, (size_t)ldn));
-    MF_CUDA(cudaMemsetAsync(d->llW, 0, sizeof(unsigned long long) * (size_t)ldm, st));
-    MF_CUDA(cudaMemsetAsync(d->llH, 0, sizeof(unsigned long long) * (size_t)ldn, st));
+    struct Handles { cudaIpcMemHandle_t f, lw, lh; int ok; int pad[15]; };
+    static_assert(sizeof(Handles) == 256, "three 64-byte handles + a flag");
     Handles mine;
-    if (cudaIpcGetMemHandle(&mine.w, W) != cudaSuccess || cudaIpcGetMemHandle(&mine.h, H) != cudaSuccess ||
-        cudaIpcGetMemHandle(&mine.f, d->flags) != cudaSuccess || cudaIpcGetMemHandle(&mine.lw, d->llW) != cudaSuccess ||
-        cudaIpcGetMemHandle(&mine.lh, d->llH) != cudaSuccess) {
-        cudaGetLastError();
-        return MF_OK;  // no IPC on this system: stay on NCCL
+    memset(&mine, 0, sizeof(mine));
+    bool local_ok = getenv("MF_NO_P2P") == nullptr;
+    if (local_ok) {
+        local_ok = dev_alloc(&d->flags, (size_t)P + 1) == MF_OK && dev_alloc(&d->llW, (size_t)ldm) == MF_OK && dev_alloc(&d->llH, (size_t)ldn) == MF_OK &&
+                   cudaMemsetAsync(d->flags, 0, sizeof(unsigned) * ((size_t)P + 1), st) == cudaSuccess &&
+                   cudaMemsetAsync(d->llW, 0, sizeof(unsigned long long) * (size_t)ldm, st) == cudaSuccess &&
+                   cudaMemsetAsync(d->llH, 0, sizeof(unsigned long long) * (size_t)ldn, st) == cudaSuccess &&
+                   cudaIpcGetMemHandle(&mine.f, d->flags) == cudaSuccess && cudaIpcGetMemHandle(&mine.lw, d->llW) == cudaSuccess &&
+                   cudaIpcGetMemHandle(&mine.lh, d->llH) == cudaSuccess;
+        if (!local_ok) cudaGetLastError();
     }
+    mine.ok = local_ok ? 1 : 0;
+    // collective 1: everybody's handles and "I can export"
     Handles* d_all = nullptr;
     MF_TRY(dev_alloc(&d_all, (size_t)P));
     MF_CUDA(cudaMemcpyAsync(d_all + d->rank, &mine, sizeof(Handles), cudaMemcpyHostToDevice, st));
@@ -195,33 +204,38 @@ int dist_setup_p2p(Dist* d, float* W, float* H, int64_t ldm, int64_t ldn, cudaSt
     std::vector<Handles> all((size_t)P);
     MF_CUDA(cudaMemcpyAsync(all.data(), d_all, sizeof(Handles) * (size_t)P, cudaMemcpyDeviceToHost, st));
     MF_CUDA(cudaStreamSynchronize(st));
-    dev_free(d_all);
-    std::vector<float*> pw((size_t)P), ph((size_t)P);
+    bool everyone = true;
+    for (int r = 0; r < P; ++r) everyone = everyone && all[r].ok != 0;
     std::vector<unsigned*> pf((size_t)P);
     std::vector<unsigned long long*> plw((size_t)P), plh((size_t)P);
-    bool ok = true;
+    bool ok = everyone;
     for (int r = 0; r < P && ok; ++r) {
-        if (r == d->rank) { pw[r] = W; ph[r] = H; pf[r] = d->flags; plw[r] = d->llW; plh[r] = d->llH; continue; }
-        const cudaIpcMemHandle_t* hs[5] = {&all[r].w, &all[r].h, &all[r].f, &all[r].lw, &all[r].lh};
-        void* m[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-        for (int q = 0; q < 5 && ok; ++q) {
+        if (r == d->rank) { pf[r] = d->flags; plw[r] = d->llW; plh[r] = d->llH; continue; }
+        const cudaIpcMemHandle_t* hs[3] = {&all[r].f, &all[r].lw, &all[r].lh};
+        void* m[3] = {nullptr, nullptr, nullptr};
+        for (int q = 0; q < 3 && ok; ++q) {
             ok = cudaIpcOpenMemHandle(&m[q], *hs[q], cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
             if (ok) d->opened.push_back(m[q]);
         }
-        pw[r] = (float*)m[0]; ph[r] = (float*)m[1]; pf[r] = (unsigned*)m[2];
-        plw[r] = (unsigned long long*)m[3]; plh[r] = (unsigned long long*)m[4];
+        pf[r] = (unsigned*)m[0]; plw[r] = (unsigned long long*)m[1]; plh[r] = (unsigned long long*)m[2];
     }
-    if (!ok) {
-        cudaGetLastError();
+    if (!ok) cudaGetLastError();
+    // collective 2: "I could map everybody" — the path is on only if that holds on every rank
+    int* d_flag = reinterpret_cast<int*>(d_all);  // reuse: P ints fit in the handle table
+    const int my_flag = ok ? 1 : 0;
+    MF_CUDA(cudaMemcpyAsync(d_flag + d->rank, &my_flag, sizeof(int), cudaMemcpyHostToDevice, st));
+    MF_NCCL(g_api.AllGather(d_flag + d->rank, d_flag, sizeof(int), ncclInt8, d->comm, st));
+    std::vector<int> flags((size_t)P);
+    MF_CUDA(cudaMemcpyAsync(flags.data(), d_flag, sizeof(int) * (size_t)P, cudaMemcpyDeviceToHost, st));
+    MF_CUDA(cudaStreamSynchronize(st));
+    dev_free(d_all);
+    for (int r = 0; r < P; ++r) ok = ok && flags[r] != 0;
+    if (!ok) {  // somebody cannot: everybody stays on the NCCL broadcast path
         for (void* p : d->opened) cudaIpcCloseMemHandle(p);
         d->opened.clear();
-        return MF_OK;  // peers not reachable: stay on NCCL
+        return MF_OK;
     }
-    MF_TRY(dev_alloc(&d->d_peerW, (size_t)P));
-    MF_TRY(dev_alloc(&d->d_peerH, (size_t)P));
     MF_TRY(dev_alloc(&d->d_peerFlags, (size_t)P));
-    MF_CUDA(cudaMemcpy(d->d_peerW, pw.data(), sizeof(float*) * (size_t)P, cudaMemcpyHostToDevice));
-    MF_CUDA(cudaMemcpy(d->d_peerH, ph.data(), sizeof(float*) * (size_t)P, cudaMemcpyHostToDevice));
     MF_CUDA(cudaMemcpy(d->d_peerFlags, pf.data(), sizeof(unsigned*) * (size_t)P, cudaMemcpyHostToDevice));
     MF_TRY(dev_alloc(&d->d_peerLLW, (size_t)P));
     MF_TRY(dev_alloc(&d->d_peerLLH, (size_t)P));
@@ -233,8 +247,6 @@ int dist_setup_p2p(Dist* d, float* W, float* H, int64_t ldm, int64_t ldn, cudaSt
 
 bool dist_p2p(const Dist* d) { return d && d->p2p; }
 int dist_rank(const Dist* d) { return d ? d->rank : 0; }
-float* const* dist_peer_W(const Dist* d) { return d->d_peerW; }
-float* const* dist_peer_H(const Dist* d) { return d->d_peerH; }
 unsigned* const* dist_peer_flags(const Dist* d) { return d->d_peerFlags; }
 unsigned* dist_flags(const Dist* d) { return d->flags; }
 unsigned dist_next_epoch(Dist* d) { return ++d->epoch; }

@@ -12,6 +12,7 @@
 //      popcounts, and moves every entry to ptr[seg] + rank(minor key)
 // Step 3 makes the output independent of the arrival order of step 2.
 #include "common.cuh"
+#include "layout.cuh"
 
 namespace mf {
 namespace {
@@ -148,6 +149,12 @@ extern "C" int mf_build_csr_csc(int64_t rows, int64_t cols, int64_t nnz, const u
     copy(d_r, coo_row, sizeof(uint32_t) * (size_t)nnz);
     copy(d_c, coo_col, sizeof(uint32_t) * (size_t)nnz);
     copy(d_v, coo_val, sizeof(float) * (size_t)nnz);
+    if (rc == MF_OK) {  // the counting kernels index with these: they must be indices
+        bool ok_r = true, ok_c = true;
+        rc = check_below(d_r, nnz, (uint64_t)rows, &ok_r, nullptr);
+        if (rc == MF_OK) rc = check_below(d_c, nnz, (uint64_t)cols, &ok_c, nullptr);
+        if (rc == MF_OK && (!ok_r || !ok_c)) { set_error("mf_build_csr_csc: a %s index is outside the %lld x %lld matrix", ok_r ? "column" : "row", (long long)rows, (long long)cols); rc = MF_ERR_ARG; }
+    }
     if (rc == MF_OK) rc = build_one(rows, cols, nnz, d_r, d_c, d_v, d_ptr, d_idx, d_out, d_tmp_idx, d_tmp_val, d_count, d_scan, sms);
     copy(csr_row_ptr, d_ptr, sizeof(uint32_t) * ((size_t)rows + 1));
     copy(csr_col_idx, d_idx, sizeof(uint32_t) * (size_t)nnz);

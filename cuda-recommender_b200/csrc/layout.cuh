@@ -68,6 +68,7 @@ struct Side {
     uint32_t* item_perm = nullptr;      // [nitems] position in `items` of the j-th item in piece order (item_ptr numbering)
     int ncta = 0;
     bool sorted = true;
+    uint32_t* unsort_perm = nullptr;  // [nnz] only when the caller's segments were not index-sorted: caller position of entry i
     // ALS work list (als.cu, built on first use): items sorted longest-first, long segments split into parts
     void* als_items = nullptr;        // AlsItem[als_nitems]
     int64_t als_nitems = 0;
@@ -82,7 +83,13 @@ int side_build_panels(Side& s, int panel_rows, int chunk, int ncta, cudaStream_t
 // dst_raw[nnz] <- current panel values in the caller's order; and the inverse
 int side_panel_to_raw(const Side& s, float* dst_raw, cudaStream_t st);
 int side_raw_to_panel(Side& s, const float* src_raw, cudaStream_t st);
-// returns 1 in *sorted when every segment's indices are strictly ascending
-int side_check_sorted(const Side& s, bool* sorted, cudaStream_t st);
+// *sorted: every segment's indices are strictly ascending; *in_range: every index is below gdim
+int side_check_sorted(const Side& s, bool* sorted, bool* in_range, cudaStream_t st);
+// sorts the segments of the caller-order arrays by index (host side; rare path), keeps the permutation in s.unsort_perm
+int side_sort_segments(Side& s, cudaStream_t st);
+// *ok = every d_a[i] < bound (device array)
+int check_below(const uint32_t* d_a, int64_t n, uint64_t bound, bool* ok, cudaStream_t st);
+// dst[perm[i]] = src[i]
+int scatter_by_perm(const uint32_t* perm, const float* src, float* dst, int64_t n, cudaStream_t st);
 
 }  // namespace mf

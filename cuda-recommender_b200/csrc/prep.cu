@@ -5,6 +5,10 @@
 // src/tools.cpp:58-59, src/pmf_util.h:108-136).
 #include "layout.cuh"
 
+#include <algorithm>
+#include <thread>
+#include <vector>
+
 namespace mf {
 namespace {
 
@@ -252,11 +256,24 @@ __global__ void k_check_sorted(int64_t nseg, const uint32_t* __restrict__ ptr, c
         bool b = false;
         for (uint32_t e = lo + lane; e < hi; e += 32) {
             uint32_t v = idx[e];
-            if (v >= gdim) b = true;
-            if (e + 1 < hi && v >= idx[e + 1]) b = true;
+            if (v >= gdim) atomicOr(bad, 2);                       // not an index at all
+            if (e + 1 < hi && v >= idx[e + 1]) b = true;           // out of order (or a duplicate)
         }
-        if (b) *bad = 1;
+        if (b) atomicOr(bad, 1);
     }
+}
+
+// bad |= 1 when any a[i] >= bound (test pairs, prediction pairs, COO indices)
+__global__ void k_check_below(int64_t n, const uint32_t* __restrict__ a, uint32_t bound, int* __restrict__ bad) {
+    bool b = false;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        if (a[i] >= bound) b = true;
+    if (b) *bad = 1;
+}
+
+// dst[perm[i]] = src[i]
+__global__ void k_scatter_perm(int64_t n, const uint32_t* __restrict__ perm, const float* __restrict__ src, float* __restrict__ dst) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) dst[perm[i]] = src[i];
 }
 
 __global__ void k_degree_bins(int64_t nseg, const uint32_t* __restrict__ ptr, unsigned long long* __restrict__ seg_in_bin,
@@ -298,14 +315,72 @@ inline unsigned grid_for(int64_t n, int block) { return (unsigned)((n + block - 
 
 int side_free(Side& s) {
     void* ptrs[] = {s.ptr, s.idx, s.val, s.piece_ptr, s.piece_first, s.item_ptr, s.idx16, s.pval, s.items,
-                    s.slot_ptr, s.partials, s.cta_item_ptr, s.cta_start_ptr, s.panel_item_ptr, s.item_perm, s.als_items, s.als_queue, s.als_counters, s.als_partial};
+                    s.slot_ptr, s.partials, s.cta_item_ptr, s.cta_start_ptr, s.panel_item_ptr, s.item_perm, s.unsort_perm, s.als_items, s.als_queue, s.als_counters, s.als_partial};
     for (void* p : ptrs)
         if (p) dev_free(p);
     s = Side();
     return MF_OK;
 }
 
-int side_check_sorted(const Side& s, bool* sorted, cudaStream_t st) {
+int check_below(const uint32_t* d_a, int64_t n, uint64_t bound, bool* ok, cudaStream_t st) {
+    *ok = true;
+    if (n <= 0 || bound > 0xffffffffull) return MF_OK;
+    int* d_bad = nullptr;
+    MF_TRY(dev_alloc(&d_bad, 1));
+    MF_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int), st));
+    k_check_below<<<148 * 4, 256, 0, st>>>(n, d_a, (uint32_t)bound, d_bad);
+    int h = 0;
+    MF_CUDA(cudaMemcpyAsync(&h, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st));
+    MF_CUDA(cudaStreamSynchronize(st));
+    dev_free(d_bad);
+    *ok = h == 0;
+    return MF_OK;
+}
+
+int scatter_by_perm(const uint32_t* perm, const float* src, float* dst, int64_t n, cudaStream_t st) {
+    if (n <= 0) return MF_OK;
+    k_scatter_perm<<<148 * 8, 256, 0, st>>>(n, perm, src, dst);
+    MF_CUDA(cudaGetLastError());
+    return MF_OK;
+}
+
+// Sorts every segment of a caller-order copy by index (the reference never asks for sorted segments, the panel cut does):
+// done on the host, one thread per stretch of segments — an input that needs it is rare (the reference's files and this
+// repo's builder are sorted) and it is paid once per session.  s.unsort_perm[i] = caller position of sorted entry i, so
+// that values can still be returned in the caller's order.
+int side_sort_segments(Side& s, cudaStream_t st) {
+    const size_t n = (size_t)s.nnz;
+    std::vector<uint32_t> ptr((size_t)s.nseg + 1), idx(n), perm(n);
+    std::vector<float> val(n);
+    MF_CUDA(cudaMemcpyAsync(ptr.data(), s.ptr, sizeof(uint32_t) * ptr.size(), cudaMemcpyDeviceToHost, st));
+    MF_CUDA(cudaMemcpyAsync(idx.data(), s.idx, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, st));
+    MF_CUDA(cudaMemcpyAsync(val.data(), s.val, sizeof(float) * n, cudaMemcpyDeviceToHost, st));
+    MF_CUDA(cudaStreamSynchronize(st));
+    std::vector<uint32_t> idx2(n);
+    std::vector<float> val2(n);
+    const unsigned nthreads = std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+    std::vector<std::thread> pool;
+    for (unsigned w = 0; w < nthreads; ++w)
+        pool.emplace_back([&, w]() {
+            std::vector<uint32_t> order;
+            for (int64_t sg = w; sg < s.nseg; sg += nthreads) {
+                const uint32_t lo = ptr[sg], hi = ptr[sg + 1];
+                order.resize(hi - lo);
+                for (uint32_t e = lo; e < hi; ++e) order[e - lo] = e;
+                std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return idx[a] < idx[b]; });
+                for (uint32_t e = lo; e < hi; ++e) { idx2[e] = idx[order[e - lo]]; val2[e] = val[order[e - lo]]; perm[e] = order[e - lo]; }
+            }
+        });
+    for (auto& t : pool) t.join();
+    MF_TRY(dev_alloc(&s.unsort_perm, n));
+    MF_CUDA(cudaMemcpyAsync(s.idx, idx2.data(), sizeof(uint32_t) * n, cudaMemcpyHostToDevice, st));
+    MF_CUDA(cudaMemcpyAsync(s.val, val2.data(), sizeof(float) * n, cudaMemcpyHostToDevice, st));
+    MF_CUDA(cudaMemcpyAsync(s.unsort_perm, perm.data(), sizeof(uint32_t) * n, cudaMemcpyHostToDevice, st));
+    MF_CUDA(cudaStreamSynchronize(st));
+    return MF_OK;
+}
+
+int side_check_sorted(const Side& s, bool* sorted, bool* in_range, cudaStream_t st) {
     int* d_bad = nullptr;
     MF_TRY(dev_alloc(&d_bad, 1));
     MF_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int), st));
@@ -317,7 +392,8 @@ int side_check_sorted(const Side& s, bool* sorted, cudaStream_t st) {
     MF_CUDA(cudaMemcpyAsync(&h, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st));
     MF_CUDA(cudaStreamSynchronize(st));
     dev_free(d_bad);
-    *sorted = (h == 0);
+    *sorted = (h & 1) == 0;
+    *in_range = (h & 2) == 0;
     return MF_OK;
 }
 

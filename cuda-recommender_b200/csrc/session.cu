@@ -175,8 +175,7 @@ int run_sweep(mf_session* s, Side& sd, int mode, const SweepVectors& v, float* o
             f.lanes = panel_finalize_lanes(sd.nseg, sd.nslots);
             f.nseg = sd.nseg; f.slot_ptr = sd.slot_ptr; f.seg_ptr = sd.ptr;
             f.lambda = s->prm.lambda; f.nmf = nmf; f.out = out + sd.seg_offset;
-            s->gridbar_total += (unsigned)sd.ncta;
-            f.bar = s->d_gridbar; f.bar_target = s->gridbar_total;
+            f.bar = s->d_gridbar; f.bar_target = s->gridbar_total + (unsigned)sd.ncta; f.status = s->d_gridbar + 1;
             f.peer_ll = push ? fp.peer_ll : nullptr;
             f.vec_off = sd.seg_offset; f.rank = s->rank; f.nranks = s->nranks; f.epoch = push ? fp.epoch : 0u;
             f.ll = push ? dist_ll(s->dist, is_h) : nullptr;  // receive the peers' blocks in the same launch
@@ -185,6 +184,7 @@ int run_sweep(mf_session* s, Side& sd, int mode, const SweepVectors& v, float* o
         if (sd.nitems > 0) {
             s->timer.start(family_of(mode));
             MF_TRY(panel_sweep(mode, a, sd.ncta, s->prm.pipeline == MF_PIPELINE_REGISTERS ? panel_sweep_threads() : 1024, sd.chunk, s->prm.pipeline, s->st));
+            if (in_kernel) s->gridbar_total += (unsigned)sd.ncta;  // only once the launch has been accepted
             s->timer.stop();
         }
         if (solve) {
@@ -441,7 +441,7 @@ void fold_stamps(mf_session* s, bool add, bool had_pending) {
 
 // after a synchronisation: did a device-side wait time out?  (persistent kernel; status word next to the barrier counter)
 int check_device_status(mf_session* s) {
-    if (!s->persistent) return MF_OK;
+    if (!s->panel || !s->d_gridbar) return MF_OK;
     unsigned st = 0;
     MF_CUDA(cudaMemcpy(&st, s->d_gridbar + 1, sizeof(unsigned), cudaMemcpyDeviceToHost));
     if (st == 0) return MF_OK;
@@ -561,6 +561,10 @@ int create_impl(const mf_ratings* R, const mf_testset* T, const mf_params* param
                   cp[R->cols], (long long)R->nnz);
         return fail(MF_ERR_ARG);
     }
+    if (!std::is_sorted(rp.begin(), rp.end()) || !std::is_sorted(cp.begin(), cp.end())) {
+        set_error("ptr arrays must be non-decreasing");
+        return fail(MF_ERR_ARG);
+    }
     partition_host(rp, nranks, s->row_bound);
     partition_host(cp, nranks, s->col_bound);
     {   // one device arena for this shard's ratings and layout arrays: ~36 B per rating (two raw copies, two panel
@@ -593,12 +597,13 @@ int create_impl(const mf_ratings* R, const mf_testset* T, const mf_params* param
     const bool ccd = params->solver_type == MF_SOLVER_CCD;
     if (ccd) {
         s->panel = params->layout == MF_LAYOUT_PANEL;
-        bool ok_r = true, ok_c = true;
-        if (s->panel) {
-            if ((rc = side_check_sorted(s->csc, &ok_c, s->st)) != MF_OK) return fail_up(rc);
-            if (!ok_c) s->panel = false;  // the panel cut needs ascending indices inside a segment
-            trace_mark("  sortedness check (CSC)");
-        }
+        bool ok_r = true, ok_c = true, range_r = true, range_c = true;
+        // every index must be an index (both layouts gather with it); the panel cut also needs them ascending inside a
+        // segment — the reference does not, so a copy that is not sorted is sorted here, once, instead of being refused
+        if ((rc = side_check_sorted(s->csc, &ok_c, &range_c, s->st)) != MF_OK) return fail_up(rc);
+        if (!range_c) { set_error("CSC copy: a row index is >= rows (%lld)", (long long)R->rows); return fail_up(MF_ERR_ARG); }
+        if (s->panel && !ok_c && (rc = side_sort_segments(s->csc, s->st)) != MF_OK) return fail_up(rc);
+        trace_mark("  index check (CSC)");
         if (s->panel) {
             // Panel size.  Shared memory a sweep needs: CSC side up to 2 vectors (u_new, u_old), CSR side up to 3
             // (v_new, v_add, v_old).  Measured (profiles/README.md): panels that fill shared memory leave the SM
@@ -626,16 +631,18 @@ int create_impl(const mf_ratings* R, const mf_testset* T, const mf_params* param
             s->csr.pad = pick_pad(s->csr, pr_r);
             if ((rc = side_build_panels(s->csc, pr_c, chunk, s->sm_count, s->st)) != MF_OK) return fail_up(rc);
             if ((rc = csr_arrived()) != MF_OK) return fail_up(rc);
-            if ((rc = side_check_sorted(s->csr, &ok_r, s->st)) != MF_OK) return fail_up(rc);
-            if (ok_r) {
-                if ((rc = side_build_panels(s->csr, pr_r, chunk, s->sm_count, s->st)) != MF_OK) return fail_up(rc);
-                trace_mark("  build both panel layouts");
-                // the caller-order index/value arrays are no longer needed: the residual lives in the panel arrays
-                dev_free(s->csc.idx); s->csc.idx = nullptr; dev_free(s->csc.val); s->csc.val = nullptr;
-                dev_free(s->csr.idx); s->csr.idx = nullptr; dev_free(s->csr.val); s->csr.val = nullptr;
-            } else {
-                s->panel = false;  // DIRECT layout on the caller's arrays; the CSC panel arrays stay unused until destroy
-            }
+            if ((rc = side_check_sorted(s->csr, &ok_r, &range_r, s->st)) != MF_OK) return fail_up(rc);
+            if (!range_r) { set_error("CSR copy: a column index is >= cols (%lld)", (long long)R->cols); return fail_up(MF_ERR_ARG); }
+            if (!ok_r && (rc = side_sort_segments(s->csr, s->st)) != MF_OK) return fail_up(rc);
+            if ((rc = side_build_panels(s->csr, pr_r, chunk, s->sm_count, s->st)) != MF_OK) return fail_up(rc);
+            trace_mark("  build both panel layouts");
+            // the caller-order index/value arrays are no longer needed: the residual lives in the panel arrays
+            dev_free(s->csc.idx); s->csc.idx = nullptr; dev_free(s->csc.val); s->csc.val = nullptr;
+            dev_free(s->csr.idx); s->csr.idx = nullptr; dev_free(s->csr.val); s->csr.val = nullptr;
+        } else {
+            if ((rc = csr_arrived()) != MF_OK) return fail_up(rc);
+            if ((rc = side_check_sorted(s->csr, &ok_r, &range_r, s->st)) != MF_OK) return fail_up(rc);
+            if (!range_r) { set_error("CSR copy: a column index is >= cols (%lld)", (long long)R->cols); return fail_up(MF_ERR_ARG); }
         }
         if ((rc = csr_arrived()) != MF_OK) return fail_up(rc);
         trace_mark("sortedness + panel layout");
@@ -653,6 +660,12 @@ int create_impl(const mf_ratings* R, const mf_testset* T, const mf_params* param
         }
     } else {
         if ((rc = csr_arrived()) != MF_OK) return fail_up(rc);
+        {   // ALS gathers factor rows with the indices: they must be indices
+            bool sorted = true, in_c = true, in_r = true;
+            if ((rc = side_check_sorted(s->csc, &sorted, &in_c, s->st)) != MF_OK) return fail_up(rc);
+            if ((rc = side_check_sorted(s->csr, &sorted, &in_r, s->st)) != MF_OK) return fail_up(rc);
+            if (!in_c || !in_r) { set_error("%s copy: an index is outside the %lld x %lld matrix", in_c ? "CSR" : "CSC", (long long)R->rows, (long long)R->cols); return fail_up(MF_ERR_ARG); }
+        }
         if (nranks > 1) arena_bind(nullptr);
         s->ldm = s->k; s->ldn = s->k;
         if ((rc = dev_alloc(&s->W, (size_t)s->rows * s->k)) != MF_OK) return fail_up(rc);
@@ -676,6 +689,10 @@ int create_impl(const mf_ratings* R, const mf_testset* T, const mf_params* param
         if ((rc = upload_bytes(s->trow, T->row, sizeof(uint32_t) * (size_t)s->nt, s->st)) != MF_OK) return fail(rc);
         if ((rc = upload_bytes(s->tcol, T->col, sizeof(uint32_t) * (size_t)s->nt, s->st)) != MF_OK) return fail(rc);
         if ((rc = upload_bytes(s->tval, T->val, sizeof(float) * (size_t)s->nt, s->st)) != MF_OK) return fail(rc);
+        bool ok_row = true, ok_col = true;
+        if ((rc = check_below(s->trow, s->nt, (uint64_t)s->rows, &ok_row, s->st)) != MF_OK) return fail(rc);
+        if ((rc = check_below(s->tcol, s->nt, (uint64_t)s->cols, &ok_col, s->st)) != MF_OK) return fail(rc);
+        if (!ok_row || !ok_col) { set_error("test set: a %s index is outside the %lld x %lld matrix", ok_row ? "column" : "row", (long long)s->rows, (long long)s->cols); return fail(MF_ERR_ARG); }
     }
     if (ccd) {
         if (s->prm.do_nmf) s->prm.nmf_project = 1;  // -N: the clamp of the finalize (inert in the reference, src/pmf.h:36)
@@ -872,9 +889,15 @@ int mf_session_get_values(mf_session* s, float* csr_val, float* csc_val) {
             float* tmp = nullptr;
             MF_TRY(dev_alloc(&tmp, (size_t)sd.nnz));
             int rc = side_panel_to_raw(sd, tmp, s->st);
-            if (rc == MF_OK && cudaMemcpyAsync(dsts[i], tmp, sizeof(float) * (size_t)sd.nnz, cudaMemcpyDefault, s->st) != cudaSuccess) rc = MF_ERR_CUDA;
+            float* tmp2 = nullptr;
+            if (rc == MF_OK && sd.unsort_perm) {  // the segments were sorted on upload: back to the caller's order
+                rc = dev_alloc(&tmp2, (size_t)sd.nnz);
+                if (rc == MF_OK) rc = scatter_by_perm(sd.unsort_perm, tmp, tmp2, sd.nnz, s->st);
+            }
+            if (rc == MF_OK && cudaMemcpyAsync(dsts[i], tmp2 ? tmp2 : tmp, sizeof(float) * (size_t)sd.nnz, cudaMemcpyDefault, s->st) != cudaSuccess) rc = MF_ERR_CUDA;
             cudaStreamSynchronize(s->st);
             dev_free(tmp);
+            if (tmp2) dev_free(tmp2);
             MF_TRY(rc);
         } else {
             MF_CUDA(cudaMemcpyAsync(dsts[i], sd.val, sizeof(float) * (size_t)sd.nnz, cudaMemcpyDefault, s->st));
@@ -908,6 +931,12 @@ int mf_session_predict(mf_session* s, int64_t n, const uint32_t* row, const uint
     if (rc == MF_OK) {
         cuda_ok(cudaMemcpyAsync(d_row, row, sizeof(uint32_t) * (size_t)n, cudaMemcpyDefault, s->st));
         cuda_ok(cudaMemcpyAsync(d_col, col, sizeof(uint32_t) * (size_t)n, cudaMemcpyDefault, s->st));
+    }
+    if (rc == MF_OK) {
+        bool ok_row = true, ok_col = true;
+        rc = check_below(d_row, n, (uint64_t)s->rows, &ok_row, s->st);
+        if (rc == MF_OK) rc = check_below(d_col, n, (uint64_t)s->cols, &ok_col, s->st);
+        if (rc == MF_OK && (!ok_row || !ok_col)) { set_error("mf_session_predict: a pair is outside the %lld x %lld matrix", (long long)s->rows, (long long)s->cols); rc = MF_ERR_ARG; }
     }
     if (rc == MF_OK) {
         if (s->prm.solver_type == MF_SOLVER_ALS)
@@ -1005,6 +1034,7 @@ int mf_session_ccdpp_iterate(mf_session* s, int n_outer, mf_iter_stats* stats) {
         MF_CUDA(cudaEventElapsedTime(&ms, s->ev_a, s->ev_b));
         total = ms * 1e-3;
         s->timer.collect(s->fam_seconds, s->fam_launches);
+        MF_TRY(check_device_status(s));
         s->last_seconds = total;
         {
             char msg[256];
@@ -1036,10 +1066,8 @@ int mf_session_ccdpp_iterate(mf_session* s, int n_outer, mf_iter_stats* stats) {
                 s->rank_rmse[t] = sqrt(acc[t] / (double)s->nt);
             }
         }
-        if (persist) {
-            MF_TRY(check_device_status(s));
-            if (timing_on) fold_stamps(s, add, had_pending);
-        }
+        MF_TRY(check_device_status(s));
+        if (persist && timing_on) fold_stamps(s, add, had_pending);
         if (stats) {
             mf_iter_stats& o = stats[it];
             const double upd = s->fam_seconds[F_UPDATE] - before[F_UPDATE];
@@ -1105,6 +1133,9 @@ int mf_session_ccd_solve(mf_session* s, int t, int side) {
     if (s->prm.solver_type != MF_SOLVER_CCD) { set_error("not a CCD++ session"); return MF_ERR_STATE; }
     MF_CUDA(cudaSetDevice(s->device));
     MF_TRY(flush_pending(s));
+    // multi-GPU: a step-level call may solve the same side twice in a row; the receive words of that side must not be
+    // overwritten while a slower peer still polls them for the previous call
+    MF_TRY(exchange_barrier(s));
     SweepVectors a;
     if (side == MF_SIDE_CSC) { a.g_new = s->W + (int64_t)t * s->ldm; MF_TRY(solve_v(s, t, kSolve, a)); }
     else                     { a.g_new = s->H + (int64_t)t * s->ldn; MF_TRY(solve_u(s, t, kSolve, a)); }

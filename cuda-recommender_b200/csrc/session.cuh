@@ -87,14 +87,12 @@ int dist_unique_id(void* id128);
 int dist_create(Dist** out, int rank, int nranks, const void* id128, int device);
 int dist_destroy(Dist* d);
 void dist_release_cached(int device);  // destroys the communicators kept between sessions
-// optional NVLink peer-to-peer exchange (CUDA IPC); falls back to NCCL silently when unavailable
+// optional NVLink peer-to-peer exchange (CUDA IPC); all ranks agree on it, and fall back to NCCL together when unavailable
 int dist_setup_p2p(Dist* d, float* W, float* H, int64_t ldm, int64_t ldn, cudaStream_t st);
 unsigned long long* const* dist_peer_ll(const Dist* d, bool h);
 unsigned long long* dist_ll(const Dist* d, bool h);
 bool dist_p2p(const Dist* d);
 int dist_rank(const Dist* d);
-float* const* dist_peer_W(const Dist* d);
-float* const* dist_peer_H(const Dist* d);
 unsigned* const* dist_peer_flags(const Dist* d);
 unsigned* dist_flags(const Dist* d);
 unsigned dist_next_epoch(Dist* d);

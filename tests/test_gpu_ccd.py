@@ -190,7 +190,7 @@ def test_csr_and_csc_residual_copies_stay_bit_identical(gpu, port, data_factory)
 
 
 def test_edge_cases(gpu, port, datagen):
-    # empty rows and columns, a 1-entry row, a dense row, k=1, T=1; unsorted input falls back to DIRECT
+    # empty rows and columns, a 1-entry row, a dense row, k=1, T=1; unsorted input is sorted on upload
     rows, cols = 40, 30
     r = np.array([0, 0, 0, 5, 7, 7, 39] + [12] * cols, np.uint32)
     c = np.array([0, 3, 29, 4, 4, 9, 0] + list(range(cols)), np.uint32)

@@ -144,3 +144,75 @@ def test_cli_nmf_and_eps_flags(gpu, datagen, data_factory, tmp_path):
     stop = _run(base + ["-e", "0.05", str(tmp_path)])
     for o in (plain, nmf, stop):
         assert "FAILED" not in o and re.search(r"Test RMSE = [\d.]+", o), o
+
+
+def _shuffled(d, seed=3):
+    """The same matrix with the entries of every row / column in random order (the reference never asks for sorted ones)."""
+    rng = np.random.default_rng(seed)
+    d2 = dict(d)
+    for side in ("csr", "csc"):
+        ptr = d[side + "_ptr"].astype(np.int64)
+        idx, val = d[side + "_idx"].copy(), d[side + "_val"].copy()
+        for s in range(len(ptr) - 1):
+            p = rng.permutation(ptr[s + 1] - ptr[s]) + ptr[s]
+            idx[ptr[s]:ptr[s + 1]], val[ptr[s]:ptr[s + 1]] = idx[p], val[p]
+        d2[side + "_idx"], d2[side + "_val"] = idx, val
+    return d2
+
+
+def test_unsorted_segments_are_sorted_on_upload_not_degraded(gpu, port, data_factory):
+    """Segments that are not index-sorted are sorted once at session creation and still get the panel layout: the factors
+    are the sorted input's, bit for bit, and the residual comes back in the CALLER's order."""
+    d = data_factory("small")
+    d2 = _shuffled(d)
+    k = 4
+    W0 = port.initial_col(k, d["rows"])
+    outs = []
+    for data in (d, d2):
+        with gpu.Session(data, gpu.make_params(k=k, lam=0.05, maxinner=2)) as s:
+            s.set_factors(W0)
+            s.iterate(2)
+            assert s.panel_layout(gpu.SIDE_CSC)["n_items"] > 0  # the panel layout, not the caller-order fallback
+            outs.append(s.get_factors() + s.get_values())
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+    for side, got_sorted, got_shuffled in (("csr", outs[0][2], outs[1][2]), ("csc", outs[0][3], outs[1][3])):
+        ptr = d[side + "_ptr"].astype(np.int64)
+        for s_ in range(len(ptr) - 1):
+            lo, hi = ptr[s_], ptr[s_ + 1]
+            order = np.argsort(d2[side + "_idx"][lo:hi], kind="stable")
+            assert np.array_equal(got_shuffled[lo:hi][order], got_sorted[lo:hi])
+
+
+def test_bad_input_is_refused(gpu, port, data_factory):
+    d = data_factory("small")
+    p = gpu.make_params(k=3, lam=0.05, maxinner=1)
+    for solver in (gpu.SOLVER_CCD, gpu.SOLVER_ALS):
+        for layout in ((0, 1) if solver == gpu.SOLVER_CCD else (0,)):
+            q = gpu.make_params(solver=solver, k=3, lam=0.05, maxinner=1, layout=layout)
+            bad = dict(d)
+            bad["csc_idx"] = d["csc_idx"].copy()
+            bad["csc_idx"][7] = d["rows"] + 5           # not a row
+            with pytest.raises(gpu.MFError, match="index"):
+                gpu.Session(bad, q)
+            bad = dict(d)
+            bad["csr_idx"] = d["csr_idx"].copy()
+            bad["csr_idx"][-1] = 0xfffffff0             # not a column
+            with pytest.raises(gpu.MFError, match="index"):
+                gpu.Session(bad, q)
+    bad = dict(d)
+    bad["csr_ptr"] = d["csr_ptr"].copy()
+    bad["csr_ptr"][5], bad["csr_ptr"][6] = d["csr_ptr"][6], d["csr_ptr"][5] - 1 if d["csr_ptr"][5] else 0
+    if not np.all(np.diff(bad["csr_ptr"].astype(np.int64)) >= 0):
+        with pytest.raises(gpu.MFError, match="non-decreasing"):
+            gpu.Session(bad, p)
+    bad = dict(d)
+    bad["test_col"] = d["test_col"].copy()
+    bad["test_col"][0] = d["cols"]
+    with pytest.raises(gpu.MFError, match="test set"):
+        gpu.Session(bad, p)
+    with gpu.Session(d, p) as s:
+        s.set_factors(port.initial_col(3, d["rows"]))
+        with pytest.raises(gpu.MFError, match="outside"):
+            s.predict(np.array([0, d["rows"]], np.uint32), np.array([0, 0], np.uint32))
+    with pytest.raises(gpu.MFError, match="outside"):
+        gpu.build_csr_csc(4, 4, np.array([0, 4], np.uint32), np.array([1, 1], np.uint32), np.array([1, 2], np.float32))
