@@ -503,12 +503,22 @@ __global__ void __launch_bounds__(kSweepThreads, 1) k_panel_sweep(PanelSweepArgs
     extern __shared__ __align__(16) float smem[];
     __shared__ unsigned s_ctr;
     pdl_launch_dependents();
+    const bool tracing = a.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+    if (tracing) a.trace[0] = global_ns();
     const uint32_t ib = a.cta_item_ptr[blockIdx.x];
     const uint32_t ie = a.cta_item_ptr[blockIdx.x + 1];
     const int p = first_panel(a.panel_item_ptr, a.npanels, ib);
     const uint32_t pend0 = p < a.npanels ? a.panel_item_ptr[p + 1] : 0u;
     pdl_wait();  // everything below reads what the previous sweep wrote (factor vectors, residual) or writes what it read
+    if (tracing) a.trace[1] = global_ns();
+    if (a.trace_cta != nullptr && threadIdx.x == 0) a.trace_cta[4 * blockIdx.x + 0] = global_ns();
     sweep_cta_range<MODE>(LaunchView{a}, smem, &s_ctr, ib, ie, p, threadIdx.x, blockDim.x, pend0);
+    if (tracing) { a.trace[2] = global_ns(); a.trace[6] = (unsigned long long)MODE; }
+    if (a.trace_cta != nullptr && threadIdx.x == 0) {
+        a.trace_cta[4 * blockIdx.x + 1] = global_ns();
+        a.trace_cta[4 * blockIdx.x + 2] = ((unsigned long long)ib << 32) | ie;
+        a.trace_cta[4 * blockIdx.x + 3] = (unsigned long long)p;
+    }
     if (SOLVE && a.fin.enabled) {
         // the first finalize round's segment metadata is on its way while the grid assembles at the barrier
         FinalizeMeta meta;
@@ -518,13 +528,16 @@ __global__ void __launch_bounds__(kSweepThreads, 1) k_panel_sweep(PanelSweepArgs
         __shared__ int s_abort;
         if (threadIdx.x == 0) s_abort = 0;
         if (!grid_barrier(a.fin.bar, a.fin.bar_target, a.fin.status, &s_abort)) return;
+        if (tracing) a.trace[3] = global_ns();
         if (a.fin.lanes == 32)
             finalize_segments<32>(a.fin.nseg, a.fin.slot_ptr, a.partials, a.fin.seg_ptr, a.fin.lambda, a.fin.nmf, a.fin.out,
                                   a.fin.peer_ll, a.fin.vec_off, a.fin.rank, a.fin.nranks, a.fin.epoch, &meta);
         else
             finalize_segments<1>(a.fin.nseg, a.fin.slot_ptr, a.partials, a.fin.seg_ptr, a.fin.lambda, a.fin.nmf, a.fin.out,
                                  a.fin.peer_ll, a.fin.vec_off, a.fin.rank, a.fin.nranks, a.fin.epoch, &meta);
+        if (tracing) a.trace[4] = global_ns();
         if (a.fin.ll != nullptr) ll_unpack_entries(a.fin.ll, a.fin.vec, a.fin.dim, a.fin.own_lo, a.fin.own_hi, a.fin.epoch, a.fin.status);
+        if (tracing) a.trace[5] = global_ns();
     }
 }
 

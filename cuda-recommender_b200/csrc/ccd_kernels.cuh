@@ -60,6 +60,9 @@ struct PanelSweepArgs {
     uint32_t ring_entries;          // STREAM pipeline: entries of the shared-memory ring (set by panel_sweep)
     uint32_t pf_dist;               // register ring: L2 prefetch distance in entries (0: off)
     uint32_t npad;                  // padded entries of the copy
+    unsigned long long* trace_cta;  // nullptr, or 4 words per CTA: after the dependency wait / after its items / item range
+    unsigned long long* trace;      // nullptr, or 8 words: %globaltimer of CTA 0 at entry / after the dependency wait / after
+                                    // its items / after the grid barrier / after its finalize share / at exit (MF_SWEEP_TRACE)
     SweepFinalize fin;    // register-ring pipeline only
 };
 

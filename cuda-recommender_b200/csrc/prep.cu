@@ -195,6 +195,16 @@ __global__ void k_panel_item_ptr(int64_t nseg, int npanels, const uint32_t* __re
     if (p <= npanels) panel_item_ptr[p] = item_ptr[(int64_t)p * nseg];
 }
 
+// What a CTA pays when its range runs into another panel (all warps drain, the panel's vectors are staged, the pipeline
+// refills) is charged to the first item of every panel but the first, so that the equal-cost cut hands the CTAs that
+// span a panel boundary fewer items.  Measured on the Netflix shape (per-CTA time stamps, profiles/README.md round 2):
+// those CTAs — one in five on the 30-panel CSC side — reached the grid barrier 7 us (solve sweep) to 22 us (fused sweep)
+// after the others: 8-17 % of a single-GPU sweep and half of an 8-GPU one.
+__global__ void k_panel_entry_cost(int npanels, const uint32_t* __restrict__ panel_item_ptr, uint32_t extra, uint32_t* __restrict__ cost) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x + 1;
+    if (p < npanels && panel_item_ptr[p + 1] > panel_item_ptr[p]) cost[panel_item_ptr[p]] += extra;
+}
+
 // equal-cost contiguous item ranges: cta_item_ptr[j] = first item whose cost prefix >= j*total/ncta
 __global__ void k_cta_ranges(int ncta, int64_t nitems, const uint32_t* __restrict__ cost_prefix,
                              uint32_t* __restrict__ cta_item_ptr) {
@@ -498,6 +508,10 @@ int side_build_panels(Side& s, int panel_rows, int chunk, int ncta, cudaStream_t
                                                                       s.idx16, s.pval);
         MF_CUDA(cudaGetLastError());
         tmp_free(len, st); tmp_free(start, st); tmp_free(tmp3, st);
+    }
+    if (s.nitems > 0 && s.npanels > 1 && s.panel_cost > 0) {
+        k_panel_entry_cost<<<grid_for(s.npanels, 128), 128, 0, st>>>(s.npanels, s.panel_item_ptr, (uint32_t)s.panel_cost, cost);
+        MF_CUDA(cudaGetLastError());
     }
     {   // (the scratch of the piece scans is sized for Q elements; a copy with long pieces has more items than pieces)
         uint32_t* tmp_cost = nullptr;

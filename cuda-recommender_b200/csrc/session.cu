@@ -155,6 +155,8 @@ int run_sweep(mf_session* s, Side& sd, int mode, const SweepVectors& v, float* o
         a.nslots = 0;
         a.cta_start_ptr = sd.cta_start_ptr; a.ring_entries = 0;
         a.pf_dist = s->pf_dist; a.npad = (uint32_t)sd.npad;
+        a.trace_cta = (s->d_trace_cta && s->trace_n >= s->trace_cta_from && s->trace_n < s->trace_cta_from + 12) ? s->d_trace_cta + 4 * 256 * (size_t)(s->trace_n - s->trace_cta_from) : nullptr;
+        a.trace = (s->d_trace && s->trace_n < s->trace_cap) ? s->d_trace + 8 * (size_t)s->trace_n++ : nullptr;
         a.fin.enabled = 0;
         const bool solve = (mode & kSolve) != 0;
         const bool is_h = push && out >= s->H && out < s->H + (int64_t)s->k * s->ldn;
@@ -527,6 +529,16 @@ int create_impl(const mf_ratings* R, const mf_testset* T, const mf_params* param
     mf_session* s = new mf_session();
     s->prm = *params;
     if (const char* e = getenv("MF_L2_PREFETCH")) s->pf_dist = (uint32_t)(atoi(e) / 8 * 8);
+    if (getenv("MF_SWEEP_TRACE")) {
+        s->trace_cap = 4096;
+        if (cudaMalloc(&s->d_trace, sizeof(unsigned long long) * 8 * (size_t)s->trace_cap) != cudaSuccess) { s->d_trace = nullptr; s->trace_cap = 0; cudaGetLastError(); }
+        else cudaMemset(s->d_trace, 0, sizeof(unsigned long long) * 8 * (size_t)s->trace_cap);
+        if (const char* e = getenv("MF_SWEEP_TRACE_CTA")) {  // per-CTA stamps of 12 launches starting at this launch number
+            s->trace_cta_from = atoi(e);
+            if (cudaMalloc(&s->d_trace_cta, sizeof(unsigned long long) * 4 * 256 * 12) != cudaSuccess) { s->d_trace_cta = nullptr; cudaGetLastError(); }
+            else cudaMemset(s->d_trace_cta, 0, sizeof(unsigned long long) * 4 * 256 * 12);
+        }
+    }
     if (const char* e = getenv("MF_PIPELINE")) {  // A/B switch for runs that do not set mf_params.pipeline themselves
         if (!strcmp(e, "stream")) s->prm.pipeline = MF_PIPELINE_STREAM;
         else if (!strcmp(e, "registers")) s->prm.pipeline = MF_PIPELINE_REGISTERS;
@@ -629,6 +641,13 @@ int create_impl(const mf_ratings* R, const mf_testset* T, const mf_params* param
             };
             s->csc.pad = pick_pad(s->csc, pr_c);
             s->csr.pad = pick_pad(s->csr, pr_r);
+            {   // panel-entry charge of the work partition (prep.cu), in units of 8 entries; measured optimum on the Netflix shape between
+                // 4000 and 16000 (flat): the CTAs that span a panel boundary then finish with the others instead of 7-22 us later
+                int pc = 8000;
+                if (const char* e = getenv("MF_PANEL_COST")) pc = atoi(e);
+                s->csc.panel_cost = pc;
+                s->csr.panel_cost = pc;
+            }
             if ((rc = side_build_panels(s->csc, pr_c, chunk, s->sm_count, s->st)) != MF_OK) return fail_up(rc);
             if ((rc = csr_arrived()) != MF_OK) return fail_up(rc);
             if ((rc = side_check_sorted(s->csr, &ok_r, &range_r, s->st)) != MF_OK) return fail_up(rc);
@@ -827,6 +846,45 @@ int mf_session_destroy(mf_session* s) {
     if (!s) return MF_OK;
     cudaSetDevice(s->device);
     if (s->st) cudaStreamSynchronize(s->st);
+    if (s->d_trace) {  // dump the sweep timeline: one line per launch, seven numbers (ns relative to the launch's entry stamp; mode last)
+        if (const char* path = getenv("MF_SWEEP_TRACE")) {
+            std::vector<unsigned long long> h(8 * (size_t)s->trace_n);
+            char name[1200];
+            snprintf(name, sizeof(name), "%s.rank%d", path, s->rank);
+            FILE* fp = s->trace_n > 0 && cudaMemcpy(h.data(), s->d_trace, sizeof(unsigned long long) * h.size(), cudaMemcpyDeviceToHost) == cudaSuccess ? fopen(name, "a") : nullptr;
+            if (fp) {
+                fprintf(fp, "# session of %d launches: entry_abs_ns after_wait after_items after_barrier after_finalize after_unpack mode\n", s->trace_n);
+                for (int i = 0; i < s->trace_n; ++i) {
+                    const unsigned long long* r = h.data() + 8 * (size_t)i;
+                    fprintf(fp, "%llu %lld %lld %lld %lld %lld %llu\n", r[0], (long long)(r[1] - r[0]), (long long)(r[2] - r[0]), r[3] ? (long long)(r[3] - r[0]) : -1,
+                            r[4] ? (long long)(r[4] - r[0]) : -1, r[5] ? (long long)(r[5] - r[0]) : -1, r[6]);
+                }
+                fclose(fp);
+            }
+        }
+        cudaFree(s->d_trace);
+        if (s->d_trace_cta) {
+            const char* path = getenv("MF_SWEEP_TRACE");
+            std::vector<unsigned long long> h(4 * 256 * 12);
+            char name[1200];
+            snprintf(name, sizeof(name), "%s.cta.rank%d", path ? path : "trace", s->rank);
+            FILE* fp = cudaMemcpy(h.data(), s->d_trace_cta, sizeof(unsigned long long) * h.size(), cudaMemcpyDeviceToHost) == cudaSuccess ? fopen(name, "w") : nullptr;
+            if (fp) {
+                fprintf(fp, "# launch cta start_ns(rel to launch min) end_ns ib ie first_panel\n");
+                for (int l = 0; l < 12; ++l) {
+                    unsigned long long t0 = ~0ull;
+                    for (int c = 0; c < 256; ++c) if (h[4 * (256 * l + c)] && h[4 * (256 * l + c)] < t0) t0 = h[4 * (256 * l + c)];
+                    for (int c = 0; c < 256; ++c) {
+                        const unsigned long long* r = h.data() + 4 * (256 * (size_t)l + c);
+                        if (!r[0]) continue;
+                        fprintf(fp, "%d %d %llu %llu %llu %llu %llu\n", s->trace_cta_from + l, c, r[0] - t0, r[1] - t0, r[2] >> 32, r[2] & 0xffffffffull, r[3]);
+                    }
+                }
+                fclose(fp);
+            }
+            cudaFree(s->d_trace_cta);
+        }
+    }
     if (s->dist) dist_destroy(s->dist);
     side_free(s->csc);
     side_free(s->csr);

@@ -71,6 +71,11 @@ struct mf_session {
     std::vector<double> rank_seconds, rank_rmse;  // last outer iteration
     std::vector<int> rank_inner;               // inner iterations run per rank in the last outer iteration
     double fundec_max = 0.0;
+    // MF_SWEEP_TRACE=<file>: in-kernel time stamps of the first launches of the session (debug timeline, profiles/)
+    unsigned long long* d_trace = nullptr;
+    int trace_cap = 0, trace_n = 0;
+    unsigned long long* d_trace_cta = nullptr;  // [kTraceCtaLaunches][ncta][4]: per-CTA stamps of launches trace_cta_from .. +kTraceCtaLaunches
+    int trace_cta_from = 0;
     int outer_done = 0;
     int pending = -1;  // rank whose subtraction from the residual is still deferred (fused schedule)
     mf::FamilyTimer timer;
