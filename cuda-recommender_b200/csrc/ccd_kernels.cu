@@ -393,9 +393,90 @@ __device__ __forceinline__ void l2_prefetch(const void* p, uint32_t bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 
+// One batch of (up to) four items through the 8-lane groups of a warp: group `grp` streams the item whose descriptor is d.
+template <int MODE, class Args>
+__device__ __forceinline__ void group_batch(const Args& a, const uint4 d, const int sl, const float* __restrict__ sm_new,
+                                            const float* __restrict__ sm_add, const float* __restrict__ sm_old) {
+    constexpr bool SUB = MODE & kSub, ADD = MODE & kAdd, SOLVE = MODE & kSolve;
+    const uint32_t len = d.y;
+    const uint32_t lane_off = 4u * (uint32_t)sl;     // this lane's 4 entries inside a 32-entry step
+    // The storage is in work-list order, so what this CTA will read pf_dist entries from now is simply this
+    // item's stretch shifted by pf_dist: one lane per item asks the L2 for it (the per-lane loads of the
+    // register ring then hit L2 instead of paying the DRAM latency under load).
+    if (a.pf_dist() != 0u && sl == 0 && len != 0u) {
+        const uint32_t q = d.x + a.pf_dist();
+        if (q < a.npad()) {
+            const uint32_t n = q + len <= a.npad() ? len : a.npad() - q;  // multiples of 8 entries
+            l2_prefetch(a.idx16() + q, n * 2u);
+            l2_prefetch(a.val() + q, n * 4u);
+        }
+    }
+    float s_add = 0.0f, s_old = 0.0f;
+    if (len != 0u) {
+        // L2 loads: the finalize of this very launch rewrites the vector s_add points into (after the grid
+        // barrier) and the persistent kernel reads vectors other CTAs wrote earlier in the launch, so the
+        // non-coherent path and L1 are off limits
+        if (ADD) s_add = __ldcg(a.s_add() + a.seg_offset() + d.z);
+        if (SUB) s_old = __ldcg(a.s_old() + a.seg_offset() + d.z);
+    }
+    const uint32_t maxlen = __reduce_max_sync(kFull, len);
+    const uint32_t minlen = __reduce_min_sync(kFull, len);
+    float g = 0.0f, h = 0.0f;
+    stream_batch<MODE>(a, d.x + lane_off, len, minlen, maxlen, lane_off, sm_new, sm_add, sm_old, s_add, s_old, g, h);
+    if (SOLVE) {
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+            g += __shfl_xor_sync(kFull, g, o);
+            h += __shfl_xor_sync(kFull, h, o);
+        }
+        if (sl == 0 && len != 0u) a.partials()[d.w] = make_float2(g, h);
+    }
+}
+
+// One item of at most 32 entries, streamed by ONE lane, with the arithmetic of an 8-lane group: the group's lane q owns
+// entries 4q .. 4q+3 and starts its (g, h) at zero; the butterfly then adds the eight lane sums as
+// ((p0+p1)+(p2+p3))+((p4+p5)+(p6+p7)), lanes without entries contributing +0.  Replayed here in that order.
+template <int MODE, class Args>
+__device__ __forceinline__ void lane_item(const Args& a, const uint4 d, const float* __restrict__ sm_new,
+                                          const float* __restrict__ sm_add, const float* __restrict__ sm_old) {
+    constexpr bool SUB = MODE & kSub, ADD = MODE & kAdd, SOLVE = MODE & kSolve;
+    constexpr bool WRITE = SUB || ADD;
+    const uint32_t len = d.y;
+    float s_add = 0.0f, s_old = 0.0f;
+    if (len != 0u) {
+        if (ADD) s_add = __ldcg(a.s_add() + a.seg_offset() + d.z);
+        if (SUB) s_old = __ldcg(a.s_old() + a.seg_offset() + d.z);
+    }
+    float pg[8], ph[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) { pg[q] = 0.0f; ph[q] = 0.0f; }
+#pragma unroll
+    for (int q0 = 0; q0 < 8; q0 += 2) {  // two 4-entry groups (24 bytes each) in flight per lane
+        Step e[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            e[u].i = make_uint2(0u, 0u);
+            e[u].v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            if (4u * (uint32_t)(q0 + u) < len) e[u] = load_step(a.idx16(), a.val(), d.x + 4u * (uint32_t)(q0 + u));
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            if (4u * (uint32_t)(q0 + u) < len) {
+                calc4<MODE>(e[u], sm_new, sm_add, sm_old, s_add, s_old, pg[q0 + u], ph[q0 + u]);
+                if (WRITE) __stcs(reinterpret_cast<float4*>(a.val() + d.x + 4u * (uint32_t)(q0 + u)), e[u].v);
+            }
+        }
+    }
+    if (SOLVE && len != 0u) {
+        const float g = ((pg[0] + pg[1]) + (pg[2] + pg[3])) + ((pg[4] + pg[5]) + (pg[6] + pg[7]));
+        const float h = ((ph[0] + ph[1]) + (ph[2] + ph[3])) + ((ph[4] + ph[5]) + (ph[6] + ph[7]));
+        a.partials()[d.w] = make_float2(g, h);
+    }
+}
+
 // One CTA's share of a sweep: the work items [ib, ie) of the list, starting in panel p (the panel that holds item ib).
 // smem: the staged panel vectors; s_ctr: a shared-memory counter the warps pull batches from.
-template <int MODE, class Args>
+template <int MODE, bool SHORT = false, class Args>
 __device__ __forceinline__ void sweep_cta_range(const Args& a, float* smem, unsigned* s_ctr, uint32_t ib, uint32_t ie, int p, const unsigned tid,
                                                 const unsigned nthr, uint32_t pend_first = 0xffffffffu) {
     constexpr bool SUB = MODE & kSub, ADD = MODE & kAdd, SOLVE = MODE & kSolve, ADDSEP = MODE & kAddSep;
@@ -433,55 +514,59 @@ __device__ __forceinline__ void sweep_cta_range(const Args& a, float* smem, unsi
             if (tid == 0) *s_ctr = ib;
             __syncthreads();
 
-            // Batches of four items (one per 8-lane group); neighbours in the list have (nearly) the same length.  The next batch's descriptors are
-            // fetched while this batch is processed.
-            uint32_t i0 = 0;
-            if (lane == 0) i0 = atomicAdd(s_ctr, 4u);
-            i0 = __shfl_sync(kFull, i0, 0);
-            uint4 d = make_uint4(0u, 0u, 0u, 0u);  // {start, len, seg, slot}; len 0 = no item
-            if (i0 + grp < pe) d = __ldg(items + i0 + grp);
-            while (i0 < pe) {
-                uint32_t i0n = 0;
-                if (lane == 0) i0n = atomicAdd(s_ctr, 4u);
-                i0n = __shfl_sync(kFull, i0n, 0);
-                uint4 dn = make_uint4(0u, 0u, 0u, 0u);
-                if (i0n + grp < pe) dn = __ldg(items + i0n + grp);
-
-                const uint32_t len = d.y;
-                const uint32_t lane_off = 4u * (uint32_t)sl;     // this lane's 4 entries inside a 32-entry step
-                // The storage is in work-list order, so what this CTA will read pf_dist entries from now is simply this
-                // item's stretch shifted by pf_dist: one lane per item asks the L2 for it (the per-lane loads of the
-                // register ring then hit L2 instead of paying the DRAM latency under load).
-                if (a.pf_dist() != 0u && sl == 0 && len != 0u) {
-                    const uint32_t q = d.x + a.pf_dist();
-                    if (q < a.npad()) {
-                        const uint32_t n = q + len <= a.npad() ? len : a.npad() - q;  // multiples of 8 entries
-                        l2_prefetch(a.idx16() + q, n * 2u);
-                        l2_prefetch(a.val() + q, n * 4u);
+            if (!SHORT) {
+                // Batches of four items (one per 8-lane group); neighbours in the list have (nearly) the same length.  The
+                // next batch's descriptors are fetched while this batch is processed.
+                uint32_t i0 = 0;
+                if (lane == 0) i0 = atomicAdd(s_ctr, 4u);
+                i0 = __shfl_sync(kFull, i0, 0);
+                uint4 d = make_uint4(0u, 0u, 0u, 0u);  // {start, len, seg, slot}; len 0 = no item
+                if (i0 + grp < pe) d = __ldg(items + i0 + grp);
+                while (i0 < pe) {
+                    uint32_t i0n = 0;
+                    if (lane == 0) i0n = atomicAdd(s_ctr, 4u);
+                    i0n = __shfl_sync(kFull, i0n, 0);
+                    uint4 dn = make_uint4(0u, 0u, 0u, 0u);
+                    if (i0n + grp < pe) dn = __ldg(items + i0n + grp);
+                    group_batch<MODE>(a, d, sl, sm_new, sm_add, sm_old);
+                    i0 = i0n;
+                    d = dn;
+                }
+            } else {
+                // Short-piece copies (a few entries per piece: the Yahoo-Music shape has ~6.5): the warp takes 32 items at a
+                // time, one descriptor per lane (one coalesced 512-byte load), and when all 32 are at most one 32-entry step
+                // long every LANE streams its own item — 32 items in flight per warp instead of 4, and with the work-list
+                // order of the storage the lanes' loads are still neighbours in memory.  The arithmetic is the 8-lane
+                // group's, replayed by one lane (lane_item): same partial sums, same tree, same bits.  A batch that holds a
+                // longer item goes through the groups, four items at a time.
+                uint32_t i0 = 0;
+                if (lane == 0) i0 = atomicAdd(s_ctr, 32u);
+                i0 = __shfl_sync(kFull, i0, 0);
+                uint4 d = make_uint4(0u, 0u, 0u, 0u);
+                if (i0 + lane < pe) d = __ldg(items + i0 + lane);
+                while (i0 < pe) {
+                    uint32_t i0n = 0;
+                    if (lane == 0) i0n = atomicAdd(s_ctr, 32u);
+                    i0n = __shfl_sync(kFull, i0n, 0);
+                    uint4 dn = make_uint4(0u, 0u, 0u, 0u);
+                    if (i0n + lane < pe) dn = __ldg(items + i0n + lane);
+                    if (__all_sync(kFull, d.y <= 32u)) {
+                        lane_item<MODE>(a, d, sm_new, sm_add, sm_old);
+                    } else {
+#pragma unroll 1
+                        for (int sb = 0; sb < 8; ++sb) {
+                            uint4 dd;
+                            dd.x = __shfl_sync(kFull, d.x, 4 * sb + grp);
+                            dd.y = __shfl_sync(kFull, d.y, 4 * sb + grp);
+                            dd.z = __shfl_sync(kFull, d.z, 4 * sb + grp);
+                            dd.w = __shfl_sync(kFull, d.w, 4 * sb + grp);
+                            if (__all_sync(kFull, dd.y == 0u)) break;
+                            group_batch<MODE>(a, dd, sl, sm_new, sm_add, sm_old);
+                        }
                     }
+                    i0 = i0n;
+                    d = dn;
                 }
-                float s_add = 0.0f, s_old = 0.0f;
-                if (len != 0u) {
-                    // L2 loads: the finalize of this very launch rewrites the vector s_add points into (after the grid
-                    // barrier) and the persistent kernel reads vectors other CTAs wrote earlier in the launch, so the
-                    // non-coherent path and L1 are off limits
-                    if (ADD) s_add = __ldcg(a.s_add() + a.seg_offset() + d.z);
-                    if (SUB) s_old = __ldcg(a.s_old() + a.seg_offset() + d.z);
-                }
-                const uint32_t maxlen = __reduce_max_sync(kFull, len);
-                const uint32_t minlen = __reduce_min_sync(kFull, len);
-                float g = 0.0f, h = 0.0f;
-                stream_batch<MODE>(a, d.x + lane_off, len, minlen, maxlen, lane_off, sm_new, sm_add, sm_old, s_add, s_old, g, h);
-                if (SOLVE) {
-#pragma unroll
-                    for (int o = 1; o < 8; o <<= 1) {
-                        g += __shfl_xor_sync(kFull, g, o);
-                        h += __shfl_xor_sync(kFull, h, o);
-                    }
-                    if (sl == 0 && len != 0u) a.partials()[d.w] = make_float2(g, h);
-                }
-                i0 = i0n;
-                d = dn;
             }
         }
         ib = pe;
@@ -497,7 +582,7 @@ __device__ __forceinline__ void sweep_cta_range(const Args& a, float* smem, unsi
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
-template <int MODE>
+template <int MODE, bool SHORT>
 __global__ void __launch_bounds__(kSweepThreads, 1) k_panel_sweep(PanelSweepArgs a) {
     constexpr bool SOLVE = MODE & kSolve;
     extern __shared__ __align__(16) float smem[];
@@ -512,7 +597,7 @@ __global__ void __launch_bounds__(kSweepThreads, 1) k_panel_sweep(PanelSweepArgs
     pdl_wait();  // everything below reads what the previous sweep wrote (factor vectors, residual) or writes what it read
     if (tracing) a.trace[1] = global_ns();
     if (a.trace_cta != nullptr && threadIdx.x == 0) a.trace_cta[4 * blockIdx.x + 0] = global_ns();
-    sweep_cta_range<MODE>(LaunchView{a}, smem, &s_ctr, ib, ie, p, threadIdx.x, blockDim.x, pend0);
+    sweep_cta_range<MODE, SHORT>(LaunchView{a}, smem, &s_ctr, ib, ie, p, threadIdx.x, blockDim.x, pend0);
     if (tracing) { a.trace[2] = global_ns(); a.trace[6] = (unsigned long long)MODE; }
     if (a.trace_cta != nullptr && threadIdx.x == 0) {
         a.trace_cta[4 * blockIdx.x + 1] = global_ns();
@@ -1496,11 +1581,11 @@ struct PerDeviceOnce {
     }
 };
 
-template <int MODE>
-int launch_panel(const PanelSweepArgs& a, int ncta, int threads, size_t smem, cudaStream_t st) {
+template <int MODE, bool SHORT>
+int launch_panel_v(const PanelSweepArgs& a, int ncta, int threads, size_t smem, cudaStream_t st) {
     static PerDeviceOnce once;  // per template instance
     if (once.need()) {
-        MF_CUDA(cudaFuncSetAttribute(k_panel_sweep<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 256));
+        MF_CUDA(cudaFuncSetAttribute(k_panel_sweep<MODE, SHORT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 256));
     }
     static const bool pdl = getenv("MF_NO_PDL") == nullptr;
     if (pdl) {
@@ -1510,12 +1595,17 @@ int launch_panel(const PanelSweepArgs& a, int ncta, int threads, size_t smem, cu
         at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         at[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
-        MF_CUDA(cudaLaunchKernelEx(&cfg, k_panel_sweep<MODE>, a));
+        MF_CUDA(cudaLaunchKernelEx(&cfg, k_panel_sweep<MODE, SHORT>, a));
     } else {
-        k_panel_sweep<MODE><<<ncta, threads, smem, st>>>(a);
+        k_panel_sweep<MODE, SHORT><<<ncta, threads, smem, st>>>(a);
     }
     MF_CUDA(cudaGetLastError());
     return MF_OK;
+}
+
+template <int MODE>
+int launch_panel(const PanelSweepArgs& a, int ncta, int threads, size_t smem, cudaStream_t st) {
+    return a.short_items ? launch_panel_v<MODE, true>(a, ncta, threads, smem, st) : launch_panel_v<MODE, false>(a, ncta, threads, smem, st);
 }
 
 template <int MODE>
@@ -1688,12 +1778,12 @@ int panel_sweep(int mode, const PanelSweepArgs& a_in, int ncta, int threads, int
 bool panel_sweep_grid_resident(int ncta, int threads, int panel_rows, int sm_count) {
     const size_t smem = panel_sweep_smem(kSolve | kSub | kAdd | kAddSep, panel_rows);  // the largest footprint of any mode
     if (smem > 227 * 1024 - 256) return false;
-    if (cudaFuncSetAttribute(k_panel_sweep<kSolve | kSub | kAdd | kAddSep>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 256) != cudaSuccess) {
+    if (cudaFuncSetAttribute(k_panel_sweep<kSolve | kSub | kAdd | kAddSep, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 256) != cudaSuccess) {
         cudaGetLastError();
         return false;
     }
     int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_panel_sweep<kSolve | kSub | kAdd | kAddSep>, threads, smem) != cudaSuccess) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_panel_sweep<kSolve | kSub | kAdd | kAddSep, false>, threads, smem) != cudaSuccess) {
         cudaGetLastError();
         return false;
     }

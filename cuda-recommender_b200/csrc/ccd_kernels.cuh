@@ -60,6 +60,7 @@ struct PanelSweepArgs {
     uint32_t ring_entries;          // STREAM pipeline: entries of the shared-memory ring (set by panel_sweep)
     uint32_t pf_dist;               // register ring: L2 prefetch distance in entries (0: off)
     uint32_t npad;                  // padded entries of the copy
+    int short_items;                // register ring: 1 = short-piece copy: warps take 32 items at a time, a lane per item when all are <= 32 entries
     unsigned long long* trace_cta;  // nullptr, or 4 words per CTA: after the dependency wait / after its items / item range
     unsigned long long* trace;      // nullptr, or 8 words: %globaltimer of CTA 0 at entry / after the dependency wait / after
                                     // its items / after the grid barrier / after its finalize share / at exit (MF_SWEEP_TRACE)

@@ -53,6 +53,7 @@ struct Side {
     // panel layout
     int panel_rows = 0, chunk = 0, npanels = 0;
     int pad = 8;  // pieces are padded to a multiple of this many entries (multiple of 8, divides chunk)
+    bool short_items = false;  // pieces average only a few entries: the sweeps run one item per LANE where they can (ccd_kernels.cu)
     int panel_cost = 0;  // cost-model charge (units of 8 entries) for entering another panel inside a CTA's range (prep.cu)
     int64_t npad = 0, nitems = 0, nslots = 0;
     uint32_t* piece_ptr = nullptr;    // [npanels*nseg + 1] start of piece (p,s) in the padded arrays

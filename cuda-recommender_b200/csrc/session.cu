@@ -155,6 +155,7 @@ int run_sweep(mf_session* s, Side& sd, int mode, const SweepVectors& v, float* o
         a.nslots = 0;
         a.cta_start_ptr = sd.cta_start_ptr; a.ring_entries = 0;
         a.pf_dist = s->pf_dist; a.npad = (uint32_t)sd.npad;
+        a.short_items = sd.short_items ? 1 : 0;
         a.trace_cta = (s->d_trace_cta && s->trace_n >= s->trace_cta_from && s->trace_n < s->trace_cta_from + 12) ? s->d_trace_cta + 4 * 256 * (size_t)(s->trace_n - s->trace_cta_from) : nullptr;
         a.trace = (s->d_trace && s->trace_n < s->trace_cap) ? s->d_trace + 8 * (size_t)s->trace_n++ : nullptr;
         a.fin.enabled = 0;
@@ -641,6 +642,20 @@ int create_impl(const mf_ratings* R, const mf_testset* T, const mf_params* param
             };
             s->csc.pad = pick_pad(s->csc, pr_c);
             s->csr.pad = pick_pad(s->csr, pr_r);
+            {   // short-piece copies (same criterion as the 16-entry padding: fewer than 24 entries per piece on average): one item
+                // per lane, and the padding can drop to 8 entries — an item's loads no longer belong to an 8-lane group
+                auto is_short = [&](const Side& sd, int pr) {
+                    const int64_t npan = (sd.gdim + pr - 1) / pr;
+                    const int64_t pieces = std::max<int64_t>(1, std::min<int64_t>(sd.nseg * npan, std::max<int64_t>(sd.nnz, 1)));
+                    return sd.nnz / pieces < 24;
+                };
+                const char* e = getenv("MF_SHORT_ITEMS");  // A/B switch: 0 = off, 1 = forced on
+                for (Side* sd : {&s->csc, &s->csr}) {
+                    const int pr = sd == &s->csc ? pr_c : pr_r;
+                    sd->short_items = e ? atoi(e) != 0 : is_short(*sd, pr);
+                    if (sd->short_items && params->pad_entries <= 0 && s->prm.pipeline != MF_PIPELINE_STREAM) sd->pad = getenv("MF_SHORT_PAD") ? atoi(getenv("MF_SHORT_PAD")) : 8;
+                }
+            }
             {   // panel-entry charge of the work partition (prep.cu), in units of 8 entries; measured optimum on the Netflix shape between
                 // 4000 and 16000 (flat): the CTAs that span a panel boundary then finish with the others instead of 7-22 us later
                 int pc = 8000;

@@ -25,10 +25,11 @@ def session_panel_rows(gdim, side_is_csr, user_panel_rows=0):
 
 
 def session_pad(nseg, nnz, gdim, panel_rows):
-    """The padding granularity a session picks (session.cu pick_pad): 16 when pieces average fewer than 24 entries."""
+    """The padding granularity a session picks (session.cu): 8 for short-piece copies (fewer than 24 entries per piece on
+    average: the sweeps then run one item per lane), else 32."""
     npan = -(-gdim // panel_rows)
     pieces = max(1, min(nseg * npan, max(nnz, 1)))
-    return 16 if nnz // pieces < 24 else 32
+    return 8 if nnz // pieces < 24 else 32
 
 
 def panel_layout(ptr, idx, val, gdim, panel_rows, chunk, pad=32):

@@ -300,3 +300,25 @@ def test_persistent_kernel_equals_per_launch_path_bitwise(gpu, port, data_factor
             outs.append(s.get_factors() + s.get_values() + (np.array([x["rmse"] for x in st]),))
     for a, b in zip(*outs):
         assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("shape,kw", [("ml100k", dict(panel_rows=64, chunk=64)), ("small", dict(panel_rows=16, chunk=32)), ("tiny", dict(panel_rows=8, chunk=8)), ("ml100k", dict())])
+@pytest.mark.parametrize("schedule", [0, 1])
+def test_lane_per_item_path_is_bitwise_the_group_path(gpu, port, data_factory, monkeypatch, shape, kw, schedule):
+    """Short-piece copies run one work item per LANE (32 items in flight per warp) where all items of a batch fit one
+    32-entry step; the lane replays the 8-lane group's arithmetic, so factors, residual and RMSE are identical whichever path
+    a batch takes — for every sweep mode (both schedules), for geometries that make pieces short, and for the padding the
+    short mode picks (8) as well as the default (32)."""
+    d = data_factory(shape)
+    k = 4
+    W0 = port.initial_col(k, d["rows"])
+    outs = []
+    for short, pad in (("0", 32), ("1", 32), ("1", 8), ("1", 0)):
+        monkeypatch.setenv("MF_SHORT_ITEMS", short)
+        with gpu.Session(d, gpu.make_params(k=k, lam=0.05, maxinner=2, schedule=schedule, pad_entries=pad, **kw)) as s:
+            s.set_factors(W0)
+            st = s.iterate(3)
+            outs.append(s.get_factors() + s.get_values() + (np.array([x["rmse"] for x in st]),))
+    for other in outs[1:]:
+        for a, b in zip(outs[0], other):
+            assert np.array_equal(a, b)

@@ -10,7 +10,7 @@ comparison (src/main.cpp:109-141) at the shapes the benchmark is quoted on.
   C2  ALS k=10, ML-20M shape: 3 iterations vs ALS_OMP, RMSE <= 1e-4 per iteration, factors as above.
   C4  ALS k=100 on Netflix-shape item columns: one H half-step on ~600 sampled columns INCLUDING the longest ones
       (>= 65 536 ratings: the multi-CTA split path), vs orc_als_half_step and its FP64 variant.
-  C5  CCD++ on the Yahoo-Music shape (1 000 990 x 624 961, 252.8 M nnz; pieces average ~6 entries -> the 16-entry
+  C5  CCD++ on the Yahoo-Music shape (1 000 990 x 624 961, 252.8 M nnz; pieces average ~6 entries -> the 8-entry
       padding path): values round-trip through the layout bit-exactly, one v-solve + u-solve vs the oracle, one
       residual update bit-exact.
 Each test is sized to finish within ~2 minutes on the box (16 host cores).
