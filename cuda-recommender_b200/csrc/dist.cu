@@ -80,10 +80,25 @@ int load_api() {
 // Communicators are kept for the life of the process, keyed by the 128-byte unique id (+ rank, size, device): a host that
 // opens one session after another with the same id — a training service, the benchmark's end-to-end leg — pays
 // ncclCommInitRank (0.5-1 s) once.  mf_release_cached_memory() destroys them.
+// The peer-to-peer state of a communicator is kept with it as well: the exported receive buffers / flag words and the
+// CUDA IPC mappings of the peers' (21 cudaIpcOpenMemHandle calls at 8 ranks) cost 45-70 ms per session at 8 GPUs — more
+// than the three outer iterations of an end-to-end call.  A later session of the same shape on the same communicator
+// adopts them (the exchange epoch carries on where the previous session stopped, so stale receive words never match).
+struct P2PState {
+    int64_t ldm = 0, ldn = 0;
+    bool in_use = false;
+    std::vector<void*> opened;
+    unsigned** d_peerFlags = nullptr;
+    unsigned* flags = nullptr;
+    unsigned long long *llW = nullptr, *llH = nullptr;
+    unsigned long long **d_peerLLW = nullptr, **d_peerLLH = nullptr;
+    unsigned epoch = 0;
+};
 struct CachedComm {
     char id[128];
     int rank, nranks, device;
     ncclComm_t comm;
+    P2PState* p2p;  // nullptr: none cached
 };
 std::vector<CachedComm> g_comms;
 
@@ -100,6 +115,7 @@ struct Dist {
     unsigned long long** d_peerLLW = nullptr;  // [nranks] device arrays of every rank's receive buffers
     unsigned long long** d_peerLLH = nullptr;
     unsigned epoch = 0;             // exchanges issued so far
+    P2PState* cached = nullptr;     // the communicator's cached peer-to-peer state this session runs on (not owned)
 };
 
 int dist_unique_id(void* id128) {
@@ -130,15 +146,36 @@ int dist_create(Dist** out, int rank, int nranks, const void* id128, int device)
         }
         CachedComm c;
         memcpy(c.id, id128, 128);
-        c.rank = rank; c.nranks = nranks; c.device = device; c.comm = d->comm;
+        c.rank = rank; c.nranks = nranks; c.device = device; c.comm = d->comm; c.p2p = nullptr;
         g_comms.push_back(c);
     }
     *out = d;
     return MF_OK;
 }
 
+static void p2p_free(P2PState* c, ncclComm_t comm, int rank, int nranks) {
+    for (void* p : c->opened) cudaIpcCloseMemHandle(p);
+    if (comm) {  // every rank has closed its imports before any rank frees its exports (see dist_destroy)
+        char* d_b = nullptr;
+        if (dev_alloc(&d_b, (size_t)nranks) == MF_OK) {
+            if (g_api.AllGather(d_b + rank, d_b, 1, ncclInt8, comm, nullptr) == ncclSuccess) cudaStreamSynchronize(nullptr);
+            dev_free(d_b);
+        }
+    }
+    void* ptrs[] = {c->d_peerFlags, c->flags, c->llW, c->llH, c->d_peerLLW, c->d_peerLLH};
+    for (void* p : ptrs)
+        if (p) dev_free(p);
+    delete c;
+}
+
 int dist_destroy(Dist* d) {
     if (!d) return MF_OK;
+    if (d->cached) {  // the state stays with the communicator for the next session of this shape
+        d->cached->epoch = d->epoch;
+        d->cached->in_use = false;
+        delete d;
+        return MF_OK;
+    }
     for (void* p : d->opened) cudaIpcCloseMemHandle(p);
     if (d->p2p && d->comm) {
         // the exporter must not free a buffer a peer still has mapped (CUDA IPC: undefined behaviour): every rank has closed
@@ -163,6 +200,7 @@ int dist_destroy(Dist* d) {
 void dist_release_cached(int device) {
     for (size_t i = 0; i < g_comms.size();) {
         if (g_comms[i].device == device) {
+            if (g_comms[i].p2p && !g_comms[i].p2p->in_use) { p2p_free(g_comms[i].p2p, g_comms[i].comm, g_comms[i].rank, g_comms[i].nranks); g_comms[i].p2p = nullptr; }
             if (g_api.CommDestroy) g_api.CommDestroy(g_comms[i].comm);
             g_comms.erase(g_comms.begin() + i);
         } else {
@@ -181,6 +219,38 @@ int dist_setup_p2p(Dist* d, float* W, float* H, int64_t ldm, int64_t ldn, cudaSt
     (void)W; (void)H;
     if (!d || d->nranks <= 1) return MF_OK;
     const int P = d->nranks;
+    CachedComm* slot = nullptr;
+    for (CachedComm& c : g_comms)
+        if (c.comm == d->comm) slot = &c;
+    {   // collective 0: can EVERY rank adopt the state cached with the communicator?  (same shape, not held by a live session)
+        const bool have = slot && slot->p2p && !slot->p2p->in_use && slot->p2p->ldm == ldm && slot->p2p->ldn == ldn && getenv("MF_NO_P2P") == nullptr &&
+                          getenv("MF_NO_P2P_CACHE") == nullptr;
+        int* d_have = nullptr;
+        MF_TRY(dev_alloc(&d_have, (size_t)P));
+        const int mine_have = have ? 1 : 0;
+        MF_CUDA(cudaMemcpyAsync(d_have + d->rank, &mine_have, sizeof(int), cudaMemcpyHostToDevice, st));
+        MF_NCCL(g_api.AllGather(d_have + d->rank, d_have, sizeof(int), ncclInt8, d->comm, st));
+        std::vector<int> all_have((size_t)P);
+        MF_CUDA(cudaMemcpyAsync(all_have.data(), d_have, sizeof(int) * (size_t)P, cudaMemcpyDeviceToHost, st));
+        MF_CUDA(cudaStreamSynchronize(st));
+        dev_free(d_have);
+        bool everyone_has = true;
+        for (int r = 0; r < P; ++r) everyone_has = everyone_has && all_have[r] != 0;
+        if (everyone_has) {
+            P2PState* c = slot->p2p;
+            c->in_use = true;
+            d->cached = c;
+            d->flags = c->flags; d->llW = c->llW; d->llH = c->llH;
+            d->d_peerFlags = c->d_peerFlags; d->d_peerLLW = c->d_peerLLW; d->d_peerLLH = c->d_peerLLH;
+            d->epoch = c->epoch;
+            d->p2p = true;
+            return MF_OK;
+        }
+        if (have) {  // somebody cannot: the cached state is of no use any more (every rank that has one drops it here)
+            p2p_free(slot->p2p, nullptr, d->rank, P);
+            slot->p2p = nullptr;
+        }
+    }
     struct Handles { cudaIpcMemHandle_t f, lw, lh; int ok; int pad[15]; };
     static_assert(sizeof(Handles) == 256, "three 64-byte handles + a flag");
     Handles mine;
@@ -242,6 +312,15 @@ int dist_setup_p2p(Dist* d, float* W, float* H, int64_t ldm, int64_t ldn, cudaSt
     MF_CUDA(cudaMemcpy(d->d_peerLLW, plw.data(), sizeof(void*) * (size_t)P, cudaMemcpyHostToDevice));
     MF_CUDA(cudaMemcpy(d->d_peerLLH, plh.data(), sizeof(void*) * (size_t)P, cudaMemcpyHostToDevice));
     d->p2p = true;
+    if (slot && !slot->p2p && getenv("MF_NO_P2P_CACHE") == nullptr) {  // keep it with the communicator (ownership moves to the cache)
+        P2PState* c = new P2PState();
+        c->ldm = ldm; c->ldn = ldn; c->in_use = true;
+        c->opened.swap(d->opened);
+        c->flags = d->flags; c->llW = d->llW; c->llH = d->llH;
+        c->d_peerFlags = d->d_peerFlags; c->d_peerLLW = d->d_peerLLW; c->d_peerLLH = d->d_peerLLH;
+        slot->p2p = c;
+        d->cached = c;
+    }
     return MF_OK;
 }
 

@@ -22,7 +22,9 @@ void set_error(const char* fmt, ...) {
 const char* get_error() { return g_err; }
 
 void trace_mark(const char* what) {
-    static const bool on = getenv("MF_TRACE") != nullptr;
+    // (multi-process launches: only the process whose RANK is MF_TRACE's value — "1" also means rank 0 — reports)
+    static const bool on = getenv("MF_TRACE") != nullptr &&
+                           (getenv("RANK") == nullptr || atoi(getenv("RANK")) == (atoi(getenv("MF_TRACE")) == 1 ? 0 : atoi(getenv("MF_TRACE"))));
     static std::chrono::steady_clock::time_point last = std::chrono::steady_clock::now();
     if (!on) return;
     auto now = std::chrono::steady_clock::now();
