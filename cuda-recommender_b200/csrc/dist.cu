@@ -227,15 +227,19 @@ int dist_setup_p2p(Dist* d, float* W, float* H, int64_t ldm, int64_t ldn, cudaSt
                           getenv("MF_NO_P2P_CACHE") == nullptr;
         int* d_have = nullptr;
         MF_TRY(dev_alloc(&d_have, (size_t)P));
-        const int mine_have = have ? 1 : 0;
+        const bool stale = !have && slot && slot->p2p && !slot->p2p->in_use;  // cached for another shape (or switched off)
+        const int mine_have = have ? 1 : (stale ? 2 : 0);
         MF_CUDA(cudaMemcpyAsync(d_have + d->rank, &mine_have, sizeof(int), cudaMemcpyHostToDevice, st));
         MF_NCCL(g_api.AllGather(d_have + d->rank, d_have, sizeof(int), ncclInt8, d->comm, st));
         std::vector<int> all_have((size_t)P);
         MF_CUDA(cudaMemcpyAsync(all_have.data(), d_have, sizeof(int) * (size_t)P, cudaMemcpyDeviceToHost, st));
         MF_CUDA(cudaStreamSynchronize(st));
         dev_free(d_have);
-        bool everyone_has = true;
-        for (int r = 0; r < P; ++r) everyone_has = everyone_has && all_have[r] != 0;
+        bool everyone_has = true, everyone_stale = true;
+        for (int r = 0; r < P; ++r) {
+            everyone_has = everyone_has && all_have[r] == 1;
+            everyone_stale = everyone_stale && all_have[r] == 2;
+        }
         if (everyone_has) {
             P2PState* c = slot->p2p;
             c->in_use = true;
@@ -246,8 +250,11 @@ int dist_setup_p2p(Dist* d, float* W, float* H, int64_t ldm, int64_t ldn, cudaSt
             d->p2p = true;
             return MF_OK;
         }
-        if (have) {  // somebody cannot: the cached state is of no use any more (every rank that has one drops it here)
-            p2p_free(slot->p2p, nullptr, d->rank, P);
+        if (have || stale) {
+            // the cached state is of no use any more: every rank that has one drops it here.  When ALL ranks do (the usual
+            // case: the next session has another shape) the exports are freed behind the communicator barrier, like in
+            // dist_destroy; in a mixed situation there is no collective every rank would enter.
+            p2p_free(slot->p2p, everyone_stale ? d->comm : nullptr, d->rank, P);
             slot->p2p = nullptr;
         }
     }
