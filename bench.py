@@ -405,11 +405,11 @@ def run_leg(ctx, pkg, dg, args, workload, headline):
         # Gram + RHS + factorisation flops of one iteration (symmetric count)
         flops = 2.0 * nnz * k * (k + 1) + 4.0 * nnz * k + (rows + cols) * (k ** 3 / 3.0 + 2.0 * k * k)
         avg = kt["als_s"] / kt["als_launches"]  # one half-step
-        ach = flops / (2 * avg) / 1e12
+        ach = flops / world / (2 * avg) / 1e12  # per GPU: every rank's launch works on 1/world of the segments
         roofline = {"bound": "fp32", "kernel": "k_als_tile (one half-step per launch)", "achieved": ach, "peak": FP32_SIMT_PEAK_TFLOPS,
                     "unit": "TFLOP/s", "frac": ach / FP32_SIMT_PEAK_TFLOPS,
-                    "peak_source": "nominal FP32 FMA peak of the part (148 SMs x 128 lanes x 2 x 1.965 GHz); MEASURED_PEAKS.json holds no FP32-SIMT figure",
-                    "traffic": None, "flops_per_iteration": flops, "avg_launch_ms": avg * 1e3, "launches": int(kt["als_launches"]),
+                    "peak_source": "nominal FP32 FMA peak of the part (148 SMs x 128 lanes x 2 x 1.965 GHz; scripts/ubench/mma_tf32.cu measures 72 TFLOP/s of FFMA on it); MEASURED_PEAKS.json holds no FP32-SIMT figure",
+                    "traffic": None, "flops_per_iteration": flops, "flops_per_launch": flops / world / 2, "avg_launch_ms": avg * 1e3, "launches": int(kt["als_launches"]),
                     "share_of_step": (2 * avg) / sec_per_iter if sec_per_iter > 0 else None,
                     "parity_note": "ALS factors are compared with an FP64 yardstick (the reference's explicit FP32 inverse is itself up to "
                                    "~2e-3 relative l2 away from it, SURVEY App. D); test RMSE within 1e-4 of the reference CPU path"}
@@ -463,7 +463,8 @@ def run_leg(ctx, pkg, dg, args, workload, headline):
             roofline = {"bound": "hbm", "kernel": f"ccd {top} sweep ({args.layout} layout)",
                         "achieved": achieved, "peak": peak,
                         "unit": "GB/s", "frac": achieved / peak, "peak_source": "measured" if peaks else "fallback",
-                        "traffic": traffic_tab.get(top), "bytes_per_launch": nbytes, "avg_launch_ms": avg * 1e3, "launches": n,
+                        # (the ncu DRAM bytes were captured on one GPU: per launch they only compare with a one-GPU launch)
+                        "traffic": traffic_tab.get(top) if world == 1 else None, "bytes_per_launch": nbytes, "avg_launch_ms": avg * 1e3, "launches": n,
                         "share_of_step": (avg * per_step[top]) / sec_per_iter if sec_per_iter > 0 else None,
                         "timing": f"CUDA events around the launches of every {max(args.timing_stride, 1)}-th rank in the timed region",
                         "achieved_at_survey_bytes": survey_bytes / avg / 1e9,
