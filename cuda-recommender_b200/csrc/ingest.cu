@@ -9,8 +9,13 @@
 //   1. histogram of the major key (atomics) -> exclusive scan -> ptr
 //   2. scatter every entry into its segment's range in arrival order (atomic cursor)
 //   3. per segment, one CTA marks the minor keys in a shared-memory bitmap, prefix-sums the word
-//      popcounts, and moves every entry to ptr[seg] + rank(minor key)
-// Step 3 makes the output independent of the arrival order of step 2.
+//      popcounts, and moves every entry to ptr[seg] + rank(minor key); a minor dimension too wide for one
+//      bitmap (> ~928 K keys in 227 KB) is handled in several passes over windows of the key range, each
+//      window's entries placed behind those of the windows before it
+// Step 3 makes the output independent of the arrival order of step 2.  A duplicate (row, col) pair shows up as a
+// segment whose distinct keys are fewer than its entries: the build fails with MF_ERR_ARG instead of leaving holes.
+#include <algorithm>
+
 #include "common.cuh"
 #include "layout.cuh"
 
@@ -34,9 +39,9 @@ __global__ void k_scatter(int64_t nnz, const uint32_t* __restrict__ key, const u
 }
 
 // one CTA per segment (grid-stride); bitmap of `words` 32-bit words in dynamic shared memory
-__global__ void __launch_bounds__(256) k_rank_place(int64_t nseg, uint32_t words, const uint32_t* __restrict__ ptr,
+__global__ void __launch_bounds__(256) k_rank_place(int64_t nseg, uint32_t words, uint32_t nminor, const uint32_t* __restrict__ ptr,
                                                     const uint32_t* __restrict__ tmp_idx, const float* __restrict__ tmp_val,
-                                                    uint32_t* __restrict__ out_idx, float* __restrict__ out_val) {
+                                                    uint32_t* __restrict__ out_idx, float* __restrict__ out_val, int* __restrict__ dup) {
     extern __shared__ uint32_t sm[];
     uint32_t* bits = sm;            // [words]
     uint32_t* pre = sm + words;     // [words] exclusive prefix of popcounts
@@ -50,13 +55,16 @@ __global__ void __launch_bounds__(256) k_rank_place(int64_t nseg, uint32_t words
             if (tid == 0) { out_idx[lo] = tmp_idx[lo]; out_val[lo] = tmp_val[lo]; }
             continue;
         }
+        uint32_t placed = 0;  // entries of the windows already done (CTA-uniform)
+        for (uint64_t wb = 0; wb < nminor; wb += (uint64_t)words * 32u) {  // one window of the key range per pass
+        const uint32_t wbeg = (uint32_t)wb;  // (keys are compared as m - wbeg, unsigned: below the window wraps to a huge value)
         __syncthreads();
         for (uint32_t w = tid; w < words; w += 256) bits[w] = 0u;
         if (tid == 0) carry_s = 0u;
         __syncthreads();
         for (uint32_t e = lo + tid; e < hi; e += 256) {
-            const uint32_t m = tmp_idx[e];
-            atomicOr(&bits[m >> 5], 1u << (m & 31));
+            const uint32_t m = tmp_idx[e] - wbeg;
+            if (m < words * 32u) atomicOr(&bits[m >> 5], 1u << (m & 31));
         }
         __syncthreads();
         // exclusive scan of popcounts, 256 words per round
@@ -80,11 +88,17 @@ __global__ void __launch_bounds__(256) k_rank_place(int64_t nseg, uint32_t words
             __syncthreads();
         }
         for (uint32_t e = lo + tid; e < hi; e += 256) {
-            const uint32_t m = tmp_idx[e];
-            const uint32_t rank = pre[m >> 5] + __popc(bits[m >> 5] & ((1u << (m & 31)) - 1u));
-            out_idx[lo + rank] = m;
-            out_val[lo + rank] = tmp_val[e];
+            const uint32_t m = tmp_idx[e] - wbeg;
+            if (m < words * 32u) {
+                const uint32_t rank = placed + pre[m >> 5] + __popc(bits[m >> 5] & ((1u << (m & 31)) - 1u));
+                out_idx[lo + rank] = m + wbeg;
+                out_val[lo + rank] = tmp_val[e];
+            }
         }
+        __syncthreads();
+        placed += carry_s;  // distinct keys of this window
+        }
+        if (tid == 0 && placed != hi - lo) *dup = 1;  // fewer distinct keys than entries: a (row, col) pair occurs twice
     }
 }
 
@@ -98,19 +112,26 @@ int build_one(int64_t nmajor, int64_t nminor, int64_t nnz, const uint32_t* d_key
     MF_CUDA(cudaMemset(d_count, 0, sizeof(uint32_t) * (size_t)nmajor));
     if (nnz > 0) {
         k_scatter<<<sm_count * 8, 256>>>(nnz, d_key, d_other, d_val, d_ptr, d_count, d_tmp_idx, d_tmp_val);
-        const uint32_t words = (uint32_t)((nminor + 31) / 32);
+        const uint32_t max_words = (uint32_t)((227 * 1024 - 256) / (2 * sizeof(uint32_t)));  // bitmap + prefix in shared memory
+        const uint32_t words = std::min<uint32_t>((uint32_t)((nminor + 31) / 32), max_words);  // one window of the key range
         const size_t smem = sizeof(uint32_t) * 2 * (size_t)words;
-        if (smem > 227 * 1024 - 256) {
-            set_error("mf_build_csr_csc: minor dimension %lld too large for the shared-memory bitmap", (long long)nminor);
-            return MF_ERR_UNSUPPORTED;
-        }
-        static size_t attr = 0;
-        if (smem > 48 * 1024 && smem > attr) {
+        static size_t attr[64] = {0};  // per device
+        int dev = 0;
+        MF_CUDA(cudaGetDevice(&dev));
+        if (smem > 48 * 1024 && (dev < 0 || dev >= 64 || smem > attr[dev])) {
             MF_CUDA(cudaFuncSetAttribute(k_rank_place, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            attr = smem;
+            if (dev >= 0 && dev < 64) attr[dev] = smem;
         }
+        int* d_dup = nullptr;
+        MF_TRY(dev_alloc(&d_dup, 1));
+        MF_CUDA(cudaMemset(d_dup, 0, sizeof(int)));
         int64_t grid = nmajor < (int64_t)sm_count * 8 ? nmajor : (int64_t)sm_count * 8;
-        k_rank_place<<<(unsigned)grid, 256, smem>>>(nmajor, words, d_ptr, d_tmp_idx, d_tmp_val, d_idx, d_outval);
+        k_rank_place<<<(unsigned)grid, 256, smem>>>(nmajor, words, (uint32_t)nminor, d_ptr, d_tmp_idx, d_tmp_val, d_idx, d_outval, d_dup);
+        int h_dup = 0;
+        const cudaError_t e = cudaMemcpy(&h_dup, d_dup, sizeof(int), cudaMemcpyDeviceToHost);
+        dev_free(d_dup);
+        if (e != cudaSuccess) { set_error("mf_build_csr_csc: %s", cudaGetErrorString(e)); return MF_ERR_CUDA; }
+        if (h_dup) { set_error("mf_build_csr_csc: a (row, col) pair occurs more than once"); return MF_ERR_ARG; }
     }
     MF_CUDA(cudaGetLastError());
     MF_CUDA(cudaDeviceSynchronize());

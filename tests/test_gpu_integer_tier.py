@@ -25,6 +25,21 @@ def test_build_csr_csc_bit_exact(gpu, port, rows, cols, nnz):
         assert np.array_equal(got, want)
 
 
+def test_build_wide_minor_dimension_and_duplicates(gpu, port):
+    """A minor dimension wider than one shared-memory bitmap (> ~928 K keys: the Yahoo-Music shape's 1 000 990 rows on the
+    CSC build) is ranked in several windows of the key range; a duplicate (row, col) pair is refused."""
+    rng = np.random.default_rng(11)
+    rows, cols, nnz = 2_100_000, 37, 60_000
+    r, c, v = _random_coo(rng, rows, cols, nnz)
+    csr, csc = gpu.build_csr_csc(rows, cols, r, c, v)
+    wcsr, wcsc = port.coo_to_csr_csc(rows, cols, r, c, v)
+    for got, want in zip(csr + csc, wcsr + wcsc):
+        assert np.array_equal(got, want)
+    r2, c2, v2 = np.concatenate([r, r[:1]]), np.concatenate([c, c[:1]]), np.concatenate([v, v[:1]])
+    with pytest.raises(gpu.MFError, match="more than once"):
+        gpu.build_csr_csc(rows, cols, r2, c2, v2)
+
+
 def test_degree_bins_and_partition_bit_exact(gpu, port, data_factory):
     d = data_factory("ml100k")
     for ptr in (d["csr_ptr"], d["csc_ptr"]):
