@@ -69,3 +69,17 @@ def test_product_never_imports_oracle():
                 assert "libmforacle" not in text and "libmfref" not in text, f
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
                 assert not re.search(r'#include\s+"[^"]*oracle/', text), f
+
+
+def test_extension_fields_sit_behind_the_reference_fields(pkg):
+    """mf_params keeps the reference's `parameter` fields first (src/pmf.h:10-24) and the extensions behind them; early_stop
+    took one of the reserved words (the struct size did not change between ABI versions 2 and 3)."""
+    names = [n for n, _ in pkg.mf_params._fields_]
+    assert names[:12] == ["solver_type", "k", "threads", "maxiter", "maxinneriter", "lambda_", "eps", "do_predict", "verbose",
+                          "do_nmf", "nBlocks", "nThreadsPerBlock"]
+    assert names.index("early_stop") == names.index("pad_entries") + 1 and names[-1] == "reserved"
+    p = pkg.make_params(k=3, eps=0.25, early_stop=1, do_nmf=1, verbose=1, do_predict=1)
+    assert (p.early_stop, p.do_nmf, p.verbose, p.do_predict) == (1, 1, 1, 1) and p.eps == pytest.approx(0.25)
+    q = pkg.mf_params()
+    pkg.lib().mf_params_default(C.byref(q))
+    assert q.early_stop == 0 and q.nmf_project == 0  # inert by default, exactly like the reference

@@ -44,3 +44,25 @@ def test_loader_reads_the_dataset_directory(cli, datagen, data_factory, tmp_path
 def test_missing_dataset_fails_loudly(cli, tmp_path):
     r = _run([cli, "-k", "3", str(tmp_path / "nope")])
     assert r.returncode != 0
+
+
+def test_usage_lists_the_round2_flags(cli):
+    out = _run([cli]).stdout
+    for text in ("-load", "-save", "-e switches the stop rule on"):
+        assert text in out, text
+
+
+def test_load_without_a_model_fails_loudly(cli, datagen, data_factory, tmp_path):
+    """-load is the predict-only path (the reference's calculate_rmse_from_file): no model file -> an error, nothing computed."""
+    datagen.write_dataset(str(tmp_path), data_factory("tiny"))
+    r = _run([cli, "-load", str(tmp_path)])
+    assert r.returncode != 0 and "can't open model file" in r.stdout
+    assert not os.path.exists(os.path.join(str(tmp_path), "output"))
+
+
+def test_load_rejects_a_truncated_model(cli, datagen, data_factory, tmp_path):
+    datagen.write_dataset(str(tmp_path), data_factory("tiny"))
+    with open(os.path.join(str(tmp_path), "model"), "wb") as f:
+        f.write(b"\x05\x00\x00\x00")
+    r = _run([cli, "-load", str(tmp_path)])
+    assert r.returncode != 0
