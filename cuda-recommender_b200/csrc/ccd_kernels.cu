@@ -1588,13 +1588,27 @@ int launch_panel_v(const PanelSweepArgs& a, int ncta, int threads, size_t smem, 
         MF_CUDA(cudaFuncSetAttribute(k_panel_sweep<MODE, SHORT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 256));
     }
     static const bool pdl = getenv("MF_NO_PDL") == nullptr;
-    if (pdl) {
+    // MF_COOP_LAUNCH=1: the sweeps that end in the in-kernel finalize (grid barrier) are launched cooperatively, so that the
+    // driver itself guarantees — or refuses — the co-residency of the grid instead of the occupancy check at session
+    // creation plus the bounded wait.  Opt-in: see profiles/README.md for what it costs.
+    static const bool coop = getenv("MF_COOP_LAUNCH") != nullptr && atoi(getenv("MF_COOP_LAUNCH")) != 0;
+    const bool want_coop = coop && a.fin.enabled;
+    if (pdl || want_coop) {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)ncta); cfg.blockDim = dim3((unsigned)threads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        at[0].val.programmaticStreamSerializationAllowed = 1;
-        cfg.attrs = at; cfg.numAttrs = 1;
+        cudaLaunchAttribute at[2];
+        unsigned n = 0;
+        if (pdl && !want_coop) {  // (a cooperative grid starts only when all of it fits: nothing to overlap with its predecessor)
+            at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            at[n].val.programmaticStreamSerializationAllowed = 1;
+            ++n;
+        }
+        if (want_coop) {
+            at[n].id = cudaLaunchAttributeCooperative;
+            at[n].val.cooperative = 1;
+            ++n;
+        }
+        cfg.attrs = at; cfg.numAttrs = n;
         MF_CUDA(cudaLaunchKernelEx(&cfg, k_panel_sweep<MODE, SHORT>, a));
     } else {
         k_panel_sweep<MODE, SHORT><<<ncta, threads, smem, st>>>(a);
