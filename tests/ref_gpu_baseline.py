@@ -4,7 +4,8 @@ reference's on-disk format (so the rating arrays are the loader's ordinary pagea
   * oracle/_ref/cuda_andre_refgpu  — the reference's own CUDA path (cuda_src/*.cu) rebuilt for sm_100a: GPU vs GPU
   * oracle/_ref/cuda_andre_dropin  — the same main.cpp linked against this repo's shim + libmfb200.so
 Prints one JSON line with the per-iteration times each binary reports and its "CUDA Training time".
-Usage: scripts/ref_gpu_baseline.py [shape=netflix] [k=40] [outer=3] [inner=3]"""
+Test infrastructure (it executes binaries under oracle/_ref): kept under tests/.
+Usage: tests/ref_gpu_baseline.py [shape=netflix] [k=40] [outer=3] [inner=3]"""
 import json
 import os
 import re
@@ -13,7 +14,7 @@ import sys
 import tempfile
 import time
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))  # tests/ -> repo root
 sys.path.insert(0, ROOT)
 from __graft_entry__ import load_package  # noqa: E402
 
